@@ -1,0 +1,92 @@
+"""The hot path as an object: per-view fused back-projection into resident (num, den)
+accumulators -- the loop body of `create_feature_field_lseg` / `_dino`
+(backproject.py:74-165, 214-289) and of `backproject_compressed.py:90-179`, minus the 2-D encoder.
+
+Reference, per view:  3 x rasterization() + 2 x backward() + clone/zero_/+= over dense [N,D]
+Here, per view:       1 x (project + bin + sort)  +  1 fused composite/contract/accumulate kernel
+
+    bp = BackProjector(means, quats, scales, opacities, feature_dim=512)
+    for viewmat, feats in views:            # feats [H,W,D] fp32 CUDA, any strides
+        bp.add_view(viewmat, K, width, height, feats)
+    features = bp.finalize()                # == create_feature_field_lseg(...) return value
+
+`raw()` exposes (num, den) for the multi-GPU all-reduce (dist.py); `prune_mask()` is
+`prune_by_gradients` (utils.py:222-271) for free: a Gaussian survives iff den received weight.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from .engine import PackedScene, View, finalize as _finalize, fpack_bytes, make_camera
+
+DEN_EPS = 1e-12  # backproject.py:63
+
+
+class BackProjector:
+    def __init__(self, means, quats, scales, opacities, feature_dim: int, device=None, kernel: str = "auto",
+                 cap_isects: Optional[int] = None, collect_stats: bool = False):
+        self.scene = PackedScene(means, quats, scales, opacities, device)
+        self.device = self.scene.device
+        self.d = int(feature_dim)
+        n = self.scene.n
+        self.num = torch.zeros(n, self.d, dtype=torch.float32, device=self.device)       # backproject.py:62
+        self.den = torch.full((n,), DEN_EPS, dtype=torch.float32, device=self.device)    # backproject.py:63
+        self.kernel = {"auto": L.KERNEL_AUTO, "simt": L.KERNEL_SIMT, "tc": L.KERNEL_TC}[kernel]
+        self.cap = cap_isects
+        self._ws: Optional[torch.Tensor] = None
+        self._fpack: Optional[torch.Tensor] = None
+        self._stats = torch.zeros(4, dtype=torch.int64, device=self.device) if collect_stats else None
+        self.n_views = 0
+        self.last_view: Optional[View] = None
+
+    # -- one view -------------------------------------------------------------------------
+    def add_view(self, viewmat, K, width, height, feats: torch.Tensor, **cam_kw) -> View:
+        assert feats.shape[-1] == self.d, f"feature dim {feats.shape[-1]} != {self.d}"
+        cam = make_camera(viewmat, K, width, height, **cam_kw)
+        view = View(self.scene, cam, self.cap, self._ws)
+        self._ws, self.cap = view.ws, view.cap  # keep (possibly grown) workspace for the next view
+        fp = None
+        if self.kernel != L.KERNEL_SIMT:
+            need = fpack_bytes(cam.width, cam.height, self.d)
+            if need:
+                if self._fpack is None or self._fpack.numel() < need:
+                    self._fpack = torch.empty(need, dtype=torch.uint8, device=self.device)
+                fp = self._fpack
+            elif self.kernel == L.KERNEL_TC:
+                raise RuntimeError(f"tcgen05 kernel does not support D={self.d}")
+        view.backproject(feats, self.num, self.den, self.kernel, fp, self._stats)
+        self.n_views += 1
+        self.last_view = view
+        return view
+
+    # -- results --------------------------------------------------------------------------
+    def raw(self):
+        """(num [N,D], den [N]) -- den includes the reference's 1e-12 initial value."""
+        return self.num, self.den
+
+    def stats(self) -> dict:
+        if self._stats is None:
+            return {}
+        s = self._stats.tolist()
+        return {"rows_nonzero": s[0], "entries_walked": s[1]}
+
+    def prune_mask(self) -> torch.Tensor:
+        """== `gaussian_grads > 0` of prune_by_gradients (utils.py:257)."""
+        return self.den > DEN_EPS
+
+    def finalize(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """backproject.py:166-169."""
+        return _finalize(self.num, self.den, out)
+
+
+def create_feature_field(means, quats, scales, opacities, K, width, height, views, feature_dim: int, **kw):
+    """Functional mirror of `create_feature_field_lseg(splats)` with the encoder factored out:
+    `views` yields (viewmat[4,4], feats[H,W,D]).  Returns the normalised [N,D] tensor that the
+    reference saves as features_*.pt (backproject.py:330)."""
+    bp = BackProjector(means, quats, scales, opacities, feature_dim, **kw)
+    for viewmat, feats in views:
+        bp.add_view(viewmat, K, width, height, feats)
+    return bp.finalize()

@@ -1,0 +1,190 @@
+// extern "C" surface of libgwbp.so (see include/gwbp.h for the contract and the reference
+// call sites each entry point replaces).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gwbp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+static int tile_bits_for(int n_tiles) {
+    int b = 1;
+    while ((1 << b) <= n_tiles) ++b;  // floor(log2(n_tiles)) + 1, as gsplat
+    return b;
+}
+
+static int check_cam(const gwbp_camera *c) {
+    GWBP_REQUIRE(c != nullptr, "camera is NULL");
+    GWBP_REQUIRE(c->width > 0 && c->height > 0, "width/height must be positive (got %d x %d)", c->width, c->height);
+    GWBP_REQUIRE(c->width <= 65536 && c->height <= 65536, "image too large (%d x %d)", c->width, c->height);
+    GWBP_REQUIRE(c->K[0] > 0.0f && c->K[4] > 0.0f, "focal lengths must be positive");
+    return 0;
+}
+
+static TileCtx tile_ctx(const gwbp_camera *cam, const void *ws, const gwbp_ws_layout &L, const gwbp_view_info *info) {
+    WsDev w = ws_view(const_cast<void *>(ws), L);
+    TileCtx t;
+    t.grec = w.grec;
+    t.flatten = w.vals[info->sorted_buf];
+    t.offsets = w.offsets;
+    t.W = cam->width; t.H = cam->height;
+    t.tw = info->tile_w; t.th = info->tile_h;
+    return t;
+}
+
+}  // namespace gwbp
+
+using namespace gwbp;
+
+extern "C" {
+
+int gwbp_abi_version(void) { return GWBP_ABI_VERSION; }
+
+const char *gwbp_last_error(void) { return g_err; }
+
+int gwbp_workspace_layout(int64_t n, int32_t width, int32_t height, int64_t cap, gwbp_ws_layout *L) {
+    GWBP_REQUIRE(L != nullptr, "layout pointer is NULL");
+    GWBP_REQUIRE(n >= 0 && n < (1ll << 31) - 1, "n out of range (%lld)", (long long)n);
+    GWBP_REQUIRE(width > 0 && height > 0, "width/height must be positive");
+    GWBP_REQUIRE(cap >= 0 && cap < (1ll << 31), "cap_isects out of range (%lld)", (long long)cap);
+    const int64_t tiles = (int64_t)((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
+    const int64_t n1 = n + 1, c1 = cap > 0 ? cap : 1;
+    size_t o = 0;
+    memset(L, 0, sizeof(*L));
+    L->cnt = o; o = align_up(o + sizeof(unsigned long long) * n1);
+    L->scan = o; o = align_up(o + sizeof(unsigned long long) * n1);
+    L->rec = o; o = align_up(o + sizeof(float4) * 2 * n1);
+    L->grec = o; o = align_up(o + sizeof(float4) * 2 * n1);
+    L->radii = o; o = align_up(o + sizeof(int) * n1);
+    L->tiles_per_gauss = o; o = align_up(o + sizeof(int) * n1);
+    L->keys0 = o; o = align_up(o + sizeof(long long) * c1);
+    L->keys1 = o; o = align_up(o + sizeof(long long) * c1);
+    L->vals0 = o; o = align_up(o + sizeof(int) * c1);
+    L->vals1 = o; o = align_up(o + sizeof(int) * c1);
+    L->offsets = o; o = align_up(o + sizeof(int) * (tiles + 1));
+    L->stats = o; o = align_up(o + sizeof(long long) * 16);
+    L->cub_tmp_bytes = binning_tmp_bytes(n, c1);
+    L->cub_tmp = o; o = align_up(o + L->cub_tmp_bytes);
+    L->total = o;
+    return 0;
+}
+
+int gwbp_pack_scene(int64_t n, const float *means, const float *quats, const float *scales,
+                    const float *opacities, void *geo, void *stream) {
+    GWBP_REQUIRE(n >= 0, "n must be >= 0");
+    if (n == 0) return 0;
+    GWBP_REQUIRE(means && quats && scales && opacities && geo, "pack_scene: NULL pointer");
+    GWBP_REQUIRE(((uintptr_t)quats & 15) == 0 && ((uintptr_t)geo & 15) == 0, "quats/geo must be 16-byte aligned");
+    return launch_pack_scene(n, means, quats, scales, opacities, geo, (cudaStream_t)stream);
+}
+
+int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws, size_t ws_bytes, int64_t cap,
+                      void *stream, gwbp_view_info *info) {
+    GWBP_REQUIRE(scene && ws && info, "view_prepare: NULL pointer");
+    if (int rc = check_cam(cam)) return rc;
+    gwbp_ws_layout L;
+    if (int rc = gwbp_workspace_layout(scene->n, cam->width, cam->height, cap, &L)) return rc;
+    GWBP_REQUIRE(ws_bytes >= L.total, "workspace too small: %zu < %zu", ws_bytes, L.total);
+    GWBP_REQUIRE(scene->n == 0 || scene->geo, "scene.geo is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    WsDev w = ws_view(ws, L);
+    const CamDev cd = make_cam(*cam);
+    const int64_t n = scene->n;
+    memset(info, 0, sizeof(*info));
+    info->tile_w = cd.tw; info->tile_h = cd.th;
+    info->cap_isects = cap;
+
+    if (int rc = launch_project(n, scene->geo, cd, w, st)) return rc;
+    if (int rc = launch_scan(n, w, st)) return rc;
+    unsigned long long totals = 0;
+    GWBP_CUDA_OK(cudaMemcpyAsync(&totals, w.scan + n, sizeof(totals), cudaMemcpyDeviceToHost, st));
+    GWBP_CUDA_OK(cudaStreamSynchronize(st));
+    info->n_vis = (int64_t)(totals >> 32);
+    info->n_isects = (int64_t)(totals & 0xffffffffull);
+    if (info->n_isects > cap) {
+        set_error("intersection capacity exceeded: need %lld, workspace sized for %lld",
+                  (long long)info->n_isects, (long long)cap);
+        return -2;
+    }
+    if (int rc = launch_emit(n, cd, w, cap, st)) return rc;
+    int sorted = 0;
+    if (int rc = launch_sort(info->n_isects, tile_bits_for(cd.tw * cd.th), w, &sorted, st)) return rc;
+    info->sorted_buf = sorted;
+    return launch_offsets(info->n_isects, cd.tw * cd.th, w.keys[sorted], w.offsets, st);
+}
+
+size_t gwbp_fpack_bytes(int32_t width, int32_t height, int32_t d) {
+    if (width <= 0 || height <= 0 || !tc_supported(d)) return 0;
+    return fpack_bytes(width, height, d);
+}
+
+int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws,
+                          const gwbp_view_info *info, const float *F, int64_t sH, int64_t sW, int64_t sD, int32_t d,
+                          float *num, float *den, int32_t kernel, void *fpack, int64_t *stats, void *stream) {
+    GWBP_REQUIRE(scene && ws && info && F && num && den, "backproject_view: NULL pointer");
+    if (int rc = check_cam(cam)) return rc;
+    GWBP_REQUIRE(d >= 1, "feature dimension must be >= 1 (got %d)", d);
+    gwbp_ws_layout L;
+    if (int rc = gwbp_workspace_layout(scene->n, cam->width, cam->height, info->cap_isects, &L)) return rc;
+    const TileCtx t = tile_ctx(cam, ws, L, info);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (info->n_isects == 0) return 0;
+    int k = kernel;
+    if (k == GWBP_KERNEL_AUTO) k = (tc_supported(d) && fpack) ? GWBP_KERNEL_TC : GWBP_KERNEL_SIMT;
+    if (k == GWBP_KERNEL_TC) {
+        GWBP_REQUIRE(tc_supported(d), "tcgen05 back-projection does not support D=%d", d);
+        GWBP_REQUIRE(fpack != nullptr, "tcgen05 back-projection needs the fpack buffer (gwbp_fpack_bytes)");
+        return launch_backproject_tc(t, F, sH, sW, sD, d, num, den, fpack, (long long *)stats, st);
+    }
+    GWBP_REQUIRE(k == GWBP_KERNEL_SIMT, "unknown kernel id %d", kernel);
+    return launch_backproject_simt(t, F, sH, sW, sD, d, num, den, (long long *)stats, st);
+}
+
+int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws, const gwbp_view_info *info,
+                     const float *colors, int64_t color_stride, int32_t d, const float *background, float *render,
+                     float *alpha, void *stream) {
+    GWBP_REQUIRE(scene && ws && info && colors && render, "render_view: NULL pointer");
+    if (int rc = check_cam(cam)) return rc;
+    GWBP_REQUIRE(d >= 1, "channel count must be >= 1 (got %d)", d);
+    GWBP_REQUIRE(color_stride >= d, "color_stride (%lld) < d (%d)", (long long)color_stride, d);
+    gwbp_ws_layout L;
+    if (int rc = gwbp_workspace_layout(scene->n, cam->width, cam->height, info->cap_isects, &L)) return rc;
+    const TileCtx t = tile_ctx(cam, ws, L, info);
+    return launch_render_simt(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream);
+}
+
+int gwbp_finalize(const float *num, const float *den, float *out, int64_t n, int32_t d, void *stream) {
+    GWBP_REQUIRE(n >= 0 && d >= 1, "finalize: bad shape");
+    if (n == 0) return 0;
+    GWBP_REQUIRE(num && den && out, "finalize: NULL pointer");
+    return launch_finalize(num, den, out, n, d, (cudaStream_t)stream);
+}
+
+int gwbp_mask3d(const float *x, int64_t rows, int32_t d, const float *text, int32_t p, int32_t npos, float threshold,
+                int32_t use_threshold, uint8_t *mask, float *score, void *stream) {
+    GWBP_REQUIRE(rows >= 0 && d >= 1, "mask3d: bad shape");
+    if (rows == 0) return 0;
+    GWBP_REQUIRE(x && text && mask, "mask3d: NULL pointer");
+    return launch_mask(x, rows, d, text, p, npos, threshold, use_threshold, mask, score, (cudaStream_t)stream);
+}
+
+int gwbp_mask2d(const float *render, int64_t pixels, int32_t d, const float *text, int32_t p, int32_t npos,
+                uint8_t *mask, void *stream) {
+    GWBP_REQUIRE(pixels >= 0 && d >= 1, "mask2d: bad shape");
+    if (pixels == 0) return 0;
+    GWBP_REQUIRE(render && text && mask, "mask2d: NULL pointer");
+    return launch_mask(render, pixels, d, text, p, npos, 0.0f, 0, mask, nullptr, (cudaStream_t)stream);
+}
+
+}  // extern "C"

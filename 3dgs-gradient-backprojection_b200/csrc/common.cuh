@@ -1,0 +1,136 @@
+// Shared declarations for libgwbp.so (sm_100a only).  See include/gwbp.h for the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gwbp.h"
+
+namespace gwbp {
+
+constexpr int kTile = GWBP_TILE;
+constexpr int kTilePix = kTile * kTile;
+constexpr float kAlphaMin = 1.0f / 255.0f;
+constexpr float kAlphaMax = 0.999f;
+constexpr float kTMin = 1e-4f;
+constexpr int kNumSMs = 148;  // B200
+
+// thread-local error string behind gwbp_last_error()
+void set_error(const char *fmt, ...);
+
+#define GWBP_CUDA_OK(expr)                                                              \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            ::gwbp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                              __FILE__, __LINE__);                                      \
+            return (int)_e;                                                             \
+        }                                                                               \
+    } while (0)
+
+#define GWBP_REQUIRE(cond, ...)             \
+    do {                                    \
+        if (!(cond)) {                      \
+            ::gwbp::set_error(__VA_ARGS__); \
+            return -1;                      \
+        }                                   \
+    } while (0)
+
+// Camera constants precomputed on the host in the oracle's evaluation order (fp32, no FMA).
+struct CamDev {
+    float V[12];  // rows 0..2 of the world->camera matrix
+    float fx, fy, cx, cy;
+    float Wf, Hf;
+    float lim_xp, lim_xn, lim_yp, lim_yn;
+    float near_plane, far_plane, radius_clip, eps2d;
+    int W, H, tw, th;
+};
+
+// Typed view of the caller's workspace.
+struct WsDev {
+    unsigned long long *cnt, *scan;
+    float4 *rec, *grec;
+    int *radii, *tiles_per_gauss;
+    long long *keys[2];
+    int *vals[2];
+    int *offsets;
+    long long *stats;
+    void *cub_tmp;
+    size_t cub_tmp_bytes;
+};
+
+inline WsDev ws_view(void *base, const gwbp_ws_layout &L) {
+    char *b = (char *)base;
+    WsDev w;
+    w.cnt = (unsigned long long *)(b + L.cnt);
+    w.scan = (unsigned long long *)(b + L.scan);
+    w.rec = (float4 *)(b + L.rec);
+    w.grec = (float4 *)(b + L.grec);
+    w.radii = (int *)(b + L.radii);
+    w.tiles_per_gauss = (int *)(b + L.tiles_per_gauss);
+    w.keys[0] = (long long *)(b + L.keys0);
+    w.keys[1] = (long long *)(b + L.keys1);
+    w.vals[0] = (int *)(b + L.vals0);
+    w.vals[1] = (int *)(b + L.vals1);
+    w.offsets = (int *)(b + L.offsets);
+    w.stats = (long long *)(b + L.stats);
+    w.cub_tmp = (void *)(b + L.cub_tmp);
+    w.cub_tmp_bytes = L.cub_tmp_bytes;
+    return w;
+}
+
+CamDev make_cam(const gwbp_camera &c);
+
+// ---- stage launchers (one per .cu) -------------------------------------------------------
+int launch_pack_scene(int64_t n, const float *means, const float *quats, const float *scales,
+                      const float *opac, void *geo, cudaStream_t st);
+int launch_project(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cudaStream_t st);
+int launch_emit(int64_t n, const CamDev &cam, WsDev ws, int64_t cap, cudaStream_t st);
+size_t binning_tmp_bytes(int64_t n, int64_t cap);
+int launch_scan(int64_t n, WsDev ws, cudaStream_t st);
+int launch_sort(int64_t n_isects, int tile_bits, WsDev ws, int *sorted_buf, cudaStream_t st);
+int launch_offsets(int64_t n_isects, int n_tiles, const long long *keys, int *offsets, cudaStream_t st);
+
+struct TileCtx {
+    const float4 *grec;
+    const int *flatten;
+    const int *offsets;
+    int W, H, tw, th;
+};
+
+int launch_backproject_simt(const TileCtx &t, const float *F, int64_t sH, int64_t sW, int64_t sD, int d,
+                            float *num, float *den, long long *stats, cudaStream_t st);
+int launch_render_simt(const TileCtx &t, const float *colors, int64_t cstride, int d, const float *bg,
+                       float *render, float *alpha, cudaStream_t st);
+int launch_finalize(const float *num, const float *den, float *out, int64_t n, int d, cudaStream_t st);
+int launch_mask(const float *x, int64_t rows, int d, const float *text, int p, int npos, float thr,
+                int use_thr, uint8_t *mask, float *score, cudaStream_t st);
+
+// tcgen05 path (backproject_tc.cu)
+size_t fpack_bytes(int W, int H, int d);
+bool tc_supported(int d);
+int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t sW, int64_t sD, int d,
+                          float *num, float *den, void *fpack, long long *stats, cudaStream_t st);
+
+// ---- device helpers ------------------------------------------------------------------------
+// One Gaussian against one pixel, gsplat rasterize_to_pixels_fwd semantics.
+// Returns the weight alpha*T (0 if skipped) and updates T / done.
+__device__ __forceinline__ float composite_step(float gx, float gy, float op, float cxx, float cxy,
+                                                float cyy, float px, float py, float &T, bool &done) {
+    const float dx = gx - px, dy = gy - py;
+    const float sigma = 0.5f * (cxx * dx * dx + cyy * dy * dy) + cxy * dx * dy;
+    const float alpha = fminf(kAlphaMax, op * __expf(-sigma));
+    float w = 0.0f;
+    if (!done && sigma >= 0.0f && alpha >= kAlphaMin) {
+        const float nT = T * (1.0f - alpha);
+        if (nT <= kTMin) {
+            done = true;
+        } else {
+            w = alpha * T;
+            T = nT;
+        }
+    }
+    return w;
+}
+
+}  // namespace gwbp

@@ -1,0 +1,98 @@
+// Dense [rows, D] passes of the path, each fused into ONE HBM-bound kernel:
+//   finalize : f = num/den; f /= ||f||; NaN -> 0          (backproject.py:166-169: 3 passes + temporaries)
+//   mask     : normalise(x) @ normalise(text).T, max(pos) > max(neg) [, score0 > thr]
+//              (segment.py:52-58 for Gaussians, segment.py:221-224 for rendered pixels)
+// One warp per row, float4 loads when D % 4 == 0.
+#include "common.cuh"
+
+namespace gwbp {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(const float *__restrict__ num, const float *__restrict__ den,
+                                                       float *__restrict__ out, int64_t n, int d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float dn = den[row];
+    const float *src = num + row * d;
+    float *dst = out + row * d;
+    float ss = 0.0f;
+    for (int j = lane; j < d; j += 32) {
+        const float q = src[j] / dn;
+        ss += q * q;
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    for (int j = lane; j < d; j += 32) {
+        float v = (src[j] / dn) / nrm;
+        if (isnan(v)) v = 0.0f;
+        dst[j] = v;
+    }
+}
+
+int launch_finalize(const float *num, const float *den, float *out, int64_t n, int d, cudaStream_t st) {
+    if (n == 0 || d == 0) return 0;
+    finalize_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(num, den, out, n, d);
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// text [p, d] is staged (normalised) in shared memory; p*d*4 bytes must fit (checked on the host)
+__global__ void __launch_bounds__(256) mask_kernel(const float *__restrict__ x, int64_t rows, int d,
+                                                   const float *__restrict__ text, int p, int npos, float thr,
+                                                   int use_thr, uint8_t *__restrict__ mask,
+                                                   float *__restrict__ score) {
+    extern __shared__ float stext[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < p; j += nwarps) {
+        float ss = 0.0f;
+        for (int k = lane; k < d; k += 32) { const float v = text[(int64_t)j * d + k]; ss += v * v; }
+        ss = warp_sum(ss);
+        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        for (int k = lane; k < d; k += 32) stext[j * d + k] = text[(int64_t)j * d + k] * inv;
+    }
+    __syncthreads();
+    for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < rows; row += (int64_t)gridDim.x * nwarps) {
+        const float *src = x + row * d;
+        float ss = 0.0f;
+        for (int k = lane; k < d; k += 32) { const float v = src[k]; ss += v * v; }
+        ss = warp_sum(ss);
+        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        float best_pos = -INFINITY, best_neg = -INFINITY, s0 = 0.0f;
+        for (int j = 0; j < p; ++j) {
+            float dot = 0.0f;
+            for (int k = lane; k < d; k += 32) dot += (src[k] * inv) * stext[j * d + k];
+            dot = warp_sum(dot);
+            if (j == 0) s0 = dot;
+            if (j < npos) best_pos = fmaxf(best_pos, dot); else best_neg = fmaxf(best_neg, dot);
+            if (score && lane == 0) score[row * p + j] = dot;
+        }
+        if (lane == 0) {
+            bool m = best_pos > best_neg;
+            if (use_thr) m = m && (s0 > thr);
+            mask[row] = m ? 1 : 0;
+        }
+    }
+}
+
+int launch_mask(const float *x, int64_t rows, int d, const float *text, int p, int npos, float thr, int use_thr,
+                uint8_t *mask, float *score, cudaStream_t st) {
+    if (rows == 0) return 0;
+    const size_t smem = (size_t)p * d * sizeof(float);
+    GWBP_REQUIRE(p >= 1 && npos >= 1 && npos <= p, "mask: need 1 <= npos <= p (npos=%d p=%d)", npos, p);
+    GWBP_REQUIRE(smem <= 200 * 1024, "mask: %d prompts x %d dims do not fit in shared memory", p, d);
+    if (smem > 48 * 1024)
+        GWBP_CUDA_OK(cudaFuncSetAttribute(mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    mask_kernel<<<(unsigned)blocks, 256, smem, st>>>(x, rows, d, text, p, npos, thr, use_thr, mask, score);
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace gwbp

@@ -1,0 +1,132 @@
+/* gwbp -- gradient-weighted feature back-projection for 3D Gaussian splats, B200 (sm_100a).
+ *
+ * C ABI of lib/libgwbp.so.  This is the drop-in boundary for ONE path of
+ * JojiJoseph/3dgs-gradient-backprojection: everything `create_feature_field_lseg`
+ * (backproject.py:25-172) asks of `gsplat.rasterization` + autograd, and the forward feature
+ * render / cosine query of segment.py:26-61,209-224.  Plain pointers and sizes only; every
+ * pointer is a DEVICE pointer unless the name says `_host`.  The library never allocates
+ * caller-visible memory: the caller sizes one workspace with gwbp_workspace_layout() and owns it.
+ *
+ * Return value of every int function: 0 = ok, <0 = bad argument / capacity, >0 = cudaError_t.
+ * gwbp_last_error() returns a thread-local description of the last failure.
+ * A handle-free design: all per-view state lives in the caller's workspace, so one workspace
+ * per (device, stream); functions are not thread-safe on the same workspace.
+ *
+ * Reference interface each entry point replaces (file:line in the reference repo; gsplat-1.4.0
+ * internals per SURVEY.md §9):
+ *   gwbp_pack_scene ........ quat/scale -> covariance part of fully_fused_projection
+ *                            (called inside rasterization(): backproject.py:89,115,133)
+ *   gwbp_view_prepare ...... fully_fused_projection(packed) + isect_tiles + radix sort +
+ *                            isect_offset_encode of ONE rasterization() call
+ *   gwbp_backproject_view .. rasterize_to_pixels backward w.r.t. colors driven by
+ *                            `(render*feats).sum().backward()` and `render.sum().backward()`
+ *                            (backproject.py:127-131,145-151) INCLUDING the accumulation
+ *                            `gaussian_features += grad; gaussian_denoms += grad0[:,0]` (:149-150)
+ *   gwbp_render_view ....... rasterize_to_pixels forward for D-channel colours (segment.py:209-220)
+ *   gwbp_finalize .......... backproject.py:166-169
+ *   gwbp_mask3d ............ segment.py:52-58
+ *   gwbp_mask2d ............ segment.py:221-224
+ */
+#ifndef GWBP_H
+#define GWBP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GWBP_TILE 16
+#define GWBP_ABI_VERSION 1
+
+/* kernel selection for gwbp_backproject_view */
+#define GWBP_KERNEL_AUTO 0
+#define GWBP_KERNEL_SIMT 1 /* fp32 CUDA-core contraction (truth kernel, any D) */
+#define GWBP_KERNEL_TC 2   /* tcgen05 split-bf16 contraction, fp32 TMEM accumulation */
+
+typedef struct gwbp_scene {
+    int64_t n;        /* Gaussians */
+    const void *geo;  /* 40*n bytes written by gwbp_pack_scene: float4 (mean.xyz, opacity)[n],
+                         float4 (c00,c01,c02,c11)[n], float2 (c12,c22)[n] */
+} gwbp_scene;
+
+typedef struct gwbp_camera {
+    float viewmat[16]; /* row-major world->camera, as get_viewmat_from_colmap_image (utils.py:215-219) */
+    float K[9];        /* row-major intrinsics */
+    int32_t width, height;
+    float near_plane, far_plane, radius_clip, eps2d; /* gsplat defaults 0.01, 1e10, 0.0, 0.3 */
+} gwbp_camera;
+
+/* byte offsets of every stage output inside the caller's workspace */
+typedef struct gwbp_ws_layout {
+    size_t total;
+    size_t cnt;       /* uint64 [n+1]   (visible<<32 | tiles) per Gaussian */
+    size_t scan;      /* uint64 [n+1]   exclusive prefix of cnt */
+    size_t rec;       /* float4 [2*n]   unpacked projection records */
+    size_t grec;      /* float4 [2*n]   packed records: (mean2d.xy, opacity, gaussian_id bits), (conic.xyz, depth) */
+    size_t radii;     /* int32  [n]     packed radii */
+    size_t tiles_per_gauss; /* int32 [n] packed */
+    size_t keys0, keys1;    /* int64 [cap]  isect_ids double buffer */
+    size_t vals0, vals1;    /* int32 [cap]  flatten_ids double buffer */
+    size_t offsets;   /* int32  [tiles+1] isect_offsets (+ terminator = n_isects) */
+    size_t stats;     /* int64  [16]    device counters */
+    size_t cub_tmp;   /* scratch for scan / sort */
+    size_t cub_tmp_bytes;
+} gwbp_ws_layout;
+
+typedef struct gwbp_view_info {
+    int64_t n_vis, n_isects;
+    int64_t cap_isects; /* the capacity the workspace layout was computed with */
+    int32_t tile_w, tile_h;
+    int32_t sorted_buf; /* which of keys0/keys1, vals0/vals1 holds the sorted result */
+    int32_t reserved;
+} gwbp_view_info;
+
+/* counters filled by gwbp_backproject_view when `stats` != NULL (device int64[4]):
+ * [0] rows with non-zero weight  [1] (tile,Gaussian) entries walked  [2],[3] reserved */
+
+int gwbp_abi_version(void);
+const char *gwbp_last_error(void);
+
+int gwbp_workspace_layout(int64_t n, int32_t width, int32_t height, int64_t cap_isects, gwbp_ws_layout *out_host);
+
+/* means [n,3], quats [n,4] wxyz un-normalised, scales [n,3] linear, opacities [n] -> geo (40*n bytes) */
+int gwbp_pack_scene(int64_t n, const float *means, const float *quats, const float *scales,
+                    const float *opacities, void *geo, void *stream);
+
+/* project + bin + sort one camera into `ws`.  Synchronises `stream` once (intersection count). */
+int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam_host, void *ws, size_t ws_bytes,
+                      int64_t cap_isects, void *stream, gwbp_view_info *info_host);
+
+/* bytes of the packed bf16 feature buffer the GWBP_KERNEL_TC path needs (0 if D unsupported) */
+size_t gwbp_fpack_bytes(int32_t width, int32_t height, int32_t d);
+
+/* num[n,d] += sum_p w(g,p) F[p,:]; den[n] += sum_p w(g,p) for the prepared view.
+ * F: fp32, element strides (sH,sW,sD) -- both [H,W,D]-contiguous and the reference's permuted
+ * [D,H,W] view (backproject.py:113) are accepted as they are. */
+int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam_host, const void *ws,
+                          const gwbp_view_info *info_host, const float *F, int64_t sH, int64_t sW, int64_t sD,
+                          int32_t d, float *num, float *den, int32_t kernel, void *fpack, int64_t *stats,
+                          void *stream);
+
+/* render[H,W,d] = sum_g w(g,p) colors[g,:] (+ (1-alpha) background), alpha[H,W] = 1-T */
+int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam_host, const void *ws,
+                     const gwbp_view_info *info_host, const float *colors, int64_t color_stride, int32_t d,
+                     const float *background, float *render, float *alpha, void *stream);
+
+/* out[g,:] = normalise(num[g,:]/den[g]); NaN -> 0   (backproject.py:166-169); out may alias num */
+int gwbp_finalize(const float *num, const float *den, float *out, int64_t n, int32_t d, void *stream);
+
+/* mask[i] = max_{j<npos} s_ij > max_{j>=npos} s_ij (and s_i0 > threshold if use_threshold),
+ * s = normalise(x_i) . normalise(text_j).  x [rows,d] contiguous, text [p,d]; score [rows,p] optional */
+int gwbp_mask3d(const float *x, int64_t rows, int32_t d, const float *text, int32_t p, int32_t npos,
+                float threshold, int32_t use_threshold, uint8_t *mask, float *score, void *stream);
+/* same compare for rendered pixels (segment.py:221-224); no threshold */
+int gwbp_mask2d(const float *render, int64_t pixels, int32_t d, const float *text, int32_t p, int32_t npos,
+                uint8_t *mask, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWBP_H */

@@ -1,0 +1,190 @@
+"""CPU tests: the oracle against itself (numpy restatement vs threaded C restatement), against the
+algebraic invariants of SURVEY.md §4, and against the committed golden fixtures.
+
+There are no reference-owned golden vectors for this path (gsplat is un-vendored, the repo has no
+tests: SURVEY.md §8c) -- parity is "unpinned"; these tests pin the two restatements to each other and
+to the invariants the reference itself asserts (utils.py:353-355, affordance demo :384-386)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import oracle_job, small_case
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "small_case.npz")
+
+
+@pytest.fixture(scope="module")
+def case(gwbp):
+    return small_case(gwbp.scene)
+
+
+def test_numpy_and_c_oracle_agree_bit_exact_on_integer_stages(case, noracle, coracle):
+    sc, vm, K, _ = case
+    for v in range(vm.shape[0]):
+        proj, isect = noracle.view_geometry(sc.means, sc.quats, sc.scales, vm[v], K, 96, 64)
+        cv = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, 96, 64)
+        e = cv.export()
+        assert np.array_equal(e["radii"], proj["radii"])
+        assert np.array_equal(e["depths"].view(np.int32), proj["depths"].view(np.int32))
+        vis = proj["radii"] > 0
+        assert np.array_equal(e["means2d"][vis].view(np.int32), proj["means2d"][vis].view(np.int32))
+        assert np.array_equal(e["conics"][vis].view(np.int32), proj["conics"][vis].view(np.int32))
+        for k in ("gaussian_ids", "isect_ids", "flatten_ids", "isect_offsets"):
+            assert np.array_equal(e[k], isect[k]), k
+        assert np.array_equal(coracle.covar(sc.quats, sc.scales).view(np.int32),
+                              noracle.quat_scale_to_covar(sc.quats, sc.scales).view(np.int32))
+
+
+def test_numpy_and_c_oracle_agree_on_accumulators(case, noracle, coracle):
+    sc, vm, K, feats = case
+    num_c, den_c, _ = oracle_job(coracle, sc, vm, K, 96, 64, feats, 8)
+    num_n = np.zeros_like(num_c)
+    den_n = np.zeros_like(den_c)
+    for v in range(vm.shape[0]):
+        a, b = noracle.backproject_view(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, 96, 64, feats[v])
+        num_n += a
+        den_n += b
+    # expf (glibc) vs np.exp differ in the last ulp of fp32 -> ~1e-7 relative
+    assert np.abs(num_c - num_n).max() <= 2e-6 * max(1.0, np.abs(num_n).max())
+    assert np.abs(den_c - den_n).max() <= 2e-6 * max(1.0, den_n.max())
+    assert np.array_equal(den_c > 0, den_n > 0)
+
+
+def test_fp32_mirror_close_to_fp64_truth(case, noracle):
+    sc, vm, K, feats = case
+    a32, d32 = noracle.backproject_view(sc.means, sc.quats, sc.scales, sc.opacities, vm[0], K, 96, 64, feats[0])
+    a64, d64 = noracle.backproject_view(sc.means, sc.quats, sc.scales, sc.opacities, vm[0], K, 96, 64, feats[0],
+                                        dtype=np.float64)
+    # threshold flips (alpha ~ 1/255, T ~ 1e-4) are possible but rare; bulk error is fp32 rounding
+    rel = np.abs(d32 - d64) / np.maximum(d64, 1e-6)
+    assert np.percentile(rel, 99) < 1e-5
+
+
+def test_invariant_sum_den_equals_sum_alpha(case, noracle, coracle):
+    """sum_g w(g,p) = 1 - T_final(p)  =>  sum_g den_v[g] = sum_p alpha_v(p)."""
+    sc, vm, K, feats = case
+    _, den, _ = oracle_job(coracle, sc, vm[:1], K, 96, 64, feats[:1], 8)
+    _, alpha = noracle.render_view(sc.means, sc.quats, sc.scales, sc.opacities, np.ones((sc.n, 1), np.float32),
+                                   vm[0], K, 96, 64)
+    assert abs(den.sum() - alpha.sum()) <= 1e-5 * alpha.sum()
+    cv = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[0], K, 96, 64)
+    _, alpha_c = cv.render(np.ones((sc.n, 1), np.float32))
+    assert abs(alpha_c.sum() - alpha.sum()) <= 1e-5 * alpha.sum()
+
+
+def test_invariant_constant_features(case, noracle, coracle):
+    """F == c  =>  num[g,:] = den[g] * c  =>  finalised row = c/||c||."""
+    sc, vm, K, _ = case
+    c = np.array([0.3, -1.0, 2.0, 0.5], np.float32)
+    F = np.broadcast_to(c, (64, 96, 4)).copy()
+    num, den, _ = oracle_job(coracle, sc, vm[:1], K, 96, 64, [F], 4)
+    assert np.allclose(num, den[:, None] * c[None, :].astype(np.float64), rtol=1e-12, atol=1e-12)
+    f = noracle.finalize(num, den + 1e-12)
+    seen = den > 0
+    assert np.allclose(f[seen], (c / np.linalg.norm(c))[None, :], atol=1e-6)
+    assert np.all(f[~seen] == 0)  # NaN -> 0 branch (backproject.py:169)
+
+
+def test_invariant_adjoint_of_forward_render(case, noracle, coracle):
+    """<render(X), F> == <X, backproject(F)> -- the back-projection IS the
+    gradient of the render w.r.t. colours (backproject.py:115-131)."""
+    sc, vm, K, feats = case
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((sc.n, 8)).astype(np.float32)
+    cv = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[1], K, 96, 64)
+    render, _ = cv.render(X)
+    num = np.zeros((sc.n, 8))
+    den = np.zeros(sc.n)
+    cv.backproject(np.asarray(feats[1]), num, den)
+    lhs = float((render * np.asarray(feats[1], np.float64)).sum())
+    rhs = float((X.astype(np.float64) * num).sum())
+    assert abs(lhs - rhs) <= 1e-9 * max(1.0, abs(lhs))
+
+
+def test_invariant_linearity_and_channel_independence(case, coracle):
+    """SURVEY §4 inv.4 (the reference's own assert: affordance demo :384-386)."""
+    sc, vm, K, feats = case
+    F = np.ascontiguousarray(feats[0])
+    G = np.ascontiguousarray(feats[1])
+    cv = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[0], K, 96, 64)
+
+    def bp(feat):
+        num = np.zeros((sc.n, feat.shape[2]))
+        den = np.zeros(sc.n)
+        cv.backproject(feat, num, den)
+        return num, den
+
+    nf, _ = bp(F)
+    ng, _ = bp(G)
+    nfg, _ = bp((2.0 * F + G).astype(np.float32))
+    assert np.allclose(nfg, 2.0 * nf + ng, rtol=1e-5, atol=1e-6)
+    ones, den = bp(np.ones((64, 96, 3), np.float32))
+    assert np.allclose(ones[:, 0], ones[:, 2]) and np.allclose(ones[:, 0], den)
+
+
+def test_view_sharding_sums_to_single_job(case, coracle):
+    """SURVEY §4 inv.5."""
+    sc, vm, K, feats = case
+    num, den, _ = oracle_job(coracle, sc, vm, K, 96, 64, feats, 8)
+    n0, d0, _ = oracle_job(coracle, sc, vm[0::2], K, 96, 64, feats[0::2], 8)
+    n1, d1, _ = oracle_job(coracle, sc, vm[1::2], K, 96, 64, feats[1::2], 8)
+    assert np.allclose(num, n0 + n1, rtol=1e-12, atol=1e-12) and np.allclose(den, d0 + d1, rtol=1e-12, atol=1e-12)
+
+
+def test_pruned_gaussians_do_not_change_the_render(case, noracle, coracle):
+    """The reference's own self-check (utils.py:292-360): dropping den==0 Gaussians changes no pixel."""
+    sc, vm, K, feats = case
+    _, den, _ = oracle_job(coracle, sc, vm, K, 96, 64, feats, 8)
+    keep = noracle.prune_mask(den)
+    assert 0 < keep.sum() < sc.n
+    rng = np.random.default_rng(1)
+    cols = rng.uniform(0, 1, (sc.n, 3)).astype(np.float32)
+    for v in range(vm.shape[0]):
+        full, _ = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, 96, 64).render(cols)
+        pruned, _ = coracle.View(sc.means[keep], sc.quats[keep], sc.scales[keep], sc.opacities[keep], vm[v], K, 96,
+                                 64).render(cols[keep])
+        assert np.abs(full - pruned).max() < 1.0 / (255 * 2)  # utils.py:353-355
+
+
+def test_edge_cases(gwbp, noracle, coracle):
+    S = gwbp.scene
+    vm, K = S.make_cameras(1, 40, 24, 0)
+    # empty scene
+    e = np.zeros((0, 3), np.float32)
+    cv = coracle.View(e, np.zeros((0, 4), np.float32), e, np.zeros(0, np.float32), vm[0], K, 40, 24)
+    assert cv.n_vis == 0 and cv.n_isects == 0
+    # behind the camera / zero scale / zero opacity / zero quaternion are legal inputs
+    means = np.array([[0, 0, 0], [100, 100, 100], [0, 0, 0.1], [0, 0, 0.2]], np.float32)
+    quats = np.array([[1, 0, 0, 0], [1, 0, 0, 0], [0, 0, 0, 0], [2, 0, 0, 0]], np.float32)
+    scales = np.array([[0.1, 0.1, 0.1], [0.1, 0.1, 0.1], [0.1, 0.1, 0.1], [0, 0, 0]], np.float32)
+    opac = np.array([0.9, 0.9, 0.9, 0.0], np.float32)
+    proj, isect = noracle.view_geometry(means, quats, scales, vm[0], K, 40, 24)
+    assert proj["radii"][0] > 0 and proj["radii"][2] == 0  # NaN quaternion is culled, not propagated
+    cv = coracle.View(means, quats, scales, opac, vm[0], K, 40, 24)
+    assert np.array_equal(cv.export()["radii"], proj["radii"])
+    num = np.zeros((4, 2))
+    den = np.zeros(4)
+    cv.backproject(np.ones((24, 40, 2), np.float32), num, den)
+    assert den[0] > 0 and den[3] == 0 and np.isfinite(num).all()
+
+
+def test_golden_fixture(gwbp, coracle, noracle):
+    """Committed fixture (tests/golden/make_golden.py): pins both restatements against drift."""
+    g = np.load(GOLDEN)
+    sc, vm, K, feats = small_case(gwbp.scene, **{k: int(g["cfg_" + k]) for k in ("n", "views", "width", "height", "d", "seed")})
+    W, H, d = int(g["cfg_width"]), int(g["cfg_height"]), int(g["cfg_d"])
+    cv = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[0], K, W, H)
+    e = cv.export()
+    assert np.array_equal(e["isect_ids"], g["isect_ids_v0"])
+    assert np.array_equal(e["flatten_ids"], g["flatten_ids_v0"])
+    assert np.array_equal(e["isect_offsets"], g["isect_offsets_v0"])
+    assert np.array_equal(e["radii"], g["radii_v0"])
+    num, den, _ = oracle_job(coracle, sc, vm, K, W, H, feats, d)
+    assert np.allclose(num, g["num"], rtol=0, atol=2e-6 * np.abs(g["num"]).max())
+    assert np.allclose(den, g["den"], rtol=0, atol=2e-6 * g["den"].max())
+    f = noracle.finalize(num, den + 1e-12)
+    assert np.abs(f - g["features"]).max() < 1e-5
+    t = gwbp.scene.make_text_queries(3, d, 0)
+    m, _ = noracle.mask3d(f, t, 1)
+    assert (m != g["mask3d"]).sum() <= 1
