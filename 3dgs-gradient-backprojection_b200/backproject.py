@@ -41,6 +41,7 @@ class BackProjector:
         self._stats = torch.zeros(4, dtype=torch.int64, device=self.device) if collect_stats else None
         self.n_views = 0
         self.last_view: Optional[View] = None
+        self.kernel_events = None  # set to [] to record (start, end) CUDA events around the fused kernel
 
     # -- one view -------------------------------------------------------------------------
     def add_view(self, viewmat, K, width, height, feats: torch.Tensor, **cam_kw) -> View:
@@ -57,7 +58,13 @@ class BackProjector:
                 fp = self._fpack
             elif self.kernel == L.KERNEL_TC:
                 raise RuntimeError(f"tcgen05 kernel does not support D={self.d}")
+        if self.kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(self.device))
         view.backproject(feats, self.num, self.den, self.kernel, fp, self._stats)
+        if self.kernel_events is not None:
+            e1.record(torch.cuda.current_stream(self.device))
+            self.kernel_events.append((e0, e1))
         self.n_views += 1
         self.last_view = view
         return view
@@ -68,10 +75,18 @@ class BackProjector:
         return self.num, self.den
 
     def stats(self) -> dict:
+        """Counters summed over all views so far (device -> host read)."""
         if self._stats is None:
             return {}
         s = self._stats.tolist()
         return {"rows_nonzero": s[0], "entries_walked": s[1]}
+
+    def reset(self) -> None:
+        self.num.zero_()
+        self.den.fill_(DEN_EPS)
+        if self._stats is not None:
+            self._stats.zero_()
+        self.n_views = 0
 
     def prune_mask(self) -> torch.Tensor:
         """== `gaussian_grads > 0` of prune_by_gradients (utils.py:257)."""

@@ -112,7 +112,7 @@ def make_feature_map_np(view: int, d: int, height: int, width: int, seed: int = 
     x0, x1, wx = src_index(width, enc_res)
     top = low[:, y0][:, :, x0] * (1 - wx) + low[:, y0][:, :, x1] * wx
     bot = low[:, y1][:, :, x0] * (1 - wx) + low[:, y1][:, :, x1] * wx
-    planar = (top * (1 - wy)[None, :, None] + bot * wy[None, :, None]).astype(np.float32)  # [d,H,W]
+    planar = np.ascontiguousarray((top * (1 - wy)[None, :, None] + bot * wy[None, :, None]).astype(np.float32))  # [d,H,W]
     return np.transpose(planar, (1, 2, 0))  # strided view, NOT contiguous
 
 

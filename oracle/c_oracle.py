@@ -67,11 +67,15 @@ class View:
         self.n_vis, self.n_isects, self.tile_width, self.tile_height = nv.value, ni.value, tw.value, th.value
 
     def close(self):
-        if self._h:
-            lib().orc_view_destroy(self._h)
-            self._h = None
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.orc_view_destroy(self._h)
+        self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
 
     def export(self):
         n, nv, ni = self.n, self.n_vis, self.n_isects

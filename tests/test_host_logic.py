@@ -1,0 +1,73 @@
+"""CPU tests of the host logic: scene determinism, view sharding, and the N>1 reduction path
+(world_size-2 gloo, as the N-GPU path uses nccl for the same call)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_scene_generator_is_deterministic(gwbp):
+    S = gwbp.scene
+    a, b = S.make_scene(1000, 3), S.make_scene(1000, 3)
+    assert all(np.array_equal(getattr(a, k), getattr(b, k)) for k in ("means", "quats", "scales", "opacities"))
+    assert not np.array_equal(a.means, S.make_scene(1000, 4).means)
+    vm, K = S.make_cameras(5, 128, 96)
+    for v in vm:  # rigid world->camera matrices looking at the origin
+        assert np.allclose(v[:3, :3] @ v[:3, :3].T, np.eye(3), atol=1e-5)
+        assert v[2, 3] > 3.0  # origin is in front of the camera
+    f = S.make_feature_map_np(0, 8, 20, 30)
+    assert f.shape == (20, 30, 8) and f.strides[2] > f.strides[1]  # permuted view of a planar buffer
+    assert np.abs(np.linalg.norm(S.make_text_queries(3, 16), axis=1) - 1).max() < 1e-6
+
+
+def test_shard_views_partition(gwbp):
+    for n_views, world in [(185, 8), (7, 2), (3, 4), (0, 2)]:
+        seen = sorted(v for r in range(world) for v in gwbp.dist.shard_views(n_views, r, world))
+        assert seen == list(range(n_views))
+        sizes = [len(gwbp.dist.shard_views(n_views, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import gwbp
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, d, n_views = 64, 4, 5
+    g = torch.Generator().manual_seed(0)
+    per_view_num = torch.rand(n_views, n, d, generator=g)
+    per_view_den = torch.rand(n_views, n, generator=g)
+    num = torch.zeros(n, d)
+    den = torch.full((n,), gwbp.DEN_EPS)
+    for v in gwbp.dist.shard_views(n_views, rank, world):
+        num += per_view_num[v]
+        den += per_view_den[v]
+    gwbp.dist.allreduce_accumulators(num, den)
+    ref_num, ref_den = per_view_num.sum(0), per_view_den.sum(0) + gwbp.DEN_EPS
+    ok = torch.allclose(num, ref_num, atol=1e-6) and torch.allclose(den, ref_den, atol=1e-6)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_allreduce_accumulators_world2_gloo():
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as m:
+        out = m.dict()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+        [p.start() for p in procs]
+        [p.join(120) for p in procs]
+        assert all(p.exitcode == 0 for p in procs)
+        assert dict(out) == {0: True, 1: True}
