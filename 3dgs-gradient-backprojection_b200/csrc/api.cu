@@ -38,6 +38,7 @@ static TileCtx tile_ctx(const gwbp_camera *cam, const void *ws, const gwbp_ws_la
     t.grec = w.grec;
     t.flatten = w.vals[info->sorted_buf];
     t.offsets = w.offsets;
+    t.scratch = w.stats;
     t.W = cam->width; t.H = cam->height;
     t.tw = info->tile_w; t.th = info->tile_h;
     return t;
@@ -132,7 +133,9 @@ size_t gwbp_fpack_bytes(int32_t width, int32_t height, int32_t d) {
 int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws,
                           const gwbp_view_info *info, const float *F, int64_t sH, int64_t sW, int64_t sD, int32_t d,
                           float *num, float *den, int32_t kernel, void *fpack, int64_t *stats, void *stream) {
-    GWBP_REQUIRE(scene && ws && info && F && num && den, "backproject_view: NULL pointer");
+    GWBP_REQUIRE(scene && info, "backproject_view: NULL pointer");
+    if (scene->n == 0 || info->n_isects == 0) return 0;
+    GWBP_REQUIRE(ws && F && num && den, "backproject_view: NULL pointer");
     if (int rc = check_cam(cam)) return rc;
     GWBP_REQUIRE(d >= 1, "feature dimension must be >= 1 (got %d)", d);
     gwbp_ws_layout L;
@@ -154,7 +157,9 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam, const
 int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws, const gwbp_view_info *info,
                      const float *colors, int64_t color_stride, int32_t d, const float *background, float *render,
                      float *alpha, void *stream) {
-    GWBP_REQUIRE(scene && ws && info && colors && render, "render_view: NULL pointer");
+    GWBP_REQUIRE(scene && info, "render_view: NULL pointer");
+    if (scene->n == 0 || info->n_isects == 0) return 0;
+    GWBP_REQUIRE(ws && colors && render, "render_view: NULL pointer");
     if (int rc = check_cam(cam)) return rc;
     GWBP_REQUIRE(d >= 1, "channel count must be >= 1 (got %d)", d);
     GWBP_REQUIRE(color_stride >= d, "color_stride (%lld) < d (%d)", (long long)color_stride, d);

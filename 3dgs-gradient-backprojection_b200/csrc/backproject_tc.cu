@@ -1,11 +1,482 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// Stage 3, tensor-core path: per-tile compositing fused with the back-projection contraction
+//      num[g, :] += sum_p w(g,p) F[p, :]          (== gsplat rasterize_to_pixels_bwd v_colors with
+//      den[g]    += sum_p w(g,p)                      v_render = F, backproject.py:127-131,145-151)
+// as a [128 Gaussians x 256 pixels] x [256 pixels x D] GEMM per (tile, Gaussian batch) on the
+// 5th-gen tensor cores (tcgen05.mma, cta_group::1, kind::f16), fp32 accumulation in TMEM.
+//
+// Precision: both operands are split into bf16 hi + lo (x ~= hi + lo, 16 mantissa bits) and three
+// MMAs are issued per K-step (hi*hi + hi*lo + lo*hi), so the contraction carries ~2^-16 relative
+// error -- the 1e-4 parity bar is not reachable with plain bf16 operands (8 bits).
+//
+// Work unit = (tile, 256-column chunk of D): D=512 is two units per tile, each regenerating W (the
+// weight generation is cheaper than the 3 x 16 MMAs it feeds) so that the [128 x 256] fp32 accumulator
+// can be double buffered in the 512 TMEM columns.
+// Data flow of one persistent CTA (1 per SM, 480 threads, warp-specialised):
+//   warps 0-7   ALU      : thread = pixel.  Walk the tile's depth-sorted list 128 Gaussians at a time,
+//                          generate w = alpha*T (sequential T per pixel), write W^T as bf16 hi/lo
+//                          straight into the UMMA canonical layout (MN-major, SWIZZLE_NONE) in smem.
+//   warp 13     producer : streams the pre-packed bf16 hi/lo feature tile through a 4-stage smem ring
+//                          with cp.async.bulk (TMA engine), one 16-pixel K-slice x <=256 columns per stage.
+//   warp 14     MMA      : one thread issues tcgen05.mma; accumulators [128 x <=256] fp32 are double
+//                          buffered in the 512 TMEM columns so the epilogue of one batch overlaps the
+//                          MMAs of the next.
+//   warps 8-11  epilogue : tcgen05.ld the accumulator (lane = Gaussian row), stage 128-byte row pieces
+//                          in smem and let the TMA engine reduce them into num[N,D] in HBM
+//                          (cp.reduce.async.bulk.add.f32: measured 2.5-2.7 TB/s of payload on scattered
+//                          2 KB rows vs 0.6 TB/s for per-lane red.v4 -- profiles/r01_probe.txt).
+// The W buffer (128 KB) is single: warp w re-fills its 32-pixel slab for batch q+1 as soon as the MMA
+// of batch q's last column chunk has consumed it (per-warp mbarriers), so generation and MMA overlap.
+//
+// The feature map is re-laid-out once per view by fpack_kernel (fp32 [H,W,D], any strides ->
+// bf16 hi/lo, tile-major, already in UMMA core-matrix order) so the producer needs no tensor map.
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace gwbp {
-size_t fpack_bytes(int, int, int) { return 0; }
-bool tc_supported(int) { return false; }
-int launch_backproject_tc(const TileCtx &, const float *, int64_t, int64_t, int64_t, int, float *, float *, void *,
-                          long long *, cudaStream_t) {
-    set_error("tcgen05 path not built");
-    return -1;
+
+using namespace tc;
+
+namespace {
+
+constexpr int MB = 128;             // Gaussians per batch = UMMA M
+constexpr int NCMAX = 256;          // columns per work unit = UMMA N (max)
+constexpr int KSL = 16;             // pixels per K-slice (= one tile row) = one UMMA K step for bf16
+constexpr int NSTAGE = 4;           // feature ring depth (16 KB stages)
+constexpr int STAGE_BYTES = NCMAX * KSL * 2 * 2;  // hi + lo = 16 KB
+constexpr int RING = 4;             // batches in flight between ALU and epilogue
+constexpr uint32_t A_SBO = 128, A_LBO = (MB / 8) * 128;  // W^T: 16 row-groups of 8 Gaussians per K-group
+constexpr int W_PART_BYTES = (kTilePix / 8) * A_LBO;     // 64 KB per hi / lo part
+constexpr int EPI_COLS = 32;                             // columns per epilogue piece (128 B per row)
+constexpr int EPI_PITCH = EPI_COLS * 4 + 16;             // padded row pitch: conflict-free 16-byte stores
+
+constexpr int kEpiWarp0 = 8, kProducerWarp = 13, kMmaWarp = 14, kThreads = 480;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct RowInfo {
+    int gid[MB];
+    float den[MB];
+    int exit_flag, pad[3];
+};
+
+struct Smem {
+    // offsets into dynamic shared memory
+    static constexpr int w_hi = 0;
+    static constexpr int w_lo = W_PART_BYTES;
+    static constexpr int fring = 2 * W_PART_BYTES;
+    static constexpr int stage_out = fring + NSTAGE * STAGE_BYTES;   // epilogue staging: 128 rows x EPI_PITCH
+    static constexpr int gbuf = stage_out + MB * EPI_PITCH;          // 128 x 2 float4
+    static constexpr int rows = gbuf + MB * 32;
+    static constexpr int ctrl = rows + RING * (int)sizeof(RowInfo);  // int[RING]
+    static constexpr int bars = ctrl + 64;
+    // barrier indices
+    static constexpr int w_full = 0, w_free = 8, f_full = 16, f_empty = f_full + NSTAGE,
+                         acc_full = f_empty + NSTAGE, acc_empty = acc_full + 2, rows_ready = acc_empty + 2,
+                         rows_free = rows_ready + RING, ctrl_full = rows_free + RING, ctrl_empty = ctrl_full + RING,
+                         nbars = ctrl_empty + RING;
+    static constexpr int tmem_slot = bars + nbars * 8;
+    static constexpr int total = tmem_slot + 16;
+};
+static_assert(Smem::total + 64 <= 232448, "shared memory budget (227 KB) exceeded");
+
+__device__ __forceinline__ int bar_red_popc_alu(bool pred) {
+    int cnt;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "bar.red.popc.u32 %0, 1, 256, p;\n\t}"
+        : "=r"(cnt)
+        : "r"((int)pred)
+        : "memory");
+    return cnt;
 }
+__device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2, what __expf lowers to after the log2(e) scale
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void bar_sync_alu() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+struct TcArgs {
+    TileCtx t;
+    const uint8_t *fpack;
+    float *num, *den;
+    int d, dp, nchunks, nunits;
+    int *unit_counter;
+    long long *stats;
+};
+
+// -------------------------------------------------------------------------------------------------
+// work unit = (tile, column chunk c): every CTA pulls units from a global counter
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ int s_unit;
+    const uint32_t sbase = smem_u32(smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    auto bar = [&](int i) -> uint32_t { return sbase + Smem::bars + 8 * i; };
+    RowInfo *rows = reinterpret_cast<RowInfo *>(smem + Smem::rows);
+    volatile int *ctrl = reinterpret_cast<volatile int *>(smem + Smem::ctrl);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Smem::tmem_slot);
+
+    if (tid == 0) {
+        for (int i = 0; i < 8; ++i) { mbar_init(bar(Smem::w_full + i), 1); mbar_init(bar(Smem::w_free + i), 1); }
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(bar(Smem::f_full + i), 1); mbar_init(bar(Smem::f_empty + i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(Smem::acc_full + i), 1); mbar_init(bar(Smem::acc_empty + i), 4); }
+        for (int i = 0; i < RING; ++i) {
+            mbar_init(bar(Smem::rows_ready + i), 8);
+            mbar_init(bar(Smem::rows_free + i), 4);
+            mbar_init(bar(Smem::ctrl_full + i), 1);
+            mbar_init(bar(Smem::ctrl_empty + i), 2);
+        }
+        mbar_init_fence();
+    }
+    if (warp == kMmaWarp) tmem_alloc<512>(smem_u32(tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 8) {
+        // ======================================= ALU =========================================
+        float4 *gbuf = reinterpret_cast<float4 *>(smem + Smem::gbuf);
+        int q = 0;
+        long long walked = 0;
+        const uint32_t wslab = (uint32_t)(tid >> 3) * A_LBO + (uint32_t)(tid & 7) * 16;  // this pixel's K-row
+        while (true) {
+            if (tid == 0) s_unit = atomicAdd(a.unit_counter, 1);
+            bar_sync_alu();
+            const int unit = s_unit;
+            bar_sync_alu();  // everyone has read s_unit before it is overwritten
+            if (unit >= a.nunits) break;
+            const int tile = unit / a.nchunks;
+            const int ty = tile / a.t.tw, tx = tile % a.t.tw;
+            const int s = a.t.offsets[tile], e = a.t.offsets[tile + 1];
+            const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
+            const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
+            bool done = !(yy < a.t.H && xx < a.t.W);
+            float T = 1.0f;
+            // prefetch the first batch's record for row `tid` (threads 0..127)
+            float4 r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid < MB && s + tid < e) {
+                const int id = a.t.flatten[s + tid];
+                r0 = a.t.grec[2 * (int64_t)id];
+                r1 = a.t.grec[2 * (int64_t)id + 1];
+            }
+            for (int b = s; b < e; b += MB, ++q) {
+                if (bar_red_popc_alu(!done) == 0) break;  // also: every warp is done reading gbuf of batch q-1
+                const int slot = q % RING;
+                if (q >= RING) mbar_wait(bar(Smem::rows_free + slot), ((q / RING) - 1) & 1);
+                if (tid < MB) {
+                    // exponent pre-scaled for ex2: alpha = op * 2^(a dx^2 + b dx dy + c dy^2)
+                    gbuf[tid] = make_float4(r0.x, r0.y, r0.z, -0.5f * kLog2e * r1.x);
+                    gbuf[MB + tid] = make_float4(-kLog2e * r1.y, -0.5f * kLog2e * r1.z, 0.f, 0.f);
+                    rows[slot].gid[tid] = __float_as_int(r0.w);
+                    rows[slot].den[tid] = 0.0f;
+                    if (tid == 0) rows[slot].exit_flag = 0;
+                }
+                if (tid == 0) {
+                    if (q >= RING) mbar_wait(bar(Smem::ctrl_empty + slot), ((q / RING) - 1) & 1);
+                    ctrl[slot] = unit;
+                    mbar_arrive(bar(Smem::ctrl_full + slot));
+                }
+                bar_sync_alu();
+                // prefetch the next batch while this one is processed
+                r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tid < MB && b + MB + tid < e) {
+                    const int id = a.t.flatten[b + MB + tid];
+                    r0 = a.t.grec[2 * (int64_t)id];
+                    r1 = a.t.grec[2 * (int64_t)id + 1];
+                }
+                if (q >= 1) mbar_wait(bar(Smem::w_free + warp), (q - 1) & 1);
+                if (unit % a.nchunks == 0) walked += min(MB, e - b);
+                if (__all_sync(0xffffffffu, done)) {
+                    // this warp's 32 pixels are finished: its slab of W is all zero
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 4
+                    for (int j = 0; j < MB / 8; ++j) {
+                        *reinterpret_cast<uint4 *>(smem + Smem::w_hi + j * A_SBO + wslab) = z;
+                        *reinterpret_cast<uint4 *>(smem + Smem::w_lo + j * A_SBO + wslab) = z;
+                    }
+                } else {
+#pragma unroll 1
+                    for (int j = 0; j < MB / 8; ++j) {
+                        float w[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 g0 = gbuf[8 * j + i], g1 = gbuf[MB + 8 * j + i];
+                            const float dx = g0.x - px, dy = g0.y - py;
+                            const float pw = dx * fmaf(g0.w, dx, g1.x * dy) + (g1.y * dy) * dy;  // -sigma*log2(e)
+                            const float alpha = fminf(kAlphaMax, g0.z * fast_ex2(pw));
+                            const float nT = fmaf(-alpha, T, T);
+                            const bool valid = !done && pw <= 0.0f && alpha >= kAlphaMin;
+                            const bool stop = valid && nT <= kTMin;
+                            const bool take = valid && !stop;
+                            w[i] = take ? alpha * T : 0.0f;
+                            T = take ? nT : T;
+                            done = done || stop;
+                        }
+                        uint4 hi, lo;
+                        split_bf16x2(w[0], w[1], hi.x, lo.x);
+                        split_bf16x2(w[2], w[3], hi.y, lo.y);
+                        split_bf16x2(w[4], w[5], hi.z, lo.z);
+                        split_bf16x2(w[6], w[7], hi.w, lo.w);
+                        const uint32_t off = (uint32_t)j * A_SBO + wslab;
+                        *reinterpret_cast<uint4 *>(smem + Smem::w_hi + off) = hi;
+                        *reinterpret_cast<uint4 *>(smem + Smem::w_lo + off) = lo;
+                        // per-Gaussian sum over the warp's 32 pixels (den): butterfly transpose-reduce
+                        const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+                        float v4[4], v2[2], v1;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float send = b16 ? w[i] : w[i + 4];
+                            v4[i] = (b16 ? w[i + 4] : w[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float send = b8 ? v4[i] : v4[i + 2];
+                            v2[i] = (b8 ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+                        {
+                            const float send = b4 ? v2[0] : v2[1];
+                            v1 = (b4 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+                        v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+                        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+                        if ((lane & 3) == 0 && v1 > 0.0f) {
+                            const int gi = (b16 ? 4 : 0) + (b8 ? 2 : 0) + (b4 ? 1 : 0);
+                            atomicAdd(&rows[slot].den[8 * j + gi], v1);
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(bar(Smem::w_full + warp));
+                    mbar_arrive(bar(Smem::rows_ready + slot));
+                }
+            }
+        }
+        // exit sentinel for the other roles
+        {
+            const int slot = q % RING;
+            if (q >= RING) mbar_wait(bar(Smem::rows_free + slot), ((q / RING) - 1) & 1);
+            if (tid == 0) {
+                rows[slot].exit_flag = 1;
+                if (q >= RING) mbar_wait(bar(Smem::ctrl_empty + slot), ((q / RING) - 1) & 1);
+                ctrl[slot] = -1;
+                mbar_arrive(bar(Smem::ctrl_full + slot));
+            }
+            bar_sync_alu();
+            if (lane == 0) mbar_arrive(bar(Smem::rows_ready + slot));
+        }
+        if (a.stats && tid == 0) atomicAdd((unsigned long long *)&a.stats[1], (unsigned long long)walked);
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
+        // ===================================== epilogue ======================================
+        // TMEM lane = Gaussian row.  Rows are staged 32 columns (128 B) at a time in shared memory
+        // and reduced into num[gid, :] by the TMA engine (cp.reduce.async.bulk .add.f32): one
+        // contiguous 128-byte reduction per live row instead of 32 scattered 16-byte atomics.
+        const int quarter = warp & 3;
+        const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
+        const int r = 32 * quarter + lane;
+        uint8_t *srow = smem + Smem::stage_out + r * EPI_PITCH;
+        const uint32_t srow_u32 = sbase + Smem::stage_out + r * EPI_PITCH;
+        long long live_rows = 0;
+        for (int q = 0;; ++q) {
+            const int slot = q % RING;
+            mbar_wait(bar(Smem::rows_ready + slot), (q / RING) & 1);
+            if (rows[slot].exit_flag) break;
+            const int unit = ctrl[slot];  // still valid: the slot is recycled only after rows_free
+            const int c = unit % a.nchunks;
+            const int gid = rows[slot].gid[r];
+            const float dn = rows[slot].den[r];
+            const bool live = (gid >= 0) && (dn > 0.0f);
+            float *dst = a.num + (int64_t)(live ? gid : 0) * a.d + c * NCMAX;
+            const int ncols = min(NCMAX, a.dp - c * NCMAX);   // padded columns of this chunk
+            const int dcols = min(NCMAX, a.d - c * NCMAX);    // real columns of this chunk
+            const int ab = q & 1;
+            mbar_wait(bar(Smem::acc_full + ab), (q >> 1) & 1);
+            tc_fence_after();
+            for (int c0 = 0; c0 < ncols; c0 += EPI_COLS) {
+                float v[32];
+                tmem_ld32(tmem + lane_base + (uint32_t)(ab * NCMAX + c0), v);
+                bulk_wait_read<0>();  // my previous reduction has finished reading my staging row
+                if (live && c0 < dcols) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4 *>(srow + 4 * i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    fence_proxy_async_smem();
+                    bulk_reduce_add_f32(dst + c0, srow_u32, (uint32_t)min(EPI_COLS, dcols - c0) * 4u);
+                    bulk_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(Smem::acc_empty + ab));
+            if (live && c == 0) atomicAdd(a.den + gid, dn);
+            if (live && c == 0) ++live_rows;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(Smem::rows_free + slot));
+        }
+        bulk_wait_all<0>();
+        if (a.stats) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) live_rows += __shfl_xor_sync(0xffffffffu, live_rows, o);
+            if (lane == 0) atomicAdd((unsigned long long *)&a.stats[0], (unsigned long long)live_rows);
+        }
+    } else if (warp == kProducerWarp) {
+        // ===================================== producer ======================================
+        if (lane == 0) {
+            int stage = 0, use = 0;
+            const int64_t tile_bytes = (int64_t)kTilePix * a.dp * 4;
+            for (int q = 0;; ++q) {
+                const int slot = q % RING;
+                mbar_wait(bar(Smem::ctrl_full + slot), (q / RING) & 1);
+                const int unit = ctrl[slot];
+                mbar_arrive(bar(Smem::ctrl_empty + slot));
+                if (unit < 0) break;
+                const int tile = unit / a.nchunks, c = unit % a.nchunks;
+                const int ncols = min(NCMAX, a.dp - c * NCMAX);
+                const uint32_t bytes = (uint32_t)ncols * KSL * 4;  // hi + lo
+                const uint8_t *cbase = a.fpack + tile * tile_bytes + (int64_t)c * NCMAX * kTilePix * 4;
+                for (int ks = 0; ks < kTilePix / KSL; ++ks) {
+                    if (use >= 1) mbar_wait(bar(Smem::f_empty + stage), (use - 1) & 1);
+                    mbar_arrive_expect_tx(bar(Smem::f_full + stage), bytes);
+                    bulk_g2s(sbase + Smem::fring + stage * STAGE_BYTES, cbase + (int64_t)ks * bytes, bytes,
+                             bar(Smem::f_full + stage));
+                    if (++stage == NSTAGE) { stage = 0; ++use; }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ======================================= MMA =========================================
+        if (lane == 0) {
+            int stage = 0, use = 0;
+            for (int q = 0;; ++q) {
+                const int slot = q % RING;
+                mbar_wait(bar(Smem::ctrl_full + slot), (q / RING) & 1);
+                const int unit = ctrl[slot];
+                mbar_arrive(bar(Smem::ctrl_empty + slot));
+                if (unit < 0) break;
+                const int c = unit % a.nchunks, ab = q & 1;
+                const int ncols = min(NCMAX, a.dp - c * NCMAX);
+                const uint32_t idesc = umma_idesc_bf16(MB, ncols, true, true);
+                const uint32_t b_lbo = (uint32_t)(ncols / 8) * 128, b_part = (uint32_t)ncols * KSL * 2;
+                if (q >= 2) mbar_wait(bar(Smem::acc_empty + ab), ((q >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + (uint32_t)(ab * NCMAX);
+                for (int ks = 0; ks < kTilePix / KSL; ++ks) {
+                    if ((ks & 1) == 0) mbar_wait(bar(Smem::w_full + (ks >> 1)), q & 1);
+                    mbar_wait(bar(Smem::f_full + stage), use & 1);
+                    tc_fence_after();
+                    const uint32_t a_off = (uint32_t)ks * 2 * A_LBO;
+                    const uint64_t a_hi = umma_smem_desc(sbase + Smem::w_hi + a_off, A_LBO, A_SBO);
+                    const uint64_t a_lo = umma_smem_desc(sbase + Smem::w_lo + a_off, A_LBO, A_SBO);
+                    const uint32_t fb = sbase + Smem::fring + stage * STAGE_BYTES;
+                    const uint64_t b_hi = umma_smem_desc(fb, b_lbo, 128);
+                    const uint64_t b_lo = umma_smem_desc(fb + b_part, b_lbo, 128);
+                    umma_bf16(d_tmem, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+                    umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+                    umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+                    umma_commit(bar(Smem::f_empty + stage));
+                    if (ks & 1) umma_commit(bar(Smem::w_free + (ks >> 1)));
+                    if (++stage == NSTAGE) { stage = 0; ++use; }
+                }
+                umma_commit(bar(Smem::acc_full + ab));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc<512>(tmem);
+}
+
+// -------------------------------------------------------------------------------------------------
+// feature re-layout: fp32 [H,W,D] (element strides sH,sW,sD) -> bf16 hi/lo, tile-major, UMMA
+// core-matrix order.  Per (tile, chunk c, K-slice ks) one contiguous block:
+//   [hi: (p/8)*LBO + (n/8)*128 + (p%8)*16 + (n%8)*2][lo: same]   LBO = (ncols/8)*128, p in 0..15
+// One CTA per (tile, chunk); HBM-bound: reads 4 B and writes 4 B per feature element.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fpack_kernel(const float *__restrict__ F, int64_t sH, int64_t sW, int64_t sD,
+                                                    int W, int H, int tw, int d, int dp, int nchunks,
+                                                    uint8_t *__restrict__ out) {
+    __shared__ __align__(16) float slab[KSL][NCMAX + 4];
+    const int tile = blockIdx.x / nchunks, c = blockIdx.x % nchunks;
+    const int ty = tile / tw, tx = tile % tw;
+    const int ncols = min(NCMAX, dp - c * NCMAX);
+    const int t = threadIdx.x;
+    uint8_t *cbase = out + (int64_t)tile * kTilePix * dp * 4 + (int64_t)c * NCMAX * kTilePix * 4;
+    const uint32_t lbo = (uint32_t)(ncols / 8) * 128, part = (uint32_t)ncols * KSL * 2;
+    const int col = c * NCMAX + t;
+    for (int ks = 0; ks < kTilePix / KSL; ++ks) {
+        const int y = ty * kTile + ks;
+        if (t < ncols) {
+#pragma unroll
+            for (int p = 0; p < KSL; ++p) {
+                const int x = tx * kTile + p;
+                const bool ok = (y < H) && (x < W) && (col < d);
+                slab[p][t] = ok ? __ldg(F + y * sH + x * sW + col * sD) : 0.0f;
+            }
+        }
+        __syncthreads();
+        // item = (pixel p, 8-column group ng): one 16-byte row of a core matrix, hi and lo
+        for (int item = t; item < KSL * (ncols / 8); item += 256) {
+            const int p = item % KSL, ng = item / KSL;
+            const float4 f0 = *reinterpret_cast<const float4 *>(&slab[p][8 * ng]);
+            const float4 f1 = *reinterpret_cast<const float4 *>(&slab[p][8 * ng + 4]);
+            uint4 hi, lo;
+            split_bf16x2(f0.x, f0.y, hi.x, lo.x);
+            split_bf16x2(f0.z, f0.w, hi.y, lo.y);
+            split_bf16x2(f1.x, f1.y, hi.z, lo.z);
+            split_bf16x2(f1.z, f1.w, hi.w, lo.w);
+            const uint32_t off = (uint32_t)(p / 8) * lbo + (uint32_t)ng * 128 + (uint32_t)(p % 8) * 16;
+            uint8_t *blk = cbase + (int64_t)ks * part * 2;
+            *reinterpret_cast<uint4 *>(blk + off) = hi;
+            *reinterpret_cast<uint4 *>(blk + part + off) = lo;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// 16-byte row pieces for the bulk reduction need D % 4 == 0; tiny D is not worth a GEMM
+bool tc_supported(int d) { return d >= 16 && d <= 2048 && d % 4 == 0; }
+
+size_t fpack_bytes(int W, int H, int d) {
+    const size_t tiles = (size_t)((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile);
+    return tiles * kTilePix * (size_t)round_up(d, 16) * 4;
+}
+
+int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t sW, int64_t sD, int d, float *num,
+                          float *den, void *fpack, long long *stats, cudaStream_t st) {
+    const int ntiles = t.tw * t.th;
+    if (ntiles == 0) return 0;
+    GWBP_REQUIRE(((uintptr_t)fpack & 127) == 0, "fpack must be 128-byte aligned");
+    GWBP_REQUIRE(((uintptr_t)num & 15) == 0, "num must be 16-byte aligned");
+    const int dp = round_up(d, 16), nchunks = (dp + NCMAX - 1) / NCMAX;
+    fpack_kernel<<<ntiles * nchunks, 256, 0, st>>>(F, sH, sW, sD, t.W, t.H, t.tw, d, dp, nchunks, (uint8_t *)fpack);
+    GWBP_CUDA_OK(cudaGetLastError());
+
+    TcArgs a;
+    a.t = t;
+    a.fpack = (const uint8_t *)fpack;
+    a.num = num; a.den = den;
+    a.d = d; a.dp = dp; a.nchunks = nchunks; a.nunits = ntiles * nchunks;
+    a.unit_counter = (int *)t.scratch;
+    a.stats = stats;
+    GWBP_CUDA_OK(cudaMemsetAsync(a.unit_counter, 0, sizeof(int), st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        GWBP_CUDA_OK(cudaFuncSetAttribute(bp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+        attr_set = true;
+    }
+    const int grid = a.nunits < kNumSMs ? a.nunits : kNumSMs;
+    bp_tc_kernel<<<grid, kThreads, Smem::total, st>>>(a);
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace gwbp

@@ -95,6 +95,7 @@ struct TileCtx {
     const float4 *grec;
     const int *flatten;
     const int *offsets;
+    long long *scratch;  // 16 device int64 in the workspace (work-queue counters)
     int W, H, tw, th;
 };
 

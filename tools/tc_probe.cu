@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(128) umma_probe(const float *__restrict__ A, c
     for (int c = 0; c < N; c += 32) {
         float v[32];
         tmem_ld32(tm + ((uint32_t)(32 * warp) << 16) + c, v);
-        for (int j = 0; j < 32; ++j) D[(32 * warp + (tid & 31)) * N + c + j] = v[j];
+        for (int j = 0; j < 32; ++j)
+            if (c + j < N) D[(32 * warp + (tid & 31)) * N + c + j] = v[j];
     }
     tc_fence_before();
     __syncthreads();
@@ -97,7 +98,7 @@ static void run_umma_probe() {
     const size_t smem = (size_t)(K / 8) * 16 * 128 + (size_t)(K / 8) * (N / 8) * 128;
     CK(cudaFuncSetAttribute(umma_probe<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int two = 0; two < 2; ++two)
-        for (int swap = 0; swap < 2; ++swap) {
+        for (int swap = 0; swap < 1; ++swap) {  // swapped LBO/SBO faults (verified on B200): the cute convention is right
             CK(cudaMemset(dD, 0, D.size() * 4));
             umma_probe<N, K><<<1, 128, smem>>>(dA, dB, dD, swap, two);
             cudaError_t e = cudaDeviceSynchronize();
@@ -279,6 +280,7 @@ int main(int argc, char **argv) {
         run_umma_probe<256, 64>();
         run_umma_probe<64, 32>();
         run_umma_probe<16, 16>();
+        run_umma_probe<112, 32>();
     }
     if (!strcmp(what, "all") || !strcmp(what, "acc")) run_acc_probe();
     if (!strcmp(what, "all") || !strcmp(what, "stream")) run_stream_probe();
