@@ -12,7 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgwbp.so")
 
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
+PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL = 0, 1
 
 
 class Scene(C.Structure):
@@ -41,7 +42,7 @@ SIGNATURES = {
     "gwbp_workspace_layout": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.POINTER(WsLayout)]),
     "gwbp_pack_scene": (C.c_int, [C.c_int64] + [C.c_void_p] * 6),
     "gwbp_view_prepare": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.c_void_p, C.c_size_t, C.c_int64,
-                                    C.c_void_p, C.POINTER(ViewInfo)]),
+                                    C.c_int32, C.c_void_p, C.POINTER(ViewInfo)]),
     "gwbp_fpack_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "gwbp_backproject_view": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.c_void_p, C.POINTER(ViewInfo),
                                         C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,

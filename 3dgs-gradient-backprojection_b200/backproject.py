@@ -27,7 +27,7 @@ DEN_EPS = 1e-12  # backproject.py:63
 
 class BackProjector:
     def __init__(self, means, quats, scales, opacities, feature_dim: int, device=None, kernel: str = "auto",
-                 cap_isects: Optional[int] = None, collect_stats: bool = False):
+                 cap_isects: Optional[int] = None, collect_stats: bool = False, tile_cull: bool = True):
         self.scene = PackedScene(means, quats, scales, opacities, device)
         self.device = self.scene.device
         self.d = int(feature_dim)
@@ -36,6 +36,7 @@ class BackProjector:
         self.den = torch.full((n,), DEN_EPS, dtype=torch.float32, device=self.device)    # backproject.py:63
         self.kernel = {"auto": L.KERNEL_AUTO, "simt": L.KERNEL_SIMT, "tc": L.KERNEL_TC}[kernel]
         self.cap = cap_isects
+        self.tile_cull = bool(tile_cull)
         self._ws: Optional[torch.Tensor] = None
         self._fpack: Optional[torch.Tensor] = None
         self._stats = torch.zeros(4, dtype=torch.int64, device=self.device) if collect_stats else None
@@ -47,7 +48,7 @@ class BackProjector:
     def add_view(self, viewmat, K, width, height, feats: torch.Tensor, **cam_kw) -> View:
         assert feats.shape[-1] == self.d, f"feature dim {feats.shape[-1]} != {self.d}"
         cam = make_camera(viewmat, K, width, height, **cam_kw)
-        view = View(self.scene, cam, self.cap, self._ws)
+        view = View(self.scene, cam, self.cap, self._ws, self.tile_cull)
         self._ws, self.cap = view.ws, view.cap  # keep (possibly grown) workspace for the next view
         fp = None
         if self.kernel != L.KERNEL_SIMT:

@@ -91,7 +91,7 @@ int gwbp_pack_scene(int64_t n, const float *means, const float *quats, const flo
 }
 
 int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws, size_t ws_bytes, int64_t cap,
-                      void *stream, gwbp_view_info *info) {
+                      int32_t flags, void *stream, gwbp_view_info *info) {
     GWBP_REQUIRE(scene && ws && info, "view_prepare: NULL pointer");
     if (int rc = check_cam(cam)) return rc;
     gwbp_ws_layout L;
@@ -100,7 +100,8 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     GWBP_REQUIRE(scene->n == 0 || scene->geo, "scene.geo is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     WsDev w = ws_view(ws, L);
-    const CamDev cd = make_cam(*cam);
+    CamDev cd = make_cam(*cam);
+    cd.cull = (flags & GWBP_PREPARE_TILE_CULL) ? 1 : 0;
     const int64_t n = scene->n;
     memset(info, 0, sizeof(*info));
     info->tile_w = cd.tw; info->tile_h = cd.th;

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             bar_sync_alu();  // everyone has read s_unit before it is overwritten
             if (unit >= a.nunits) break;
             const int tile = unit / a.nchunks;
+            const bool need_den = (unit % a.nchunks) == 0;
             const int ty = tile / a.t.tw, tx = tile % a.t.tw;
             const int s = a.t.offsets[tile], e = a.t.offsets[tile + 1];
             const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                     r1 = a.t.grec[2 * (int64_t)id + 1];
                 }
                 if (q >= 1) mbar_wait(bar(Smem::w_free + warp), (q - 1) & 1);
-                if (unit % a.nchunks == 0) walked += min(MB, e - b);
+                if (need_den) walked += min(MB, e - b);
                 if (__all_sync(0xffffffffu, done)) {
                     // this warp's 32 pixels are finished: its slab of W is all zero
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -224,28 +225,37 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                         const uint32_t off = (uint32_t)j * A_SBO + wslab;
                         *reinterpret_cast<uint4 *>(smem + Smem::w_hi + off) = hi;
                         *reinterpret_cast<uint4 *>(smem + Smem::w_lo + off) = lo;
-                        // per-Gaussian sum over the warp's 32 pixels (den): butterfly transpose-reduce
-                        const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
-                        float v4[4], v2[2], v1;
+                        if (need_den) {
+                            // per-Gaussian sum over the warp's 32 pixels (den): butterfly transpose-reduce
+                            const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+                            float v4[4], v2[2], v1;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float send = b16 ? w[i] : w[i + 4];
-                            v4[i] = (b16 ? w[i + 4] : w[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
-                        }
+                            for (int i = 0; i < 4; ++i) {
+                                const float send = b16 ? w[i] : w[i + 4];
+                                v4[i] = (b16 ? w[i + 4] : w[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
+                            }
 #pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            const float send = b8 ? v4[i] : v4[i + 2];
-                            v2[i] = (b8 ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
-                        }
-                        {
-                            const float send = b4 ? v2[0] : v2[1];
-                            v1 = (b4 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, send, 4);
-                        }
-                        v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
-                        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-                        if ((lane & 3) == 0 && v1 > 0.0f) {
-                            const int gi = (b16 ? 4 : 0) + (b8 ? 2 : 0) + (b4 ? 1 : 0);
-                            atomicAdd(&rows[slot].den[8 * j + gi], v1);
+                            for (int i = 0; i < 2; ++i) {
+                                const float send = b8 ? v4[i] : v4[i + 2];
+                                v2[i] = (b8 ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
+                            }
+                            {
+                                const float send = b4 ? v2[0] : v2[1];
+                                v1 = (b4 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, send, 4);
+                            }
+                            v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+                            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+                            if ((lane & 3) == 0 && v1 > 0.0f) {
+                                const int gi = (b16 ? 4 : 0) + (b8 ? 2 : 0) + (b4 ? 1 : 0);
+                                atomicAdd(&rows[slot].den[8 * j + gi], v1);
+                            }
+                        } else {
+                            // den is accumulated by the chunk-0 unit of this tile; here only "row is live"
+                            unsigned nz = 0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) nz |= (w[i] > 0.0f ? 1u : 0u) << i;
+                            nz = __reduce_or_sync(0xffffffffu, nz);
+                            if (lane < 8 && (nz >> lane & 1u)) rows[slot].den[8 * j + lane] = 1.0f;
                         }
                     }
                 }
@@ -438,6 +448,47 @@ __global__ void __launch_bounds__(256) fpack_kernel(const float *__restrict__ F,
     }
 }
 
+
+// Planar input ([D,H,W] buffer exposed as a permuted [H,W,D] view: sW == 1, the reference's layout,
+// backproject.py:110-113).  Only pixels are contiguous, so one CTA takes one image row x 32 pixels
+// (two tiles) x one column chunk: every warp load is 128 contiguous bytes of one channel.
+__global__ void __launch_bounds__(256) fpack_planar_kernel(const float *__restrict__ F, int64_t sH, int64_t sD,
+                                                           int W, int H, int tw, int d, int dp, int nchunks,
+                                                           uint8_t *__restrict__ out) {
+    __shared__ float slab[NCMAX][33];  // [channel][pixel], +1 pad: conflict-free both ways
+    const int span = blockIdx.x, y = blockIdx.y, c = blockIdx.z;
+    const int ncols = min(NCMAX, dp - c * NCMAX);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int x = span * 32 + lane;
+    const bool xok = x < W;
+    for (int n = warp; n < ncols; n += 8) {
+        const int col = c * NCMAX + n;
+        slab[n][lane] = (xok && col < d) ? __ldg(F + y * sH + x + col * sD) : 0.0f;
+    }
+    __syncthreads();
+    const int ty = y / kTile, ks = y % kTile;
+    const uint32_t lbo = (uint32_t)(ncols / 8) * 128, part = (uint32_t)ncols * KSL * 2;
+    // item = (pixel 0..31, 8-column group): one 16-byte core-matrix row, hi and lo
+    for (int item = t; item < 32 * (ncols / 8); item += 256) {
+        const int px = item & 31, ng = item >> 5;
+        const int tx = span * 2 + (px >> 4), p = px & 15;
+        if (tx >= tw) continue;
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = slab[8 * ng + i][px];
+        uint4 hi, lo;
+        split_bf16x2(f[0], f[1], hi.x, lo.x);
+        split_bf16x2(f[2], f[3], hi.y, lo.y);
+        split_bf16x2(f[4], f[5], hi.z, lo.z);
+        split_bf16x2(f[6], f[7], hi.w, lo.w);
+        const int tile = ty * tw + tx;
+        uint8_t *blk = out + (int64_t)tile * kTilePix * dp * 4 + (int64_t)c * NCMAX * kTilePix * 4 + (int64_t)ks * part * 2;
+        const uint32_t off = (uint32_t)(p / 8) * lbo + (uint32_t)ng * 128 + (uint32_t)(p % 8) * 16;
+        *reinterpret_cast<uint4 *>(blk + off) = hi;
+        *reinterpret_cast<uint4 *>(blk + part + off) = lo;
+    }
+}
+
 }  // namespace
 
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -457,7 +508,17 @@ int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t 
     GWBP_REQUIRE(((uintptr_t)fpack & 127) == 0, "fpack must be 128-byte aligned");
     GWBP_REQUIRE(((uintptr_t)num & 15) == 0, "num must be 16-byte aligned");
     const int dp = round_up(d, 16), nchunks = (dp + NCMAX - 1) / NCMAX;
-    fpack_kernel<<<ntiles * nchunks, 256, 0, st>>>(F, sH, sW, sD, t.W, t.H, t.tw, d, dp, nchunks, (uint8_t *)fpack);
+    if (sW == 1 && sD != 1) {
+        // rows of the last tile row beyond H are never written by the planar kernel: they are only
+        // ever multiplied by zero weights, but must not hold NaN/Inf bit patterns -> clear once per view
+        if (t.H % kTile)
+            GWBP_CUDA_OK(cudaMemsetAsync((uint8_t *)fpack + (size_t)(t.th - 1) * t.tw * kTilePix * dp * 4, 0,
+                                         (size_t)t.tw * kTilePix * dp * 4, st));
+        dim3 grid((t.W + 31) / 32, t.H, nchunks);
+        fpack_planar_kernel<<<grid, 256, 0, st>>>(F, sH, sD, t.W, t.H, t.tw, d, dp, nchunks, (uint8_t *)fpack);
+    } else {
+        fpack_kernel<<<ntiles * nchunks, 256, 0, st>>>(F, sH, sW, sD, t.W, t.H, t.tw, d, dp, nchunks, (uint8_t *)fpack);
+    }
     GWBP_CUDA_OK(cudaGetLastError());
 
     TcArgs a;

@@ -44,6 +44,7 @@ struct CamDev {
     float lim_xp, lim_xn, lim_yp, lim_yn;
     float near_plane, far_plane, radius_clip, eps2d;
     int W, H, tw, th;
+    int cull;  // exact tile culling (GWBP_PREPARE_TILE_CULL)
 };
 
 // Typed view of the caller's workspace.

@@ -30,6 +30,7 @@ CamDev make_cam(const gwbp_camera &c) {
     d.lim_yp = ayp + t3y; d.lim_yn = ayn + t3y;
     d.near_plane = c.near_plane; d.far_plane = c.far_plane;
     d.radius_clip = c.radius_clip; d.eps2d = c.eps2d;
+    d.cull = 0;
     return d;
 }
 
@@ -80,6 +81,8 @@ int launch_pack_scene(int64_t n, const float *means, const float *quats, const f
 // ---------------------------------------------------------------------------------------------
 // tile rectangle of a projected Gaussian (gsplat isect_tiles)
 // ---------------------------------------------------------------------------------------------
+constexpr int kCoopTiles = 32;  // Gaussians covering more tiles than this are handled warp-wide
+
 __device__ __forceinline__ int clamp_tile(float f, int hi) {
     if (!(f > 0.0f)) return 0;
     if (f >= (float)hi) return hi;
@@ -95,6 +98,44 @@ __device__ __forceinline__ void tile_rect(float m2x, float m2y, int radius, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// exact tile culling (GWBP_PREPARE_TILE_CULL; mirrors oracle.c tile_hit / gsplat_oracle.tile_hit)
+// A (Gaussian, tile) pair is kept iff alpha = op*exp(-sigma) can reach 1/255 somewhere on the tile's
+// pixel-centre box: min_box sigma <= ln(255 op) + 0.01.  Dropped pairs have zero weight on every
+// pixel of the tile, so the accumulators are unchanged while the list to sort / walk shrinks ~40 %.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ln_approx(float x) {  // fixed-order fp32 series, x > 0
+    const unsigned bits = __float_as_uint(x);
+    const int e = (int)((bits >> 23) & 0xffu) - 127;
+    const float m = __uint_as_float((bits & 0x7fffffu) | 0x3f800000u);
+    const float s = __fdiv_rn(m - 1.0f, m + 1.0f);
+    const float s2 = s * s;
+    const float p = ((s2 * (1.0f / 7.0f) + 0.2f) * s2 + (1.0f / 3.0f)) * s2 + 1.0f;
+    return (float)e * 0.69314718f + (2.0f * s) * p;
+}
+__device__ __forceinline__ float cull_tau(float op) {
+    const float x = 255.0f * op;
+    return (x > 1.0f) ? ln_approx(x) + 0.01f : -1.0f;
+}
+__device__ __forceinline__ float quad(float A, float B, float C, float dx, float dy) {
+    return 0.5f * ((A * dx) * dx + (C * dy) * dy) + (B * dx) * dy;
+}
+__device__ __forceinline__ float clampf(float t, float lo, float hi) { return fminf(fmaxf(t, lo), hi); }
+__device__ __forceinline__ bool tile_hit(float gx, float gy, float A, float B, float C, float tau, int tx, int ty,
+                                         int W, int H) {
+    if (tau < 0.0f) return false;
+    const int xe = min(tx * kTile + kTile - 1, W - 1), ye = min(ty * kTile + kTile - 1, H - 1);
+    const float X0 = (float)(tx * kTile) + 0.5f, X1 = (float)xe + 0.5f;
+    const float Y0 = (float)(ty * kTile) + 0.5f, Y1 = (float)ye + 0.5f;
+    const float dx0 = gx - X1, dx1 = gx - X0, dy0 = gy - Y1, dy1 = gy - Y0;
+    if (dx0 <= 0.0f && dx1 >= 0.0f && dy0 <= 0.0f && dy1 >= 0.0f) return true;
+    float best = quad(A, B, C, dx0, clampf(__fdiv_rn(-(B * dx0), C), dy0, dy1));
+    best = fminf(best, quad(A, B, C, dx1, clampf(__fdiv_rn(-(B * dx1), C), dy0, dy1)));
+    best = fminf(best, quad(A, B, C, clampf(__fdiv_rn(-(B * dy0), A), dx0, dx1), dy0));
+    best = fminf(best, quad(A, B, C, clampf(__fdiv_rn(-(B * dy1), A), dx0, dx1), dy1));
+    return best <= tau;
+}
+
+// ---------------------------------------------------------------------------------------------
 // EWA projection: one thread per Gaussian
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) project_kernel(int64_t n, const float4 *__restrict__ geo0,
@@ -103,11 +144,12 @@ __global__ void __launch_bounds__(256) project_kernel(int64_t n, const float4 *_
                                                       unsigned long long *__restrict__ cnt,
                                                       float4 *__restrict__ rec) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    if (i == n) { cnt[n] = 0ull; return; }  // terminator so the exclusive scan yields the totals
-    const float4 a = geo0[i];
-    const float4 b4 = geo1[i];
-    const float2 c2 = geo2[i];
+    if (i == n) cnt[n] = 0ull;  // terminator so the exclusive scan yields the totals
+    const bool in_range = i < n;
+    const int64_t il = in_range ? i : 0;  // out-of-range lanes stay alive for the warp collectives below
+    const float4 a = n ? geo0[il] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b4 = n ? geo1[il] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float2 c2 = n ? geo2[il] : make_float2(0.f, 0.f);
     const float mx = a.x, my = a.y, mz = a.z;
     const float *V = cam.V;
     float p[3];
@@ -140,21 +182,50 @@ __global__ void __launch_bounds__(256) project_kernel(int64_t n, const float4 *_
     const float bb = 0.5f * (A + Cc);
     const float v1 = bb + __fsqrt_rn(fmaxf(0.01f, bb * bb - det));
     float rad = ceilf(3.0f * __fsqrt_rn(v1));
-    bool ok = (z >= cam.near_plane) && (z <= cam.far_plane) && (det > 0.0f) && isfinite(rad);
+    bool ok = in_range && (z >= cam.near_plane) && (z <= cam.far_plane) && (det > 0.0f) && isfinite(rad);
     ok = ok && (rad > cam.radius_clip);
     ok = ok && (m2x + rad > 0.0f) && (m2x - rad < cam.Wf) && (m2y + rad > 0.0f) && (m2y - rad < cam.Hf);
     ok = ok && isfinite(m2x) && isfinite(m2y) && isfinite(con_x) && isfinite(con_y) && isfinite(con_z);
-    unsigned long long c = 0ull;
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    unsigned tiles = 0;
     if (ok) {
         const int radius = (int)fminf(rad, 16777216.0f);
-        int x0, x1, y0, y1;
         tile_rect(m2x, m2y, radius, cam.tw, cam.th, x0, x1, y0, y1);
-        const unsigned tiles = (unsigned)((y1 - y0) * (x1 - x0));
-        c = (1ull << 32) | (unsigned long long)tiles;
+        tiles = (unsigned)((y1 - y0) * (x1 - x0));
         rec[2 * i] = make_float4(m2x, m2y, a.w, z);
         rec[2 * i + 1] = make_float4(con_x, con_y, con_z, __int_as_float(radius));
     }
-    cnt[i] = c;
+    if (cam.cull) {
+        // count only the tiles the footprint can reach; big rectangles are counted by the whole warp
+        const float tau = cull_tau(a.w);
+        const int bw = x1 - x0;
+        const bool big = ok && tiles > kCoopTiles;
+        if (ok && !big) {
+            unsigned hits = 0;
+            for (unsigned k = 0; k < tiles; ++k)
+                hits += tile_hit(m2x, m2y, con_x, con_y, con_z, tau, x0 + (int)(k % bw), y0 + (int)(k / bw), cam.W, cam.H);
+            tiles = hits;
+        }
+        const int lane = threadIdx.x & 31;
+        unsigned m = __ballot_sync(0xffffffffu, big);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float sx = __shfl_sync(0xffffffffu, m2x, src), sy = __shfl_sync(0xffffffffu, m2y, src);
+            const float sA = __shfl_sync(0xffffffffu, con_x, src), sB = __shfl_sync(0xffffffffu, con_y, src);
+            const float sC = __shfl_sync(0xffffffffu, con_z, src), st = __shfl_sync(0xffffffffu, tau, src);
+            const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
+            const int sbw = __shfl_sync(0xffffffffu, bw, src);
+            const unsigned snt = __shfl_sync(0xffffffffu, tiles, src);
+            unsigned hits = 0;
+            for (unsigned k = lane; k < snt; k += 32)
+                hits += tile_hit(sx, sy, sA, sB, sC, st, sx0 + (int)(k % sbw), sy0 + (int)(k / sbw), cam.W, cam.H);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
+            if (lane == src) tiles = hits;
+        }
+    }
+    if (in_range) cnt[i] = ok ? ((1ull << 32) | (unsigned long long)tiles) : 0ull;
 }
 
 int launch_project(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cudaStream_t st) {
@@ -169,8 +240,6 @@ int launch_project(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cuda
 // ---------------------------------------------------------------------------------------------
 // emission: packed records + (tile|depth) keys in ascending-Gaussian, row-major-tile order
 // ---------------------------------------------------------------------------------------------
-constexpr int kCoopTiles = 32;  // Gaussians covering more tiles than this are emitted warp-wide
-
 __global__ void __launch_bounds__(256) emit_kernel(int64_t n, CamDev cam, const unsigned long long *__restrict__ cnt,
                                                    const unsigned long long *__restrict__ scan,
                                                    const float4 *__restrict__ rec, float4 *__restrict__ grec,
@@ -182,6 +251,7 @@ __global__ void __launch_bounds__(256) emit_kernel(int64_t n, CamDev cam, const 
     bool vis = false;
     int x0 = 0, x1 = 0, y0 = 0, y1 = 0, pos = 0;
     long long base = 0, dbits = 0;
+    float gx = 0.f, gy = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, tau = -1.f;
     if (i < n && (cnt[i] >> 32)) {
         vis = true;
         const unsigned long long sc = scan[i];
@@ -193,20 +263,24 @@ __global__ void __launch_bounds__(256) emit_kernel(int64_t n, CamDev cam, const 
         grec[2 * (int64_t)pos] = make_float4(r0.x, r0.y, r0.z, __int_as_float((int)i));
         grec[2 * (int64_t)pos + 1] = make_float4(r1.x, r1.y, r1.z, r0.w);
         radii[pos] = radius;
-        tpg[pos] = (y1 - y0) * (x1 - x0);
+        tpg[pos] = (int)(cnt[i] & 0xffffffffull);
         dbits = (long long)(unsigned)__float_as_int(r0.w);
+        gx = r0.x; gy = r0.y; cA = r1.x; cB = r1.y; cC = r1.z;
+        tau = cull_tau(r0.z);
     }
     const int bw = x1 - x0;
     const int ntiles = (y1 - y0) * bw;
     const bool big = vis && ntiles > kCoopTiles;
     if (vis && !big) {
+        long long o = base;
         for (int k = 0; k < ntiles; ++k) {
-            const long long o = base + k;
+            const int ty = y0 + k / bw, tx = x0 + k % bw;
+            if (cam.cull && !tile_hit(gx, gy, cA, cB, cC, tau, tx, ty, cam.W, cam.H)) continue;
             if (o < cap) {
-                const int ty = y0 + k / bw, tx = x0 + k % bw;
                 keys[o] = ((long long)(ty * cam.tw + tx) << 32) | dbits;
                 vals[o] = pos;
             }
+            ++o;
         }
     }
     unsigned m = __ballot_sync(0xffffffffu, big);
@@ -216,14 +290,22 @@ __global__ void __launch_bounds__(256) emit_kernel(int64_t n, CamDev cam, const 
         const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
         const int sbw = __shfl_sync(0xffffffffu, bw, src), snt = __shfl_sync(0xffffffffu, ntiles, src);
         const int spos = __shfl_sync(0xffffffffu, pos, src);
-        const long long sbase = __shfl_sync(0xffffffffu, base, src), sd = __shfl_sync(0xffffffffu, dbits, src);
-        for (int k = lane; k < snt; k += 32) {
-            const long long o = sbase + k;
-            if (o < cap) {
-                const int ty = sy0 + k / sbw, tx = sx0 + k % sbw;
+        long long sbase = __shfl_sync(0xffffffffu, base, src);
+        const long long sd = __shfl_sync(0xffffffffu, dbits, src);
+        const float sx = __shfl_sync(0xffffffffu, gx, src), sy = __shfl_sync(0xffffffffu, gy, src);
+        const float sA = __shfl_sync(0xffffffffu, cA, src), sB = __shfl_sync(0xffffffffu, cB, src);
+        const float sC = __shfl_sync(0xffffffffu, cC, src), st = __shfl_sync(0xffffffffu, tau, src);
+        for (int k0 = 0; k0 < snt; k0 += 32) {  // ordered warp compaction keeps row-major tile order
+            const int k = k0 + lane;
+            const int ty = sy0 + k / sbw, tx = sx0 + k % sbw;
+            const bool hit = (k < snt) && (!cam.cull || tile_hit(sx, sy, sA, sB, sC, st, tx, ty, cam.W, cam.H));
+            const unsigned hm = __ballot_sync(0xffffffffu, hit);
+            const long long o = sbase + __popc(hm & ((1u << lane) - 1u));
+            if (hit && o < cap) {
                 keys[o] = ((long long)(ty * cam.tw + tx) << 32) | sd;
                 vals[o] = spos;
             }
+            sbase += __popc(hm);
         }
     }
 }

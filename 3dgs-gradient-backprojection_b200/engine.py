@@ -85,7 +85,10 @@ class View:
     (= everything one `rasterization()` call computes before compositing)."""
 
     def __init__(self, scene: PackedScene, cam: L.Camera, cap_isects: Optional[int] = None,
-                 workspace: Optional[torch.Tensor] = None):
+                 workspace: Optional[torch.Tensor] = None, tile_cull: bool = False):
+        """tile_cull=False: the intersection list is gsplat-1.4.0's (bit-exact `meta`).
+        tile_cull=True : pairs that cannot reach alpha >= 1/255 on the tile are dropped before the sort
+        (identical accumulators, less work) -- the BackProjector default."""
         self.scene, self.cam = scene, cam
         n = scene.n
         cap = int(cap_isects) if cap_isects else max(1 << 16, 8 * n)
@@ -96,7 +99,8 @@ class View:
             info = L.ViewInfo()
             with torch.cuda.device(scene.device):
                 rc = L.lib().gwbp_view_prepare(C.byref(scene.c), C.byref(cam), workspace.data_ptr(), workspace.numel(),
-                                               cap, _stream_ptr(scene.device), C.byref(info))
+                                               cap, L.PREPARE_TILE_CULL if tile_cull else L.PREPARE_GSPLAT_EXACT,
+                                               _stream_ptr(scene.device), C.byref(info))
             if rc == -2:  # capacity: the library told us the exact need; grow once and redo
                 cap = int(info.n_isects * 1.25) + 1024
                 workspace = None

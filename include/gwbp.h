@@ -38,12 +38,17 @@ extern "C" {
 #endif
 
 #define GWBP_TILE 16
-#define GWBP_ABI_VERSION 1
+#define GWBP_ABI_VERSION 2
 
 /* kernel selection for gwbp_backproject_view */
 #define GWBP_KERNEL_AUTO 0
 #define GWBP_KERNEL_SIMT 1 /* fp32 CUDA-core contraction (truth kernel, any D) */
 #define GWBP_KERNEL_TC 2   /* tcgen05 split-bf16 contraction, fp32 TMEM accumulation */
+
+/* flags for gwbp_view_prepare */
+#define GWBP_PREPARE_GSPLAT_EXACT 0 /* intersection list == gsplat-1.4.0 isect_tiles (bounding-square test) */
+#define GWBP_PREPARE_TILE_CULL 1    /* additionally drop (Gaussian, tile) pairs whose alpha stays < 1/255 on the
+                                       whole tile: same accumulators, ~40 % shorter list to sort and walk */
 
 typedef struct gwbp_scene {
     int64_t n;        /* Gaussians */
@@ -97,7 +102,7 @@ int gwbp_pack_scene(int64_t n, const float *means, const float *quats, const flo
 
 /* project + bin + sort one camera into `ws`.  Synchronises `stream` once (intersection count). */
 int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam_host, void *ws, size_t ws_bytes,
-                      int64_t cap_isects, void *stream, gwbp_view_info *info_host);
+                      int64_t cap_isects, int32_t flags, void *stream, gwbp_view_info *info_host);
 
 /* bytes of the packed bf16 feature buffer the GWBP_KERNEL_TC path needs (0 if D unsupported) */
 size_t gwbp_fpack_bytes(int32_t width, int32_t height, int32_t d);

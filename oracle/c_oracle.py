@@ -27,7 +27,7 @@ def lib():
             build()
         L = C.CDLL(_SO)
         L.orc_view_create.restype = C.c_void_p
-        L.orc_view_create.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_float] * 4
+        L.orc_view_create.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int]
         L.orc_view_destroy.argtypes = [C.c_void_p]
         L.orc_view_counts.argtypes = [C.c_void_p] * 5
         L.orc_view_export.argtypes = [C.c_void_p] * 9
@@ -56,12 +56,12 @@ class View:
     """One camera's projected + binned + sorted scene."""
 
     def __init__(self, means, quats, scales, opacities, viewmat, K, width, height,
-                 near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3):
+                 near_plane=0.01, far_plane=1e10, radius_clip=0.0, eps2d=0.3, cull=False):
         self._keep = [_f32(means), _f32(quats), _f32(scales), _f32(opacities), _f32(viewmat), _f32(K)]
         self.n = self._keep[0].shape[0]
         self.width, self.height = int(width), int(height)
         self._h = lib().orc_view_create(self.n, *[_p(a) for a in self._keep], self.width, self.height,
-                                        near_plane, far_plane, radius_clip, eps2d)
+                                        near_plane, far_plane, radius_clip, eps2d, int(bool(cull)))
         nv, ni, tw, th = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32()
         lib().orc_view_counts(self._h, C.byref(nv), C.byref(ni), C.byref(tw), C.byref(th))
         self.n_vis, self.n_isects, self.tile_width, self.tile_height = nv.value, ni.value, tw.value, th.value

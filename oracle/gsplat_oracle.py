@@ -161,7 +161,46 @@ def tile_bounds(means2d, radii, width, height):
     return x0, x1, y0, y1, tw, th
 
 
-def isect_tiles(proj, width, height):
+def ln_approx(x):
+    """Fixed-order fp32 series for ln(x), x > 0 (no libm, so CPU and GPU agree bit for bit):
+    x = m 2^e, s = (m-1)/(m+1), ln x = e ln2 + 2 s (1 + s^2/3 + s^4/5 + s^6/7)."""
+    x = np.asarray(x, F32)
+    bits = x.view(np.uint32)
+    e = ((bits >> 23) & 0xFF).astype(np.int32) - 127
+    m = ((bits & np.uint32(0x7FFFFF)) | np.uint32(0x3F800000)).view(F32)
+    s = (m - F32(1.0)) / (m + F32(1.0))
+    s2 = s * s
+    p = ((s2 * F32(1.0 / 7.0) + F32(0.2)) * s2 + F32(1.0 / 3.0)) * s2 + F32(1.0)
+    return e.astype(F32) * F32(0.69314718) + (F32(2.0) * s) * p
+
+
+def tile_hit(gx, gy, A, B, C, op, tx, ty, width, height):
+    """Exact tile culling (extension, see oracle.c): can alpha reach 1/255 anywhere on the tile's
+    pixel-centre box?  All arguments are per-pair fp32 / int arrays."""
+    with np.errstate(all="ignore"):
+        x255 = F32(255.0) * op
+        tau = np.where(x255 > 1, ln_approx(np.where(x255 > 1, x255, F32(2.0))) + F32(0.01), F32(-1.0)).astype(F32)
+        xe = np.minimum(tx * TILE + TILE - 1, width - 1)
+        ye = np.minimum(ty * TILE + TILE - 1, height - 1)
+        X0, X1 = (tx * TILE).astype(F32) + F32(0.5), xe.astype(F32) + F32(0.5)
+        Y0, Y1 = (ty * TILE).astype(F32) + F32(0.5), ye.astype(F32) + F32(0.5)
+        dx0, dx1, dy0, dy1 = gx - X1, gx - X0, gy - Y1, gy - Y0
+        inside = (dx0 <= 0) & (dx1 >= 0) & (dy0 <= 0) & (dy1 >= 0)
+
+        def q(dx, dy):
+            return F32(0.5) * ((A * dx) * dx + (C * dy) * dy) + (B * dx) * dy
+
+        def clamp(t, lo, hi):
+            return np.minimum(np.maximum(t, lo), hi)
+
+        best = q(dx0, clamp(-(B * dx0) / C, dy0, dy1))
+        best = np.minimum(best, q(dx1, clamp(-(B * dx1) / C, dy0, dy1)))
+        best = np.minimum(best, q(clamp(-(B * dy0) / A, dx0, dx1), dy0))
+        best = np.minimum(best, q(clamp(-(B * dy1) / A, dx0, dx1), dy1))
+    return (tau >= 0) & (inside | (best <= tau))
+
+
+def isect_tiles(proj, width, height, opacities=None, cull=False):
     """Packed (visible-only, ascending Gaussian index) intersection list, sorted by
     (tile, depth bits) with a STABLE sort (= cub::DeviceRadixSort).  Returns dict with
     gaussian_ids[nnz], tiles_per_gauss[nnz], isect_ids[I] int64, flatten_ids[I] int32
@@ -181,6 +220,13 @@ def isect_tiles(proj, width, height):
     tx = np.repeat(x0.astype(np.int64), tpg) + local % np.maximum(bw, 1)
     tile_id = ty * tw + tx
     depth_bits = np.repeat(dep.view(np.int32).astype(np.int64), tpg)
+    if cull:
+        con = proj["conics"][gids][flat]
+        hit = tile_hit(m2[flat, 0], m2[flat, 1], con[:, 0], con[:, 1], con[:, 2],
+                       np.asarray(opacities, F32)[gids][flat], tx, ty, width, height)
+        tile_id, depth_bits, flat = tile_id[hit], depth_bits[hit], flat[hit]
+        tpg = np.bincount(flat, minlength=len(gids)).astype(np.int32)
+        total = int(hit.sum())
     keys = (tile_id << 32) | depth_bits
     order = np.argsort(keys, kind="stable")
     isect_ids = keys[order]
@@ -263,20 +309,20 @@ def _tile_pixels(ty, tx, width, height):
 # 4. the hot path: per-view back-projection == d/d(colors) of <render(colors), F>
 #    (backproject.py:115-151 through gsplat's rasterize_to_pixels_bwd v_colors; §9.5-9.6)
 # --------------------------------------------------------------------------------------
-def view_geometry(means, quats, scales, viewmat, K, width, height, **kw):
+def view_geometry(means, quats, scales, viewmat, K, width, height, opacities=None, cull=False, **kw):
     cov = quat_scale_to_covar(quats, scales)
     proj = project(means, cov, viewmat, K, width, height, **kw)
-    isect = isect_tiles(proj, width, height)
+    isect = isect_tiles(proj, width, height, opacities, cull)
     return proj, isect
 
 
 def backproject_view(means, quats, scales, opacities, viewmat, K, width, height, feats, dtype=F32,
-                     stats=None, **kw):
+                     stats=None, cull=False, **kw):
     """num_v[g,:] = sum_p w(g,p) F[p,:],  den_v[g] = sum_p w(g,p)  for one view.
     `feats` is [H,W,D] (any strides).  Returns (num_v [N,D] fp64, den_v [N] fp64)."""
     n = means.shape[0]
     d = feats.shape[2]
-    proj, isect = view_geometry(means, quats, scales, viewmat, K, width, height, **kw)
+    proj, isect = view_geometry(means, quats, scales, viewmat, K, width, height, opacities, cull, **kw)
     num = np.zeros((n, d), np.float64)
     den = np.zeros(n, np.float64)
     gids = isect["gaussian_ids"]

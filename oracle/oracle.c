@@ -28,7 +28,7 @@
 #define NPIX 256
 
 typedef struct OrcView {
-    int n, W, H, tw, th;
+    int n, W, H, tw, th, cull;
     int64_t n_vis, n_isects;
     /* unpacked [n] */
     int32_t *radii;
@@ -124,6 +124,44 @@ static inline int clampi(float f, int hi) {
     return (int)f;
 }
 
+/* --- optional exact tile culling (an extension over gsplat-1.4.0, OFF by default) -------------------
+ * A (Gaussian, tile) pair is dropped when alpha = op*exp(-sigma) < 1/255 on the whole pixel-centre
+ * box of the tile, i.e. when min_box sigma > ln(255 op).  Dropped pairs have zero weight on every
+ * pixel, so num/den are unchanged; the intersection list shrinks ~2x.  ln() is a fixed-order fp32
+ * series (no libm) so that CPU and GPU agree bit for bit; +0.01 keeps the test conservative. */
+static inline float orc_ln_approx(float x) { /* x > 0 */
+    uint32_t bits; memcpy(&bits, &x, 4);
+    const int e = (int)((bits >> 23) & 0xff) - 127;
+    const uint32_t mb = (bits & 0x7fffffu) | 0x3f800000u;
+    float m; memcpy(&m, &mb, 4);
+    const float s = (m - 1.0f) / (m + 1.0f);
+    const float s2 = s * s;
+    const float p = ((s2 * (1.0f / 7.0f) + 0.2f) * s2 + (1.0f / 3.0f)) * s2 + 1.0f;
+    return (float)e * 0.69314718f + (2.0f * s) * p;
+}
+static inline float orc_tau(float op) {
+    const float x = 255.0f * op;
+    return (x > 1.0f) ? orc_ln_approx(x) + 0.01f : -1.0f;
+}
+static inline float orc_q(float A, float B, float C, float dx, float dy) {
+    return 0.5f * ((A * dx) * dx + (C * dy) * dy) + (B * dx) * dy;
+}
+static inline float orc_clampf(float t, float lo, float hi) { return fminf(fmaxf(t, lo), hi); }
+static int tile_hit(float gx, float gy, float A, float B, float C, float tau, int tx, int ty, int W, int H) {
+    if (tau < 0.0f) return 0;
+    const int xe = (tx * TILE + TILE - 1 < W - 1) ? tx * TILE + TILE - 1 : W - 1;
+    const int ye = (ty * TILE + TILE - 1 < H - 1) ? ty * TILE + TILE - 1 : H - 1;
+    const float X0 = (float)(tx * TILE) + 0.5f, X1 = (float)xe + 0.5f;
+    const float Y0 = (float)(ty * TILE) + 0.5f, Y1 = (float)ye + 0.5f;
+    const float dx0 = gx - X1, dx1 = gx - X0, dy0 = gy - Y1, dy1 = gy - Y0;
+    if (dx0 <= 0.0f && dx1 >= 0.0f && dy0 <= 0.0f && dy1 >= 0.0f) return 1;
+    float best = orc_q(A, B, C, dx0, orc_clampf(-(B * dx0) / C, dy0, dy1));
+    best = fminf(best, orc_q(A, B, C, dx1, orc_clampf(-(B * dx1) / C, dy0, dy1)));
+    best = fminf(best, orc_q(A, B, C, orc_clampf(-(B * dy0) / A, dx0, dx1), dy0));
+    best = fminf(best, orc_q(A, B, C, orc_clampf(-(B * dy1) / A, dx0, dx1), dy1));
+    return best <= tau;
+}
+
 static void tile_rect(const OrcView *v, int g, int *x0, int *x1, int *y0, int *y1) {
     const float tr = (float)v->radii[g] / (float)TILE;
     const float txc = v->means2d[2 * (size_t)g] / (float)TILE, tyc = v->means2d[2 * (size_t)g + 1] / (float)TILE;
@@ -170,7 +208,15 @@ static void bin_and_sort(OrcView *v) {
         if (v->radii[g] > 0) {
             int x0, x1, y0, y1;
             tile_rect(v, g, &x0, &x1, &y0, &y1);
-            total += (int64_t)(y1 - y0) * (x1 - x0);
+            if (!v->cull) {
+                total += (int64_t)(y1 - y0) * (x1 - x0);
+            } else {
+                const float tau = orc_tau(v->opac[g]);
+                for (int i = y0; i < y1; ++i)
+                    for (int j = x0; j < x1; ++j)
+                        total += tile_hit(v->means2d[2 * (size_t)g], v->means2d[2 * (size_t)g + 1], v->conics[3 * (size_t)g],
+                                          v->conics[3 * (size_t)g + 1], v->conics[3 * (size_t)g + 2], tau, j, i, v->W, v->H);
+            }
             v->gaussian_ids[k++] = g;
         }
     v->n_vis = nvis; v->n_isects = total;
@@ -182,8 +228,12 @@ static void bin_and_sort(OrcView *v) {
         int x0, x1, y0, y1;
         tile_rect(v, g, &x0, &x1, &y0, &y1);
         int32_t dbits; memcpy(&dbits, &v->depths[g], 4);
+        const float tau = orc_tau(v->opac[g]);
         for (int i = y0; i < y1; ++i)
             for (int j = x0; j < x1; ++j) {
+                if (v->cull && !tile_hit(v->means2d[2 * (size_t)g], v->means2d[2 * (size_t)g + 1], v->conics[3 * (size_t)g],
+                                         v->conics[3 * (size_t)g + 1], v->conics[3 * (size_t)g + 2], tau, j, i, v->W, v->H))
+                    continue;
                 v->isect_ids[pos] = ((int64_t)(i * v->tw + j) << 32) | (int64_t)(uint32_t)dbits;
                 v->flatten_ids[pos] = (int32_t)r;
                 ++pos;
@@ -202,8 +252,9 @@ static void bin_and_sort(OrcView *v) {
 
 OrcView *orc_view_create(int n, const float *means, const float *quats, const float *scales, const float *opac,
                          const float *viewmat, const float *K, int W, int H, float near_plane, float far_plane,
-                         float radius_clip, float eps2d) {
+                         float radius_clip, float eps2d, int cull) {
     OrcView *v = (OrcView *)calloc(1, sizeof(OrcView));
+    v->cull = cull;
     v->n = n; v->W = W; v->H = H; v->tw = (W + TILE - 1) / TILE; v->th = (H + TILE - 1) / TILE;
     v->opac = opac;
     v->radii = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n ? n : 1));

@@ -65,17 +65,19 @@ def case(gwbp):
 def test_native_library_is_loaded(gwbp):
     import ctypes
     assert torch.cuda.is_available()
-    assert gwbp._lib.lib().gwbp_abi_version() == 1
+    assert gwbp._lib.lib().gwbp_abi_version() == gwbp._lib.ABI_VERSION
     with open("/proc/self/maps") as f:
         assert "libgwbp.so" in f.read()
 
 
-def test_integer_stages_bit_exact(gwbp, coracle, case):
+@pytest.mark.parametrize("cull", [False, True])
+def test_integer_stages_bit_exact(gwbp, coracle, case, cull):
+    """cull=False: gsplat-1.4.0 isect_tiles semantics; cull=True: the exact tile-culling extension."""
     sc, vm, K, _ = case
     scene = gwbp.PackedScene(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities))
     for v in range(vm.shape[0]):
-        view = gwbp.View(scene, gwbp.make_camera(vm[v], K, 96, 64))
-        e = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, 96, 64).export()
+        view = gwbp.View(scene, gwbp.make_camera(vm[v], K, 96, 64), tile_cull=cull)
+        e = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, 96, 64, cull=cull).export()
         m = view.meta()
         gids = m["gaussian_ids"].cpu().numpy()
         assert np.array_equal(gids, e["gaussian_ids"])
@@ -95,12 +97,13 @@ def test_integer_stages_bit_exact_config_S_and_odd_sizes(gwbp, coracle):
         sc = S.make_scene(n, seed)
         vm, K = S.make_cameras(2, W, H, seed)
         scene = gwbp.PackedScene(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities))
-        view = gwbp.View(scene, gwbp.make_camera(vm[1], K, W, H))
-        e = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[1], K, W, H).export()
-        m = view.meta()
-        assert np.array_equal(m["isect_ids"].cpu().numpy(), e["isect_ids"]), (n, W, H)
-        assert np.array_equal(m["flatten_ids"].cpu().numpy(), e["flatten_ids"]), (n, W, H)
-        assert np.array_equal(m["isect_offsets"].cpu().numpy()[0], e["isect_offsets"]), (n, W, H)
+        for cull in (False, True):
+            view = gwbp.View(scene, gwbp.make_camera(vm[1], K, W, H), tile_cull=cull)
+            e = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[1], K, W, H, cull=cull).export()
+            m = view.meta()
+            assert np.array_equal(m["isect_ids"].cpu().numpy(), e["isect_ids"]), (n, W, H, cull)
+            assert np.array_equal(m["flatten_ids"].cpu().numpy(), e["flatten_ids"]), (n, W, H, cull)
+            assert np.array_equal(m["isect_offsets"].cpu().numpy()[0], e["isect_offsets"]), (n, W, H, cull)
 
 
 @pytest.mark.parametrize("kernel", ["simt", "auto"])
@@ -136,6 +139,22 @@ def test_backprojection_feature_dims(gwbp, coracle, noracle, d):
     for kernel in ("simt", "auto"):
         bp = _gpu_job(gwbp, sc, vm, K, 64, 48, feats, d, kernel)
         _check_features(bp, num_o, den_o, noracle)
+
+
+def test_tile_culling_does_not_change_the_accumulators(gwbp, case):
+    """Culled (Gaussian, tile) pairs have zero weight on every pixel: same rows, same sums."""
+    sc, vm, K, feats = case
+    out = []
+    for cull in (False, True):
+        bp = gwbp.BackProjector(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities), 8, kernel="simt",
+                                collect_stats=True, tile_cull=cull)
+        for v in range(vm.shape[0]):
+            bp.add_view(vm[v], K, 96, 64, _feat_dev(feats[v]))
+        out.append((bp.num.clone(), bp.den.clone(), bp.stats()))
+    (n0, d0, s0), (n1, d1, s1) = out
+    assert torch.allclose(n0, n1, rtol=1e-5, atol=1e-6) and torch.allclose(d0, d1, rtol=1e-5, atol=1e-7)
+    assert s0["rows_nonzero"] == s1["rows_nonzero"] and s1["entries_walked"] < s0["entries_walked"]
+    assert torch.equal(d0 > 1e-12, d1 > 1e-12)
 
 
 def test_feature_strides_do_not_matter(gwbp, case):

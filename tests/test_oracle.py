@@ -36,6 +36,30 @@ def test_numpy_and_c_oracle_agree_bit_exact_on_integer_stages(case, noracle, cor
                               noracle.quat_scale_to_covar(sc.quats, sc.scales).view(np.int32))
 
 
+def test_tile_culling_extension(case, noracle, coracle):
+    """The exact tile-culling extension: both restatements agree bit for bit, the culled list is a
+    sub-list of gsplat's, and no (pixel, Gaussian) pair with non-zero weight is lost."""
+    sc, vm, K, feats = case
+    for v in range(vm.shape[0]):
+        _, full = noracle.view_geometry(sc.means, sc.quats, sc.scales, vm[v], K, 96, 64)
+        _, cut = noracle.view_geometry(sc.means, sc.quats, sc.scales, vm[v], K, 96, 64, sc.opacities, True)
+        cv = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, 96, 64, cull=True)
+        e = cv.export()
+        for k in ("isect_ids", "flatten_ids", "isect_offsets"):
+            assert np.array_equal(e[k], cut[k]), k
+        assert cut["n_isects"] < full["n_isects"]
+        pairs_full = set(zip(full["isect_ids"].tolist(), full["flatten_ids"].tolist()))
+        assert set(zip(cut["isect_ids"].tolist(), cut["flatten_ids"].tolist())) <= pairs_full
+        a0 = np.zeros((sc.n, 8)); d0 = np.zeros(sc.n)
+        a1 = np.zeros((sc.n, 8)); d1 = np.zeros(sc.n)
+        s0 = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, 96, 64).backproject(np.asarray(feats[v]), a0, d0)
+        s1 = cv.backproject(np.asarray(feats[v]), a1, d1)
+        assert s0["rows_nonzero"] == s1["rows_nonzero"] and s0["pairs"] == s1["pairs"]
+        assert np.allclose(a0, a1, rtol=1e-12, atol=1e-14) and np.allclose(d0, d1, rtol=1e-12, atol=1e-14)
+    x = np.array([1.0001, 1.5, 2.0, 3.7, 100.0, 254.9], np.float32)
+    assert np.abs(noracle.ln_approx(x) - np.log(x.astype(np.float64))).max() < 2e-5
+
+
 def test_numpy_and_c_oracle_agree_on_accumulators(case, noracle, coracle):
     sc, vm, K, feats = case
     num_c, den_c, _ = oracle_job(coracle, sc, vm, K, 96, 64, feats, 8)
