@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgwbp.so")
 
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL = 0, 1
 
 
@@ -26,8 +26,10 @@ class Camera(C.Structure):
 
 
 class WsLayout(C.Structure):
-    _fields_ = [(k, C.c_size_t) for k in ("total", "cnt", "scan", "rec", "grec", "radii", "tiles_per_gauss", "keys0",
-                                          "keys1", "vals0", "vals1", "offsets", "stats", "cub_tmp", "cub_tmp_bytes")]
+    _fields_ = [(k, C.c_size_t) for k in ("total", "cnt", "scan", "rec", "mask", "grec", "pmask", "radii",
+                                          "tiles_per_gauss", "dkeys0", "dkeys1", "dvals0", "dvals1", "cnt2", "base2",
+                                          "tkeys0", "tkeys1", "tvals0", "tvals1", "offsets", "stats", "cub_tmp",
+                                          "cub_tmp_bytes")]
 
 
 class ViewInfo(C.Structure):

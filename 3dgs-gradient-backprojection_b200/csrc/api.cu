@@ -36,7 +36,7 @@ static TileCtx tile_ctx(const gwbp_camera *cam, const void *ws, const gwbp_ws_la
     WsDev w = ws_view(const_cast<void *>(ws), L);
     TileCtx t;
     t.grec = w.grec;
-    t.flatten = w.vals[info->sorted_buf];
+    t.flatten = w.tvals[info->sorted_buf];
     t.offsets = w.offsets;
     t.scratch = w.stats;
     t.W = cam->width; t.H = cam->height;
@@ -66,13 +66,21 @@ int gwbp_workspace_layout(int64_t n, int32_t width, int32_t height, int64_t cap,
     L->cnt = o; o = align_up(o + sizeof(unsigned long long) * n1);
     L->scan = o; o = align_up(o + sizeof(unsigned long long) * n1);
     L->rec = o; o = align_up(o + sizeof(float4) * 2 * n1);
+    L->mask = o; o = align_up(o + sizeof(unsigned long long) * n1);
     L->grec = o; o = align_up(o + sizeof(float4) * 2 * n1);
+    L->pmask = o; o = align_up(o + sizeof(unsigned long long) * n1);
     L->radii = o; o = align_up(o + sizeof(int) * n1);
     L->tiles_per_gauss = o; o = align_up(o + sizeof(int) * n1);
-    L->keys0 = o; o = align_up(o + sizeof(long long) * c1);
-    L->keys1 = o; o = align_up(o + sizeof(long long) * c1);
-    L->vals0 = o; o = align_up(o + sizeof(int) * c1);
-    L->vals1 = o; o = align_up(o + sizeof(int) * c1);
+    L->dkeys0 = o; o = align_up(o + sizeof(unsigned) * n1);
+    L->dkeys1 = o; o = align_up(o + sizeof(unsigned) * n1);
+    L->dvals0 = o; o = align_up(o + sizeof(unsigned) * n1);
+    L->dvals1 = o; o = align_up(o + sizeof(unsigned) * n1);
+    L->cnt2 = o; o = align_up(o + sizeof(unsigned) * n1);
+    L->base2 = o; o = align_up(o + sizeof(unsigned) * n1);
+    L->tkeys0 = o; o = align_up(o + sizeof(unsigned) * c1);
+    L->tkeys1 = o; o = align_up(o + sizeof(unsigned) * c1);
+    L->tvals0 = o; o = align_up(o + sizeof(int) * c1);
+    L->tvals1 = o; o = align_up(o + sizeof(int) * c1);
     L->offsets = o; o = align_up(o + sizeof(int) * (tiles + 1));
     L->stats = o; o = align_up(o + sizeof(long long) * 16);
     L->cub_tmp_bytes = binning_tmp_bytes(n, c1);
@@ -119,11 +127,17 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
                   (long long)info->n_isects, (long long)cap);
         return -2;
     }
-    if (int rc = launch_emit(n, cd, w, cap, st)) return rc;
+    if (int rc = launch_compact(n, cd, w, st)) return rc;
+    int dsel = 0;
+    if (int rc = launch_depth_sort(info->n_vis, w, &dsel, st)) return rc;
+    const unsigned *order = w.dvals[dsel];
+    if (int rc = launch_gather_counts(info->n_vis, order, w, st)) return rc;
+    if (int rc = launch_scan_counts(info->n_vis, w, st)) return rc;
+    if (int rc = launch_emit(info->n_vis, cd, order, w, cap, st)) return rc;
     int sorted = 0;
-    if (int rc = launch_sort(info->n_isects, tile_bits_for(cd.tw * cd.th), w, &sorted, st)) return rc;
+    if (int rc = launch_tile_sort(info->n_isects, tile_bits_for(cd.tw * cd.th), w, &sorted, st)) return rc;
     info->sorted_buf = sorted;
-    return launch_offsets(info->n_isects, cd.tw * cd.th, w.keys[sorted], w.offsets, st);
+    return launch_offsets(info->n_isects, cd.tw * cd.th, w.tkeys[sorted], w.offsets, st);
 }
 
 size_t gwbp_fpack_bytes(int32_t width, int32_t height, int32_t d) {

@@ -1,10 +1,11 @@
-// Stage 2: prefix scan of per-Gaussian (visible, tiles) counts, stable radix sort of
-// (tile | depth-bits) keys, per-tile range finding.  Integer work, bit-exact against the oracle.
-// Semantics: gsplat-1.4.0 isect_tiles / cub radix sort / isect_offset_encode.
+// Stage 2: prefix scans, the two stable radix sorts and per-tile range finding.  Integer work,
+// bit-exact against the oracle.  Semantics: gsplat-1.4.0 isect_tiles / radix sort /
+// isect_offset_encode -- the sorted (tile, depth, packed index) order is the same,
+// but instead of one 45-bit sort over all I intersections (6 onesweep passes x 12 B x 2) the n_vis
+// visible Gaussians are depth-sorted first (4 passes x 8 B) and, after emission in depth order, a
+// stable sort on the <= 13 tile bits (2 passes x 8 B) finishes the job.
 //
-// The scan and the sort are CUB device primitives (part of the CUDA toolkit, like cuBLAS for a
-// plain GEMM); they are HBM-bound passes over 8 B (scan) and 12 B (sort) records.  Only the bits
-// that can differ are sorted: 32 depth bits + floor(log2(tiles))+1 tile bits.
+// Scan and sort are CUB device primitives (part of the CUDA toolkit, like cuBLAS for a plain GEMM).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -29,16 +30,17 @@ int launch_scan(int64_t n, WsDev ws, cudaStream_t st) {
     return 0;
 }
 
-int launch_sort(int64_t n_isects, int tile_bits, WsDev ws, int *sorted_buf, cudaStream_t st) {
+template <typename K, typename V>
+static int sort_pairs(K *k0, K *k1, V *v0, V *v1, int64_t n, int bits, WsDev ws, int *sorted_buf, cudaStream_t st) {
     *sorted_buf = 0;
-    if (n_isects == 0) return 0;
-    cub::DoubleBuffer<long long> k(ws.keys[0], ws.keys[1]);
-    cub::DoubleBuffer<int> v(ws.vals[0], ws.vals[1]);
+    if (n == 0) return 0;
+    cub::DoubleBuffer<K> k(k0, k1);
+    cub::DoubleBuffer<V> v(v0, v1);
     size_t need = 0;
-    GWBP_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, need, k, v, (long long)n_isects, 0, 32 + tile_bits, st));
+    GWBP_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, need, k, v, (long long)n, 0, bits, st));
     GWBP_REQUIRE(need <= ws.cub_tmp_bytes, "sort scratch too small: %zu > %zu", need, ws.cub_tmp_bytes);
     size_t b = ws.cub_tmp_bytes;
-    GWBP_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.cub_tmp, b, k, v, (long long)n_isects, 0, 32 + tile_bits, st));
+    GWBP_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.cub_tmp, b, k, v, (long long)n, 0, bits, st));
     *sorted_buf = k.selector;
     if (v.selector != k.selector) {
         set_error("radix sort returned mismatched key/value buffers");
@@ -47,22 +49,42 @@ int launch_sort(int64_t n_isects, int tile_bits, WsDev ws, int *sorted_buf, cuda
     return 0;
 }
 
+// stage 1: visible Gaussians by depth bits (stable: ties keep ascending packed index)
+int launch_depth_sort(int64_t n_vis, WsDev ws, int *sorted_buf, cudaStream_t st) {
+    return sort_pairs(ws.dkeys[0], ws.dkeys[1], ws.dvals[0], ws.dvals[1], n_vis, 32, ws, sorted_buf, st);
+}
+
+// exclusive offsets of the per-Gaussian tile counts in depth order (n_vis + 1 entries)
+int launch_scan_counts(int64_t n_vis, WsDev ws, cudaStream_t st) {
+    size_t need = 0;
+    GWBP_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, need, ws.cnt2, ws.base2, (long long)(n_vis + 1), st));
+    GWBP_REQUIRE(need <= ws.cub_tmp_bytes, "scan scratch too small: %zu > %zu", need, ws.cub_tmp_bytes);
+    size_t b = ws.cub_tmp_bytes;
+    GWBP_CUDA_OK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp, b, ws.cnt2, ws.base2, (long long)(n_vis + 1), st));
+    return 0;
+}
+
+// stage 2: intersections (already in depth order) by tile id only -- stable, floor(log2(tiles))+1 bits
+int launch_tile_sort(int64_t n_isects, int tile_bits, WsDev ws, int *sorted_buf, cudaStream_t st) {
+    return sort_pairs(ws.tkeys[0], ws.tkeys[1], ws.tvals[0], ws.tvals[1], n_isects, tile_bits, ws, sorted_buf, st);
+}
+
 __global__ void __launch_bounds__(256) offsets_kernel(int64_t n_isects, int n_tiles,
-                                                      const long long *__restrict__ keys, int *__restrict__ offsets) {
+                                                      const unsigned *__restrict__ keys, int *__restrict__ offsets) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n_isects == 0) {
         if (i <= n_tiles) offsets[i] = 0;
         return;
     }
     if (i >= n_isects) return;
-    const int cur = (int)(keys[i] >> 32);
-    const int prev = i ? (int)(keys[i - 1] >> 32) : -1;
+    const int cur = (int)keys[i];
+    const int prev = i ? (int)keys[i - 1] : -1;
     for (int t = prev + 1; t <= cur; ++t) offsets[t] = (int)i;
     if (i == n_isects - 1)
         for (int t = cur + 1; t <= n_tiles; ++t) offsets[t] = (int)n_isects;
 }
 
-int launch_offsets(int64_t n_isects, int n_tiles, const long long *keys, int *offsets, cudaStream_t st) {
+int launch_offsets(int64_t n_isects, int n_tiles, const unsigned *keys, int *offsets, cudaStream_t st) {
     const int64_t work = n_isects > 0 ? n_isects : (int64_t)n_tiles + 1;
     offsets_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(n_isects, n_tiles, keys, offsets);
     GWBP_CUDA_OK(cudaGetLastError());

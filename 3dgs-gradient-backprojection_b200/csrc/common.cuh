@@ -49,11 +49,13 @@ struct CamDev {
 
 // Typed view of the caller's workspace.
 struct WsDev {
-    unsigned long long *cnt, *scan;
+    unsigned long long *cnt, *scan, *mask, *pmask;
     float4 *rec, *grec;
     int *radii, *tiles_per_gauss;
-    long long *keys[2];
-    int *vals[2];
+    unsigned *dkeys[2], *dvals[2];  // depth sort of the visible Gaussians
+    unsigned *cnt2, *base2;         // tile counts / exclusive offsets in depth order
+    unsigned *tkeys[2];             // tile id per intersection
+    int *tvals[2];                  // packed Gaussian index per intersection (flatten_ids)
     int *offsets;
     long long *stats;
     void *cub_tmp;
@@ -65,14 +67,18 @@ inline WsDev ws_view(void *base, const gwbp_ws_layout &L) {
     WsDev w;
     w.cnt = (unsigned long long *)(b + L.cnt);
     w.scan = (unsigned long long *)(b + L.scan);
+    w.mask = (unsigned long long *)(b + L.mask);
+    w.pmask = (unsigned long long *)(b + L.pmask);
     w.rec = (float4 *)(b + L.rec);
     w.grec = (float4 *)(b + L.grec);
     w.radii = (int *)(b + L.radii);
     w.tiles_per_gauss = (int *)(b + L.tiles_per_gauss);
-    w.keys[0] = (long long *)(b + L.keys0);
-    w.keys[1] = (long long *)(b + L.keys1);
-    w.vals[0] = (int *)(b + L.vals0);
-    w.vals[1] = (int *)(b + L.vals1);
+    w.dkeys[0] = (unsigned *)(b + L.dkeys0); w.dkeys[1] = (unsigned *)(b + L.dkeys1);
+    w.dvals[0] = (unsigned *)(b + L.dvals0); w.dvals[1] = (unsigned *)(b + L.dvals1);
+    w.cnt2 = (unsigned *)(b + L.cnt2);
+    w.base2 = (unsigned *)(b + L.base2);
+    w.tkeys[0] = (unsigned *)(b + L.tkeys0); w.tkeys[1] = (unsigned *)(b + L.tkeys1);
+    w.tvals[0] = (int *)(b + L.tvals0); w.tvals[1] = (int *)(b + L.tvals1);
     w.offsets = (int *)(b + L.offsets);
     w.stats = (long long *)(b + L.stats);
     w.cub_tmp = (void *)(b + L.cub_tmp);
@@ -86,11 +92,15 @@ CamDev make_cam(const gwbp_camera &c);
 int launch_pack_scene(int64_t n, const float *means, const float *quats, const float *scales,
                       const float *opac, void *geo, cudaStream_t st);
 int launch_project(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cudaStream_t st);
-int launch_emit(int64_t n, const CamDev &cam, WsDev ws, int64_t cap, cudaStream_t st);
+int launch_compact(int64_t n, const CamDev &cam, WsDev ws, cudaStream_t st);
+int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, cudaStream_t st);
+int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, cudaStream_t st);
 size_t binning_tmp_bytes(int64_t n, int64_t cap);
 int launch_scan(int64_t n, WsDev ws, cudaStream_t st);
-int launch_sort(int64_t n_isects, int tile_bits, WsDev ws, int *sorted_buf, cudaStream_t st);
-int launch_offsets(int64_t n_isects, int n_tiles, const long long *keys, int *offsets, cudaStream_t st);
+int launch_depth_sort(int64_t n_vis, WsDev ws, int *sorted_buf, cudaStream_t st);
+int launch_scan_counts(int64_t n_vis, WsDev ws, cudaStream_t st);
+int launch_tile_sort(int64_t n_isects, int tile_bits, WsDev ws, int *sorted_buf, cudaStream_t st);
+int launch_offsets(int64_t n_isects, int n_tiles, const unsigned *tkeys, int *offsets, cudaStream_t st);
 
 struct TileCtx {
     const float4 *grec;

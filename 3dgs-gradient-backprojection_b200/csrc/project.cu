@@ -7,7 +7,11 @@
 // fully_fused_projection_packed_fwd + isect_tiles, i.e. what every
 // rasterization() call of backproject.py:89,115,133 does first.
 //
-// B200 notes: all three kernels are HBM-bound streaming kernels.  The scene is repacked ONCE
+// Binning is a two-stage sort (binning.cu): the ~n_vis visible Gaussians are sorted by depth bits
+// first, intersections are emitted in that order, and a stable 13-bit sort on the tile id finishes;
+// the result is identical to gsplat's 45-bit (tile|depth) sort of all intersections at ~1/5 the traffic.
+//
+// B200 notes: all kernels here are HBM-bound streaming kernels.  The scene is repacked ONCE
 // into SoA float4/float4/float2 (40 B/Gaussian, 16-byte coalesced loads); projection reads those
 // 40 B, writes an 8-byte count for every Gaussian and a 32-byte record for visible ones only.
 #include "common.cuh"
@@ -81,7 +85,7 @@ int launch_pack_scene(int64_t n, const float *means, const float *quats, const f
 // ---------------------------------------------------------------------------------------------
 // tile rectangle of a projected Gaussian (gsplat isect_tiles)
 // ---------------------------------------------------------------------------------------------
-constexpr int kCoopTiles = 32;  // Gaussians covering more tiles than this are handled warp-wide
+constexpr int kMaskTiles = 64;  // rectangles up to this many tiles are handled by one thread (hit mask = 1 word)
 
 __device__ __forceinline__ int clamp_tile(float f, int hi) {
     if (!(f > 0.0f)) return 0;
@@ -112,27 +116,42 @@ __device__ __forceinline__ float ln_approx(float x) {  // fixed-order fp32 serie
     const float p = ((s2 * (1.0f / 7.0f) + 0.2f) * s2 + (1.0f / 3.0f)) * s2 + 1.0f;
     return (float)e * 0.69314718f + (2.0f * s) * p;
 }
-__device__ __forceinline__ float cull_tau(float op) {
+struct CullGauss {  // per-Gaussian constants of the tile test
+    float gx, gy, A, B, C, kx, ky, tau;
+};
+__device__ __forceinline__ CullGauss cull_setup(float gx, float gy, float A, float B, float C, float op) {
+    CullGauss g;
+    g.gx = gx; g.gy = gy; g.A = A; g.B = B; g.C = C;
+    g.kx = -__fdiv_rn(B, C);  // argmin over dy of the quadratic at fixed dx is kx*dx
+    g.ky = -__fdiv_rn(B, A);
     const float x = 255.0f * op;
-    return (x > 1.0f) ? ln_approx(x) + 0.01f : -1.0f;
+    g.tau = (x > 1.0f) ? ln_approx(x) + 0.01f : -1.0f;
+    return g;
 }
-__device__ __forceinline__ float quad(float A, float B, float C, float dx, float dy) {
-    return 0.5f * ((A * dx) * dx + (C * dy) * dy) + (B * dx) * dy;
+__device__ __forceinline__ float quad(const CullGauss &g, float dx, float dy) {
+    return 0.5f * ((g.A * dx) * dx + (g.C * dy) * dy) + (g.B * dx) * dy;
 }
 __device__ __forceinline__ float clampf(float t, float lo, float hi) { return fminf(fmaxf(t, lo), hi); }
-__device__ __forceinline__ bool tile_hit(float gx, float gy, float A, float B, float C, float tau, int tx, int ty,
-                                         int W, int H) {
-    if (tau < 0.0f) return false;
+__device__ __forceinline__ bool tile_hit(const CullGauss &g, int tx, int ty, int W, int H) {
+    if (g.tau < 0.0f) return false;
     const int xe = min(tx * kTile + kTile - 1, W - 1), ye = min(ty * kTile + kTile - 1, H - 1);
     const float X0 = (float)(tx * kTile) + 0.5f, X1 = (float)xe + 0.5f;
     const float Y0 = (float)(ty * kTile) + 0.5f, Y1 = (float)ye + 0.5f;
-    const float dx0 = gx - X1, dx1 = gx - X0, dy0 = gy - Y1, dy1 = gy - Y0;
+    const float dx0 = g.gx - X1, dx1 = g.gx - X0, dy0 = g.gy - Y1, dy1 = g.gy - Y0;
     if (dx0 <= 0.0f && dx1 >= 0.0f && dy0 <= 0.0f && dy1 >= 0.0f) return true;
-    float best = quad(A, B, C, dx0, clampf(__fdiv_rn(-(B * dx0), C), dy0, dy1));
-    best = fminf(best, quad(A, B, C, dx1, clampf(__fdiv_rn(-(B * dx1), C), dy0, dy1)));
-    best = fminf(best, quad(A, B, C, clampf(__fdiv_rn(-(B * dy0), A), dx0, dx1), dy0));
-    best = fminf(best, quad(A, B, C, clampf(__fdiv_rn(-(B * dy1), A), dx0, dx1), dy1));
-    return best <= tau;
+    float best = quad(g, dx0, clampf(g.kx * dx0, dy0, dy1));
+    best = fminf(best, quad(g, dx1, clampf(g.kx * dx1, dy0, dy1)));
+    best = fminf(best, quad(g, clampf(g.ky * dy0, dx0, dx1), dy0));
+    best = fminf(best, quad(g, clampf(g.ky * dy1, dx0, dx1), dy1));
+    return best <= g.tau;
+}
+__device__ __forceinline__ CullGauss shfl_cull(const CullGauss &g, int src) {
+    CullGauss r;
+    r.gx = __shfl_sync(0xffffffffu, g.gx, src); r.gy = __shfl_sync(0xffffffffu, g.gy, src);
+    r.A = __shfl_sync(0xffffffffu, g.A, src); r.B = __shfl_sync(0xffffffffu, g.B, src);
+    r.C = __shfl_sync(0xffffffffu, g.C, src); r.kx = __shfl_sync(0xffffffffu, g.kx, src);
+    r.ky = __shfl_sync(0xffffffffu, g.ky, src); r.tau = __shfl_sync(0xffffffffu, g.tau, src);
+    return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -142,7 +161,8 @@ __global__ void __launch_bounds__(256) project_kernel(int64_t n, const float4 *_
                                                       const float4 *__restrict__ geo1,
                                                       const float2 *__restrict__ geo2, CamDev cam,
                                                       unsigned long long *__restrict__ cnt,
-                                                      float4 *__restrict__ rec) {
+                                                      float4 *__restrict__ rec,
+                                                      unsigned long long *__restrict__ mask) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == n) cnt[n] = 0ull;  // terminator so the exclusive scan yields the totals
     const bool in_range = i < n;
@@ -196,30 +216,30 @@ __global__ void __launch_bounds__(256) project_kernel(int64_t n, const float4 *_
         rec[2 * i + 1] = make_float4(con_x, con_y, con_z, __int_as_float(radius));
     }
     if (cam.cull) {
-        // count only the tiles the footprint can reach; big rectangles are counted by the whole warp
-        const float tau = cull_tau(a.w);
+        // Test every tile of the bounding rectangle ONCE: rectangles of <= 64 tiles keep the result as a
+        // bit mask for the emission pass; larger ones are counted (and later re-tested) by the whole warp.
+        const CullGauss cg = cull_setup(m2x, m2y, con_x, con_y, con_z, a.w);
         const int bw = x1 - x0;
-        const bool big = ok && tiles > kCoopTiles;
+        const bool big = ok && tiles > kMaskTiles;
         if (ok && !big) {
-            unsigned hits = 0;
+            unsigned long long mk = 0ull;
             for (unsigned k = 0; k < tiles; ++k)
-                hits += tile_hit(m2x, m2y, con_x, con_y, con_z, tau, x0 + (int)(k % bw), y0 + (int)(k / bw), cam.W, cam.H);
-            tiles = hits;
+                if (tile_hit(cg, x0 + (int)(k % bw), y0 + (int)(k / bw), cam.W, cam.H)) mk |= 1ull << k;
+            mask[i] = mk;
+            tiles = (unsigned)__popcll(mk);
         }
         const int lane = threadIdx.x & 31;
         unsigned m = __ballot_sync(0xffffffffu, big);
         while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;
-            const float sx = __shfl_sync(0xffffffffu, m2x, src), sy = __shfl_sync(0xffffffffu, m2y, src);
-            const float sA = __shfl_sync(0xffffffffu, con_x, src), sB = __shfl_sync(0xffffffffu, con_y, src);
-            const float sC = __shfl_sync(0xffffffffu, con_z, src), st = __shfl_sync(0xffffffffu, tau, src);
+            const CullGauss sg = shfl_cull(cg, src);
             const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
             const int sbw = __shfl_sync(0xffffffffu, bw, src);
             const unsigned snt = __shfl_sync(0xffffffffu, tiles, src);
             unsigned hits = 0;
             for (unsigned k = lane; k < snt; k += 32)
-                hits += tile_hit(sx, sy, sA, sB, sC, st, sx0 + (int)(k % sbw), sy0 + (int)(k / sbw), cam.W, cam.H);
+                hits += tile_hit(sg, sx0 + (int)(k % sbw), sy0 + (int)(k / sbw), cam.W, cam.H);
 #pragma unroll
             for (int o = 16; o; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
             if (lane == src) tiles = hits;
@@ -232,88 +252,124 @@ int launch_project(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cuda
     const float4 *g0 = (const float4 *)geo;
     const float4 *g1 = g0 + n;
     const float2 *g2 = (const float2 *)(g1 + n);
-    project_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(n, g0, g1, g2, cam, ws.cnt, ws.rec);
+    project_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(n, g0, g1, g2, cam, ws.cnt, ws.rec, ws.mask);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// emission: packed records + (tile|depth) keys in ascending-Gaussian, row-major-tile order
+// compaction of the visible Gaussians (ascending index = gsplat's packed order) + depth-sort input
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) emit_kernel(int64_t n, CamDev cam, const unsigned long long *__restrict__ cnt,
-                                                   const unsigned long long *__restrict__ scan,
-                                                   const float4 *__restrict__ rec, float4 *__restrict__ grec,
-                                                   int *__restrict__ radii, int *__restrict__ tpg,
-                                                   long long *__restrict__ keys, int *__restrict__ vals,
-                                                   int64_t cap) {
+__global__ void __launch_bounds__(256) compact_kernel(int64_t n, int cull, const unsigned long long *__restrict__ cnt,
+                                                      const unsigned long long *__restrict__ scan,
+                                                      const float4 *__restrict__ rec,
+                                                      const unsigned long long *__restrict__ mask,
+                                                      float4 *__restrict__ grec, int *__restrict__ radii,
+                                                      int *__restrict__ tpg, unsigned long long *__restrict__ pmask,
+                                                      unsigned *__restrict__ dkeys, unsigned *__restrict__ dvals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long c = cnt[i];
+    if (!(c >> 32)) return;
+    const int pos = (int)(scan[i] >> 32);
+    const float4 r0 = rec[2 * i], r1 = rec[2 * i + 1];
+    grec[2 * (int64_t)pos] = make_float4(r0.x, r0.y, r0.z, __int_as_float((int)i));
+    grec[2 * (int64_t)pos + 1] = make_float4(r1.x, r1.y, r1.z, r0.w);
+    radii[pos] = __float_as_int(r1.w);
+    tpg[pos] = (int)(c & 0xffffffffull);
+    if (cull) pmask[pos] = mask[i];
+    dkeys[pos] = __float_as_uint(r0.w);  // depth > 0: the bit pattern orders like the value
+    dvals[pos] = (unsigned)pos;
+}
+
+int launch_compact(int64_t n, const CamDev &cam, WsDev ws, cudaStream_t st) {
+    if (n == 0) return 0;
+    compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, cam.cull, ws.cnt, ws.scan, ws.rec, ws.mask, ws.grec,
+                                                              ws.radii, ws.tiles_per_gauss, ws.pmask, ws.dkeys[0],
+                                                              ws.dvals[0]);
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) gather_counts_kernel(int64_t n_vis, const unsigned *__restrict__ order,
+                                                            const int *__restrict__ tpg, unsigned *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_vis) out[i] = (unsigned)tpg[order[i]];
+    if (i == n_vis) out[i] = 0u;
+}
+
+int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, cudaStream_t st) {
+    gather_counts_kernel<<<(unsigned)((n_vis + 1 + 255) / 256), 256, 0, st>>>(n_vis, order, ws.tiles_per_gauss, ws.cnt2);
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// emission in DEPTH order: thread i takes the i-th nearest visible Gaussian and writes one
+// (tile id, packed index) pair per tile it reaches.  A stable sort on the tile id alone then yields
+// exactly the order of gsplat's 64-bit (tile | depth) sort (ties: ascending packed index).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) emit_kernel(int64_t n_vis, CamDev cam, const unsigned *__restrict__ order,
+                                                   const unsigned *__restrict__ base2,
+                                                   const float4 *__restrict__ grec, const int *__restrict__ radii,
+                                                   const unsigned long long *__restrict__ pmask,
+                                                   unsigned *__restrict__ tkeys, int *__restrict__ tvals, int64_t cap) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    bool vis = false;
+    bool vis = i < n_vis;
     int x0 = 0, x1 = 0, y0 = 0, y1 = 0, pos = 0;
-    long long base = 0, dbits = 0;
-    float gx = 0.f, gy = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, tau = -1.f;
-    if (i < n && (cnt[i] >> 32)) {
-        vis = true;
-        const unsigned long long sc = scan[i];
-        pos = (int)(sc >> 32);
-        base = (long long)(sc & 0xffffffffull);
-        const float4 r0 = rec[2 * i], r1 = rec[2 * i + 1];
-        const int radius = __float_as_int(r1.w);
-        tile_rect(r0.x, r0.y, radius, cam.tw, cam.th, x0, x1, y0, y1);
-        grec[2 * (int64_t)pos] = make_float4(r0.x, r0.y, r0.z, __int_as_float((int)i));
-        grec[2 * (int64_t)pos + 1] = make_float4(r1.x, r1.y, r1.z, r0.w);
-        radii[pos] = radius;
-        tpg[pos] = (int)(cnt[i] & 0xffffffffull);
-        dbits = (long long)(unsigned)__float_as_int(r0.w);
-        gx = r0.x; gy = r0.y; cA = r1.x; cB = r1.y; cC = r1.z;
-        tau = cull_tau(r0.z);
+    long long base = 0;
+    CullGauss cg = {};
+    if (vis) {
+        pos = (int)order[i];
+        base = base2[i];
+        const float4 r0 = grec[2 * (int64_t)pos], r1 = grec[2 * (int64_t)pos + 1];
+        tile_rect(r0.x, r0.y, radii[pos], cam.tw, cam.th, x0, x1, y0, y1);
+        if (cam.cull) cg = cull_setup(r0.x, r0.y, r1.x, r1.y, r1.z, r0.z);
     }
     const int bw = x1 - x0;
     const int ntiles = (y1 - y0) * bw;
-    const bool big = vis && ntiles > kCoopTiles;
+    const bool big = vis && ntiles > kMaskTiles;
     if (vis && !big) {
         long long o = base;
-        for (int k = 0; k < ntiles; ++k) {
-            const int ty = y0 + k / bw, tx = x0 + k % bw;
-            if (cam.cull && !tile_hit(gx, gy, cA, cB, cC, tau, tx, ty, cam.W, cam.H)) continue;
-            if (o < cap) {
-                keys[o] = ((long long)(ty * cam.tw + tx) << 32) | dbits;
-                vals[o] = pos;
+        if (cam.cull) {
+            unsigned long long mk = pmask[pos];
+            while (mk) {
+                const int k = __ffsll((long long)mk) - 1;
+                mk &= mk - 1;
+                if (o < cap) { tkeys[o] = (unsigned)((y0 + k / bw) * cam.tw + x0 + k % bw); tvals[o] = pos; }
+                ++o;
             }
-            ++o;
+        } else {
+            for (int k = 0; k < ntiles; ++k, ++o)
+                if (o < cap) { tkeys[o] = (unsigned)((y0 + k / bw) * cam.tw + x0 + k % bw); tvals[o] = pos; }
         }
     }
     unsigned m = __ballot_sync(0xffffffffu, big);
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
+        const CullGauss sg = shfl_cull(cg, src);
         const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
         const int sbw = __shfl_sync(0xffffffffu, bw, src), snt = __shfl_sync(0xffffffffu, ntiles, src);
         const int spos = __shfl_sync(0xffffffffu, pos, src);
         long long sbase = __shfl_sync(0xffffffffu, base, src);
-        const long long sd = __shfl_sync(0xffffffffu, dbits, src);
-        const float sx = __shfl_sync(0xffffffffu, gx, src), sy = __shfl_sync(0xffffffffu, gy, src);
-        const float sA = __shfl_sync(0xffffffffu, cA, src), sB = __shfl_sync(0xffffffffu, cB, src);
-        const float sC = __shfl_sync(0xffffffffu, cC, src), st = __shfl_sync(0xffffffffu, tau, src);
-        for (int k0 = 0; k0 < snt; k0 += 32) {  // ordered warp compaction keeps row-major tile order
+        for (int k0 = 0; k0 < snt; k0 += 32) {  // ordered warp compaction
             const int k = k0 + lane;
             const int ty = sy0 + k / sbw, tx = sx0 + k % sbw;
-            const bool hit = (k < snt) && (!cam.cull || tile_hit(sx, sy, sA, sB, sC, st, tx, ty, cam.W, cam.H));
+            const bool hit = (k < snt) && (!cam.cull || tile_hit(sg, tx, ty, cam.W, cam.H));
             const unsigned hm = __ballot_sync(0xffffffffu, hit);
             const long long o = sbase + __popc(hm & ((1u << lane) - 1u));
-            if (hit && o < cap) {
-                keys[o] = ((long long)(ty * cam.tw + tx) << 32) | sd;
-                vals[o] = spos;
-            }
+            if (hit && o < cap) { tkeys[o] = (unsigned)(ty * cam.tw + tx); tvals[o] = spos; }
             sbase += __popc(hm);
         }
     }
 }
 
-int launch_emit(int64_t n, const CamDev &cam, WsDev ws, int64_t cap, cudaStream_t st) {
-    if (n == 0) return 0;
-    emit_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, cam, ws.cnt, ws.scan, ws.rec, ws.grec, ws.radii,
-                                                           ws.tiles_per_gauss, ws.keys[0], ws.vals[0], cap);
+int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, cudaStream_t st) {
+    if (n_vis == 0) return 0;
+    emit_kernel<<<(unsigned)((n_vis + 255) / 256), 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.pmask,
+                                                               ws.tkeys[0], ws.tvals[0], cap);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }

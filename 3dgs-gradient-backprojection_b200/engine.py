@@ -131,9 +131,12 @@ class View:
         g = self.grec()
         nv, ni = self.n_vis, self.n_isects
         sb = self.info.sorted_buf
-        keys = self._win(self.layout.keys1 if sb else self.layout.keys0, ni, torch.int64)
-        vals = self._win(self.layout.vals1 if sb else self.layout.vals0, ni, torch.int32)
+        tiles = self._win(self.layout.tkeys1 if sb else self.layout.tkeys0, ni, torch.int32)
+        vals = self._win(self.layout.tvals1 if sb else self.layout.tvals0, ni, torch.int32)
         th, tw = self.info.tile_h, self.info.tile_w
+        # gsplat's int64 keys (tile << 32 | depth bits), rebuilt from the two-stage sort's outputs
+        depth_bits = g[:, 7].contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        keys = (tiles.to(torch.int64) << 32) | depth_bits[vals.to(torch.int64)]
         return {
             "camera_ids": torch.zeros(nv, dtype=torch.int64, device=self.ws.device),
             "gaussian_ids": g[:, 3].contiguous().view(torch.int32).to(torch.int64),

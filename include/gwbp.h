@@ -38,7 +38,7 @@ extern "C" {
 #endif
 
 #define GWBP_TILE 16
-#define GWBP_ABI_VERSION 2
+#define GWBP_ABI_VERSION 3
 
 /* kernel selection for gwbp_backproject_view */
 #define GWBP_KERNEL_AUTO 0
@@ -69,11 +69,17 @@ typedef struct gwbp_ws_layout {
     size_t cnt;       /* uint64 [n+1]   (visible<<32 | tiles) per Gaussian */
     size_t scan;      /* uint64 [n+1]   exclusive prefix of cnt */
     size_t rec;       /* float4 [2*n]   unpacked projection records */
+    size_t mask;      /* uint64 [n]     unpacked tile-hit masks (tile culling) */
     size_t grec;      /* float4 [2*n]   packed records: (mean2d.xy, opacity, gaussian_id bits), (conic.xyz, depth) */
+    size_t pmask;     /* uint64 [n]     packed tile-hit masks */
     size_t radii;     /* int32  [n]     packed radii */
     size_t tiles_per_gauss; /* int32 [n] packed */
-    size_t keys0, keys1;    /* int64 [cap]  isect_ids double buffer */
-    size_t vals0, vals1;    /* int32 [cap]  flatten_ids double buffer */
+    size_t dkeys0, dkeys1;  /* uint32 [n]  depth bits of the visible Gaussians (sort double buffer) */
+    size_t dvals0, dvals1;  /* uint32 [n]  packed index */
+    size_t cnt2;      /* uint32 [n+1]   tile counts in depth order */
+    size_t base2;     /* uint32 [n+1]   exclusive prefix of cnt2 */
+    size_t tkeys0, tkeys1;  /* uint32 [cap] tile id per intersection (sort double buffer) */
+    size_t tvals0, tvals1;  /* int32  [cap] flatten_ids: packed index per intersection */
     size_t offsets;   /* int32  [tiles+1] isect_offsets (+ terminator = n_isects) */
     size_t stats;     /* int64  [16]    device counters */
     size_t cub_tmp;   /* scratch for scan / sort */
@@ -84,7 +90,7 @@ typedef struct gwbp_view_info {
     int64_t n_vis, n_isects;
     int64_t cap_isects; /* the capacity the workspace layout was computed with */
     int32_t tile_w, tile_h;
-    int32_t sorted_buf; /* which of keys0/keys1, vals0/vals1 holds the sorted result */
+    int32_t sorted_buf; /* which of tkeys0/tkeys1, tvals0/tvals1 holds the sorted result */
     int32_t reserved;
 } gwbp_view_info;
 

@@ -193,10 +193,11 @@ def tile_hit(gx, gy, A, B, C, op, tx, ty, width, height):
         def clamp(t, lo, hi):
             return np.minimum(np.maximum(t, lo), hi)
 
-        best = q(dx0, clamp(-(B * dx0) / C, dy0, dy1))
-        best = np.minimum(best, q(dx1, clamp(-(B * dx1) / C, dy0, dy1)))
-        best = np.minimum(best, q(clamp(-(B * dy0) / A, dx0, dx1), dy0))
-        best = np.minimum(best, q(clamp(-(B * dy1) / A, dx0, dx1), dy1))
+        kx, ky = -(B / C), -(B / A)  # argmin of the quadratic along an edge: dy = kx*dx, dx = ky*dy
+        best = q(dx0, clamp(kx * dx0, dy0, dy1))
+        best = np.minimum(best, q(dx1, clamp(kx * dx1, dy0, dy1)))
+        best = np.minimum(best, q(clamp(ky * dy0, dx0, dx1), dy0))
+        best = np.minimum(best, q(clamp(ky * dy1, dx0, dx1), dy1))
     return (tau >= 0) & (inside | (best <= tau))
 
 

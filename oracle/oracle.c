@@ -155,10 +155,11 @@ static int tile_hit(float gx, float gy, float A, float B, float C, float tau, in
     const float Y0 = (float)(ty * TILE) + 0.5f, Y1 = (float)ye + 0.5f;
     const float dx0 = gx - X1, dx1 = gx - X0, dy0 = gy - Y1, dy1 = gy - Y0;
     if (dx0 <= 0.0f && dx1 >= 0.0f && dy0 <= 0.0f && dy1 >= 0.0f) return 1;
-    float best = orc_q(A, B, C, dx0, orc_clampf(-(B * dx0) / C, dy0, dy1));
-    best = fminf(best, orc_q(A, B, C, dx1, orc_clampf(-(B * dx1) / C, dy0, dy1)));
-    best = fminf(best, orc_q(A, B, C, orc_clampf(-(B * dy0) / A, dx0, dx1), dy0));
-    best = fminf(best, orc_q(A, B, C, orc_clampf(-(B * dy1) / A, dx0, dx1), dy1));
+    const float kx = -(B / C), ky = -(B / A); /* argmin of the quadratic along an edge: dy = kx*dx, dx = ky*dy */
+    float best = orc_q(A, B, C, dx0, orc_clampf(kx * dx0, dy0, dy1));
+    best = fminf(best, orc_q(A, B, C, dx1, orc_clampf(kx * dx1, dy0, dy1)));
+    best = fminf(best, orc_q(A, B, C, orc_clampf(ky * dy0, dx0, dx1), dy0));
+    best = fminf(best, orc_q(A, B, C, orc_clampf(ky * dy1, dx0, dx1), dy1));
     return best <= tau;
 }
 
