@@ -8,9 +8,10 @@
 // MMAs are issued per K-step (hi*hi + hi*lo + lo*hi), so the contraction carries ~2^-16 relative
 // error -- the 1e-4 parity bar is not reachable with plain bf16 operands (8 bits).
 //
-// Work unit = (tile, 256-column chunk of D): D=512 is two units per tile, each regenerating W (the
-// weight generation is cheaper than the 3 x 16 MMAs it feeds) so that the [128 x 256] fp32 accumulator
-// can be double buffered in the 512 TMEM columns.
+// Work unit = one tile.  D is processed in chunks of <= 256 columns: for every batch of 128 Gaussians the
+// weights are generated ONCE and the MMA loops over the chunks, alternating between the two
+// [128 x 256] fp32 accumulators in the 512 TMEM columns, so the epilogue of chunk c overlaps the MMAs
+// of chunk c+1 (or of the next batch's chunk 0).
 // Data flow of one persistent CTA (1 per SM, 480 threads, warp-specialised):
 //   warps 0-7   ALU      : thread = pixel.  Walk the tile's depth-sorted list 128 Gaussians at a time,
 //                          generate w = alpha*T (sequential T per pixel), write W^T as bf16 hi/lo
@@ -25,7 +26,7 @@
 //                          (cp.reduce.async.bulk.add.f32: measured 2.5-2.7 TB/s of payload on scattered
 //                          2 KB rows vs 0.6 TB/s for per-lane red.v4 -- profiles/r01_probe.txt).
 // The W buffer (128 KB) is single: warp w re-fills its 32-pixel slab for batch q+1 as soon as the MMA
-// of batch q's last column chunk has consumed it (per-warp mbarriers), so generation and MMA overlap.
+// of batch q's LAST column chunk has consumed it (per-warp mbarriers), so generation and MMA overlap.
 //
 // The feature map is re-laid-out once per view by fpack_kernel (fp32 [H,W,D], any strides ->
 // bf16 hi/lo, tile-major, already in UMMA core-matrix order) so the producer needs no tensor map.
@@ -106,7 +107,7 @@ struct TcArgs {
 };
 
 // -------------------------------------------------------------------------------------------------
-// work unit = (tile, column chunk c): every CTA pulls units from a global counter
+// work unit = tile: every CTA pulls tiles from a global counter
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -148,8 +149,8 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             const int unit = s_unit;
             bar_sync_alu();  // everyone has read s_unit before it is overwritten
             if (unit >= a.nunits) break;
-            const int tile = unit / a.nchunks;
-            const bool need_den = (unit % a.nchunks) == 0;
+            const int tile = unit;
+            constexpr bool need_den = true;
             const int ty = tile / a.t.tw, tx = tile % a.t.tw;
             const int s = a.t.offsets[tile], e = a.t.offsets[tile + 1];
             const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
@@ -296,35 +297,37 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             const int slot = q % RING;
             mbar_wait(bar(Smem::rows_ready + slot), (q / RING) & 1);
             if (rows[slot].exit_flag) break;
-            const int unit = ctrl[slot];  // still valid: the slot is recycled only after rows_free
-            const int c = unit % a.nchunks;
             const int gid = rows[slot].gid[r];
             const float dn = rows[slot].den[r];
             const bool live = (gid >= 0) && (dn > 0.0f);
-            float *dst = a.num + (int64_t)(live ? gid : 0) * a.d + c * NCMAX;
-            const int ncols = min(NCMAX, a.dp - c * NCMAX);   // padded columns of this chunk
-            const int dcols = min(NCMAX, a.d - c * NCMAX);    // real columns of this chunk
-            const int ab = q & 1;
-            mbar_wait(bar(Smem::acc_full + ab), (q >> 1) & 1);
-            tc_fence_after();
-            for (int c0 = 0; c0 < ncols; c0 += EPI_COLS) {
-                float v[32];
-                tmem_ld32(tmem + lane_base + (uint32_t)(ab * NCMAX + c0), v);
-                bulk_wait_read<0>();  // my previous reduction has finished reading my staging row
-                if (live && c0 < dcols) {
+            for (int c = 0; c < a.nchunks; ++c) {
+                const int u = q * a.nchunks + c, ab = u & 1;
+                float *dst = a.num + (int64_t)(live ? gid : 0) * a.d + c * NCMAX;
+                const int ncols = min(NCMAX, a.dp - c * NCMAX);   // padded columns of this chunk
+                const int dcols = min(NCMAX, a.d - c * NCMAX);    // real columns of this chunk
+                mbar_wait(bar(Smem::acc_full + ab), (u >> 1) & 1);
+                tc_fence_after();
+                for (int c0 = 0; c0 < ncols; c0 += EPI_COLS) {
+                    float v[32];
+                    tmem_ld32(tmem + lane_base + (uint32_t)(ab * NCMAX + c0), v);
+                    bulk_wait_read<0>();  // my previous reduction has finished reading my staging row
+                    if (live && c0 < dcols) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4 *>(srow + 4 * i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    fence_proxy_async_smem();
-                    bulk_reduce_add_f32(dst + c0, srow_u32, (uint32_t)min(EPI_COLS, dcols - c0) * 4u);
-                    bulk_commit();
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4 *>(srow + 4 * i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        fence_proxy_async_smem();
+                        bulk_reduce_add_f32(dst + c0, srow_u32, (uint32_t)min(EPI_COLS, dcols - c0) * 4u);
+                        bulk_commit();
+                    }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(Smem::acc_empty + ab));
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(Smem::acc_empty + ab));
-            if (live && c == 0) atomicAdd(a.den + gid, dn);
-            if (live && c == 0) ++live_rows;
+            if (live) {
+                atomicAdd(a.den + gid, dn);
+                ++live_rows;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(Smem::rows_free + slot));
         }
@@ -345,16 +348,18 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 const int unit = ctrl[slot];
                 mbar_arrive(bar(Smem::ctrl_empty + slot));
                 if (unit < 0) break;
-                const int tile = unit / a.nchunks, c = unit % a.nchunks;
-                const int ncols = min(NCMAX, a.dp - c * NCMAX);
-                const uint32_t bytes = (uint32_t)ncols * KSL * 4;  // hi + lo
-                const uint8_t *cbase = a.fpack + tile * tile_bytes + (int64_t)c * NCMAX * kTilePix * 4;
-                for (int ks = 0; ks < kTilePix / KSL; ++ks) {
-                    if (use >= 1) mbar_wait(bar(Smem::f_empty + stage), (use - 1) & 1);
-                    mbar_arrive_expect_tx(bar(Smem::f_full + stage), bytes);
-                    bulk_g2s(sbase + Smem::fring + stage * STAGE_BYTES, cbase + (int64_t)ks * bytes, bytes,
-                             bar(Smem::f_full + stage));
-                    if (++stage == NSTAGE) { stage = 0; ++use; }
+                const uint8_t *tbase = a.fpack + unit * tile_bytes;
+                for (int c = 0; c < a.nchunks; ++c) {
+                    const int ncols = min(NCMAX, a.dp - c * NCMAX);
+                    const uint32_t bytes = (uint32_t)ncols * KSL * 4;  // hi + lo
+                    const uint8_t *cbase = tbase + (int64_t)c * NCMAX * kTilePix * 4;
+                    for (int ks = 0; ks < kTilePix / KSL; ++ks) {
+                        if (use >= 1) mbar_wait(bar(Smem::f_empty + stage), (use - 1) & 1);
+                        mbar_arrive_expect_tx(bar(Smem::f_full + stage), bytes);
+                        bulk_g2s(sbase + Smem::fring + stage * STAGE_BYTES, cbase + (int64_t)ks * bytes, bytes,
+                                 bar(Smem::f_full + stage));
+                        if (++stage == NSTAGE) { stage = 0; ++use; }
+                    }
                 }
             }
         }
@@ -368,31 +373,34 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 const int unit = ctrl[slot];
                 mbar_arrive(bar(Smem::ctrl_empty + slot));
                 if (unit < 0) break;
-                const int c = unit % a.nchunks, ab = q & 1;
-                const int ncols = min(NCMAX, a.dp - c * NCMAX);
-                const uint32_t idesc = umma_idesc_bf16(MB, ncols, true, true);
-                const uint32_t b_lbo = (uint32_t)(ncols / 8) * 128, b_part = (uint32_t)ncols * KSL * 2;
-                if (q >= 2) mbar_wait(bar(Smem::acc_empty + ab), ((q >> 1) - 1) & 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem + (uint32_t)(ab * NCMAX);
-                for (int ks = 0; ks < kTilePix / KSL; ++ks) {
-                    if ((ks & 1) == 0) mbar_wait(bar(Smem::w_full + (ks >> 1)), q & 1);
-                    mbar_wait(bar(Smem::f_full + stage), use & 1);
+                for (int c = 0; c < a.nchunks; ++c) {
+                    const int u = q * a.nchunks + c, ab = u & 1;
+                    const int ncols = min(NCMAX, a.dp - c * NCMAX);
+                    const uint32_t idesc = umma_idesc_bf16(MB, ncols, true, true);
+                    const uint32_t b_lbo = (uint32_t)(ncols / 8) * 128, b_part = (uint32_t)ncols * KSL * 2;
+                    if (u >= 2) mbar_wait(bar(Smem::acc_empty + ab), ((u >> 1) - 1) & 1);
                     tc_fence_after();
-                    const uint32_t a_off = (uint32_t)ks * 2 * A_LBO;
-                    const uint64_t a_hi = umma_smem_desc(sbase + Smem::w_hi + a_off, A_LBO, A_SBO);
-                    const uint64_t a_lo = umma_smem_desc(sbase + Smem::w_lo + a_off, A_LBO, A_SBO);
-                    const uint32_t fb = sbase + Smem::fring + stage * STAGE_BYTES;
-                    const uint64_t b_hi = umma_smem_desc(fb, b_lbo, 128);
-                    const uint64_t b_lo = umma_smem_desc(fb + b_part, b_lbo, 128);
-                    umma_bf16(d_tmem, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
-                    umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
-                    umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
-                    umma_commit(bar(Smem::f_empty + stage));
-                    if (ks & 1) umma_commit(bar(Smem::w_free + (ks >> 1)));
-                    if (++stage == NSTAGE) { stage = 0; ++use; }
+                    const uint32_t d_tmem = tmem + (uint32_t)(ab * NCMAX);
+                    const bool last = (c == a.nchunks - 1);
+                    for (int ks = 0; ks < kTilePix / KSL; ++ks) {
+                        if (c == 0 && (ks & 1) == 0) mbar_wait(bar(Smem::w_full + (ks >> 1)), q & 1);
+                        mbar_wait(bar(Smem::f_full + stage), use & 1);
+                        tc_fence_after();
+                        const uint32_t a_off = (uint32_t)ks * 2 * A_LBO;
+                        const uint64_t a_hi = umma_smem_desc(sbase + Smem::w_hi + a_off, A_LBO, A_SBO);
+                        const uint64_t a_lo = umma_smem_desc(sbase + Smem::w_lo + a_off, A_LBO, A_SBO);
+                        const uint32_t fb = sbase + Smem::fring + stage * STAGE_BYTES;
+                        const uint64_t b_hi = umma_smem_desc(fb, b_lbo, 128);
+                        const uint64_t b_lo = umma_smem_desc(fb + b_part, b_lbo, 128);
+                        umma_bf16(d_tmem, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+                        umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+                        umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+                        umma_commit(bar(Smem::f_empty + stage));
+                        if (last && (ks & 1)) umma_commit(bar(Smem::w_free + (ks >> 1)));
+                        if (++stage == NSTAGE) { stage = 0; ++use; }
+                    }
+                    umma_commit(bar(Smem::acc_full + ab));
                 }
-                umma_commit(bar(Smem::acc_full + ab));
             }
         }
     }
@@ -525,7 +533,7 @@ int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t 
     a.t = t;
     a.fpack = (const uint8_t *)fpack;
     a.num = num; a.den = den;
-    a.d = d; a.dp = dp; a.nchunks = nchunks; a.nunits = ntiles * nchunks;
+    a.d = d; a.dp = dp; a.nchunks = nchunks; a.nunits = ntiles;
     a.unit_counter = (int *)t.scratch;
     a.stats = stats;
     GWBP_CUDA_OK(cudaMemsetAsync(a.unit_counter, 0, sizeof(int), st));

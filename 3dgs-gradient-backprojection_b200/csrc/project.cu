@@ -222,9 +222,10 @@ __global__ void __launch_bounds__(256) project_kernel(int64_t n, const float4 *_
         const int bw = x1 - x0;
         const bool big = ok && tiles > kMaskTiles;
         if (ok && !big) {
-            unsigned long long mk = 0ull;
-            for (unsigned k = 0; k < tiles; ++k)
-                if (tile_hit(cg, x0 + (int)(k % bw), y0 + (int)(k / bw), cam.W, cam.H)) mk |= 1ull << k;
+            unsigned long long mk = 0ull, bit = 1ull;  // bit k <-> k-th tile of the rectangle, row-major
+            for (int ty = y0; ty < y1; ++ty)
+                for (int tx = x0; tx < x1; ++tx, bit <<= 1)
+                    if (tile_hit(cg, tx, ty, cam.W, cam.H)) mk |= bit;
             mask[i] = mk;
             tiles = (unsigned)__popcll(mk);
         }
@@ -332,17 +333,17 @@ __global__ void __launch_bounds__(256) emit_kernel(int64_t n_vis, CamDev cam, co
     const bool big = vis && ntiles > kMaskTiles;
     if (vis && !big) {
         long long o = base;
-        if (cam.cull) {
-            unsigned long long mk = pmask[pos];
-            while (mk) {
-                const int k = __ffsll((long long)mk) - 1;
-                mk &= mk - 1;
-                if (o < cap) { tkeys[o] = (unsigned)((y0 + k / bw) * cam.tw + x0 + k % bw); tvals[o] = pos; }
+        unsigned long long mk = cam.cull ? pmask[pos] : ~0ull;
+        for (int ty = y0; ty < y1; ++ty) {
+            unsigned long long row = mk & ((bw < 64) ? ((1ull << bw) - 1ull) : ~0ull);
+            mk = (bw < 64) ? (mk >> bw) : 0ull;
+            const unsigned tbase = (unsigned)(ty * cam.tw + x0);
+            while (row) {
+                const int k = __ffsll((long long)row) - 1;
+                row &= row - 1;
+                if (o < cap) { tkeys[o] = tbase + (unsigned)k; tvals[o] = pos; }
                 ++o;
             }
-        } else {
-            for (int k = 0; k < ntiles; ++k, ++o)
-                if (o < cap) { tkeys[o] = (unsigned)((y0 + k / bw) * cam.tw + x0 + k % bw); tvals[o] = pos; }
         }
     }
     unsigned m = __ballot_sync(0xffffffffu, big);
