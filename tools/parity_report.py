@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""GPU-vs-oracle parity report (run on the B200 box; output is committed under profiles/).
+Uses oracle/ as the checker only."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import gwbp  # noqa: E402
+from helpers import oracle_job, row_cosine, row_rel_err  # noqa: E402
+from oracle import c_oracle, gsplat_oracle  # noqa: E402
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def run(name, n, views, W, H, d, seed=0, enc=24):
+    S = gwbp.scene
+    sc = S.make_scene(n, seed)
+    vm, K = S.make_cameras(views, W, H, seed)
+    feats = [S.make_feature_map_np(v, d, H, W, seed, enc_res=enc) for v in range(views)]
+    num_o, den_o, st = oracle_job(c_oracle, sc, vm, K, W, H, feats, d)
+    f_o = gsplat_oracle.finalize(num_o, den_o + 1e-12)
+    sel = den_o > 1e-6
+    print(f"== {name}: N={n} views={views} {W}x{H} D={d}; rows with den>1e-6: {int(sel.sum())}; "
+          f"oracle rows_nonzero={sum(s['rows_nonzero'] for s in st)} pairs={sum(s['pairs'] for s in st)}")
+    for kernel in ("simt", "tc"):
+        if kernel == "tc" and not gwbp.fpack_bytes(W, H, d):
+            continue
+        bp = gwbp.BackProjector(dev(sc.means), dev(sc.quats), dev(sc.scales), dev(sc.opacities), d, kernel=kernel,
+                                collect_stats=True)
+        for v in range(views):
+            planar = dev(np.transpose(feats[v], (2, 0, 1)))
+            bp.add_view(vm[v], K, W, H, planar.permute(1, 2, 0))
+        f = bp.finalize().double().cpu().numpy()
+        den = bp.den.double().cpu().numpy() - 1e-12
+        rel, _ = row_rel_err(f[sel], f_o[sel])
+        cos, _ = row_cosine(f[sel], f_o[sel])
+        den_rel = np.abs(den[sel] - den_o[sel]) / den_o[sel]
+        mask_eq = np.array_equal(den > 5e-13, den_o > 0)
+        print(f"  [{kernel:4s}] feature row rel-err: max {rel.max():.3e} p99.9 {np.percentile(rel, 99.9):.3e} "
+              f"median {np.median(rel):.3e} | rows > 1e-4: {int((rel > 1e-4).sum())} | cosine min {cos.min():.8f} | "
+              f"den rel-err p99.9 {np.percentile(den_rel, 99.9):.3e} max {den_rel.max():.3e} | prune mask identical: {mask_eq} | "
+              f"rows_nonzero gpu {bp.stats()['rows_nonzero']}")
+    # query side
+    text = S.make_text_queries(3, d, 0)
+    m_o, score = gsplat_oracle.mask3d(f_o, text, 1)
+    m, _ = gwbp.get_mask3d(dev(f_o.astype(np.float32)), dev(text), 1)
+    margin = np.abs(score[:, 0] - score[:, 1:].max(1))
+    diff = m.cpu().numpy() != m_o
+    print(f"  3-D mask: {int(diff.sum())} of {len(m_o)} differ (all with |margin| < {margin[diff].max() if diff.any() else 0:.1e})")
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0))
+    run("config S (BASELINE config 1)", 50_000, 8, 256, 256, 64)
+    run("512-d, 3 views", 20_000, 3, 320, 208, 512)
+    run("768-d (config M feature width)", 8_000, 2, 160, 112, 768, enc=12)
+    run("16-d (compressed path)", 20_000, 4, 256, 192, 16)
