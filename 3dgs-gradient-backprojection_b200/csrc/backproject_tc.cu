@@ -21,10 +21,10 @@
 //   warp 14     MMA      : one thread issues tcgen05.mma; accumulators [128 x <=256] fp32 are double
 //                          buffered in the 512 TMEM columns so the epilogue of one batch overlaps the
 //                          MMAs of the next.
-//   warps 8-11  epilogue : tcgen05.ld the accumulator (lane = Gaussian row), stage 128-byte row pieces
-//                          in smem and let the TMA engine reduce them into num[N,D] in HBM
-//                          (cp.reduce.async.bulk.add.f32: measured 2.5-2.7 TB/s of payload on scattered
-//                          2 KB rows vs 0.6 TB/s for per-lane red.v4 -- profiles/r01_probe.txt).
+//   warps 8-11  epilogue : tcgen05.ld the accumulator (lane = Gaussian row), transpose 32x32 pieces
+//                          through padded smem and reduce them into num[N,D] with row-contiguous
+//                          red.global.add.v4.f32 (measured 2.6 TB/s of payload on scattered 2 KB rows vs
+//                          0.6 TB/s for per-lane rows -- profiles/r01_probe.txt).
 // The W buffer (128 KB) is single: warp w re-fills its 32-pixel slab for batch q+1 as soon as the MMA
 // of batch q's LAST column chunk has consumed it (per-warp mbarriers), so generation and MMA overlap.
 //
@@ -150,7 +150,6 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             bar_sync_alu();  // everyone has read s_unit before it is overwritten
             if (unit >= a.nunits) break;
             const int tile = unit;
-            constexpr bool need_den = true;
             const int ty = tile / a.t.tw, tx = tile % a.t.tw;
             const int s = a.t.offsets[tile], e = a.t.offsets[tile + 1];
             const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
@@ -191,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                     r1 = a.t.grec[2 * (int64_t)id + 1];
                 }
                 if (q >= 1) mbar_wait(bar(Smem::w_free + warp), (q - 1) & 1);
-                if (need_den) walked += min(MB, e - b);
+                walked += min(MB, e - b);
                 if (__all_sync(0xffffffffu, done)) {
                     // this warp's 32 pixels are finished: its slab of W is all zero
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -202,11 +201,13 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                     }
                 } else {
 #pragma unroll 1
-                    for (int j = 0; j < MB / 8; ++j) {
-                        float w[8];
+                    for (int j = 0; j < MB / 16; ++j) {
+                        // 16 Gaussians per step: alpha evaluation is independent across Gaussians (ILP);
+                        // only the T update is a serial chain
+                        float w[16];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 g0 = gbuf[8 * j + i], g1 = gbuf[MB + 8 * j + i];
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 g0 = gbuf[16 * j + i], g1 = gbuf[MB + 16 * j + i];
                             const float dx = g0.x - px, dy = g0.y - py;
                             const float pw = dx * fmaf(g0.w, dx, g1.x * dy) + (g1.y * dy) * dy;  // -sigma*log2(e)
                             const float alpha = fminf(kAlphaMax, g0.z * fast_ex2(pw));
@@ -218,45 +219,44 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                             T = take ? nT : T;
                             done = done || stop;
                         }
-                        uint4 hi, lo;
-                        split_bf16x2(w[0], w[1], hi.x, lo.x);
-                        split_bf16x2(w[2], w[3], hi.y, lo.y);
-                        split_bf16x2(w[4], w[5], hi.z, lo.z);
-                        split_bf16x2(w[6], w[7], hi.w, lo.w);
-                        const uint32_t off = (uint32_t)j * A_SBO + wslab;
-                        *reinterpret_cast<uint4 *>(smem + Smem::w_hi + off) = hi;
-                        *reinterpret_cast<uint4 *>(smem + Smem::w_lo + off) = lo;
-                        if (need_den) {
-                            // per-Gaussian sum over the warp's 32 pixels (den): butterfly transpose-reduce
-                            const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
-                            float v4[4], v2[2], v1;
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float send = b16 ? w[i] : w[i + 4];
-                                v4[i] = (b16 ? w[i + 4] : w[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
-                            }
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 hi, lo;
+                            split_bf16x2(w[8 * h + 0], w[8 * h + 1], hi.x, lo.x);
+                            split_bf16x2(w[8 * h + 2], w[8 * h + 3], hi.y, lo.y);
+                            split_bf16x2(w[8 * h + 4], w[8 * h + 5], hi.z, lo.z);
+                            split_bf16x2(w[8 * h + 6], w[8 * h + 7], hi.w, lo.w);
+                            const uint32_t off = (uint32_t)(2 * j + h) * A_SBO + wslab;
+                            *reinterpret_cast<uint4 *>(smem + Smem::w_hi + off) = hi;
+                            *reinterpret_cast<uint4 *>(smem + Smem::w_lo + off) = lo;
+                        }
+                        // den: per-Gaussian sum over the warp's 32 pixels.  Butterfly transpose-reduce:
+                        // 16 values x 32 lanes -> lane L ends with the full sum of Gaussian (L >> 1).
+                        const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4, b2 = lane & 2;
+                        float v8[8], v4[4], v2[2], v1;
 #pragma unroll
-                            for (int i = 0; i < 2; ++i) {
-                                const float send = b8 ? v4[i] : v4[i + 2];
-                                v2[i] = (b8 ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
-                            }
-                            {
-                                const float send = b4 ? v2[0] : v2[1];
-                                v1 = (b4 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, send, 4);
-                            }
-                            v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
-                            v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-                            if ((lane & 3) == 0 && v1 > 0.0f) {
-                                const int gi = (b16 ? 4 : 0) + (b8 ? 2 : 0) + (b4 ? 1 : 0);
-                                atomicAdd(&rows[slot].den[8 * j + gi], v1);
-                            }
-                        } else {
-                            // den is accumulated by the chunk-0 unit of this tile; here only "row is live"
-                            unsigned nz = 0;
+                        for (int i = 0; i < 8; ++i) {
+                            const float send = b16 ? w[i] : w[i + 8];
+                            v8[i] = (b16 ? w[i + 8] : w[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
+                        }
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) nz |= (w[i] > 0.0f ? 1u : 0u) << i;
-                            nz = __reduce_or_sync(0xffffffffu, nz);
-                            if (lane < 8 && (nz >> lane & 1u)) rows[slot].den[8 * j + lane] = 1.0f;
+                        for (int i = 0; i < 4; ++i) {
+                            const float send = b8 ? v8[i] : v8[i + 4];
+                            v4[i] = (b8 ? v8[i + 4] : v8[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            const float send = b4 ? v4[i] : v4[i + 2];
+                            v2[i] = (b4 ? v4[i + 2] : v4[i]) + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+                        {
+                            const float send = b2 ? v2[0] : v2[1];
+                            v1 = (b2 ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, send, 2);
+                        }
+                        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+                        if ((lane & 1) == 0 && v1 > 0.0f) {
+                            const int gi = (b16 ? 8 : 0) + (b8 ? 4 : 0) + (b4 ? 2 : 0) + (b2 ? 1 : 0);
+                            atomicAdd(&rows[slot].den[16 * j + gi], v1);
                         }
                     }
                 }
@@ -284,14 +284,16 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
         if (a.stats && tid == 0) atomicAdd((unsigned long long *)&a.stats[1], (unsigned long long)walked);
     } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
         // ===================================== epilogue ======================================
-        // TMEM lane = Gaussian row.  Rows are staged 32 columns (128 B) at a time in shared memory
-        // and reduced into num[gid, :] by the TMA engine (cp.reduce.async.bulk .add.f32): one
-        // contiguous 128-byte reduction per live row instead of 32 scattered 16-byte atomics.
+        // TMEM lane = Gaussian row, but a reduction wants one ROW contiguous per instruction (measured:
+        // 2.6 TB/s coalesced vs 0.6 TB/s for per-lane rows, profiles/r01_probe.txt).  So each warp stages
+        // its 32 rows x 32 columns in padded smem and re-reads them row-wise: 8 lanes x 16 B = one 128-byte
+        // row piece, 4 rows per `red.global.add.v4.f32` instruction.
         const int quarter = warp & 3;
         const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
         const int r = 32 * quarter + lane;
-        uint8_t *srow = smem + Smem::stage_out + r * EPI_PITCH;
-        const uint32_t srow_u32 = sbase + Smem::stage_out + r * EPI_PITCH;
+        uint8_t *wstage = smem + Smem::stage_out + (32 * quarter) * EPI_PITCH;  // this warp's 32 staging rows
+        uint8_t *srow = wstage + lane * EPI_PITCH;
+        const int sub = lane >> 3, piece = lane & 7;  // row-in-group / 16-byte piece of the 128-byte row
         long long live_rows = 0;
         for (int q = 0;; ++q) {
             const int slot = q % RING;
@@ -300,9 +302,13 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             const int gid = rows[slot].gid[r];
             const float dn = rows[slot].den[r];
             const bool live = (gid >= 0) && (dn > 0.0f);
+            const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+            // the 8 rows this lane will reduce (rows 4*i + sub) and their accumulator rows
+            int64_t grow[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) grow[i] = (int64_t)__shfl_sync(0xffffffffu, gid, 4 * i + sub) * a.d;
             for (int c = 0; c < a.nchunks; ++c) {
                 const int u = q * a.nchunks + c, ab = u & 1;
-                float *dst = a.num + (int64_t)(live ? gid : 0) * a.d + c * NCMAX;
                 const int ncols = min(NCMAX, a.dp - c * NCMAX);   // padded columns of this chunk
                 const int dcols = min(NCMAX, a.d - c * NCMAX);    // real columns of this chunk
                 mbar_wait(bar(Smem::acc_full + ab), (u >> 1) & 1);
@@ -310,14 +316,24 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 for (int c0 = 0; c0 < ncols; c0 += EPI_COLS) {
                     float v[32];
                     tmem_ld32(tmem + lane_base + (uint32_t)(ab * NCMAX + c0), v);
-                    bulk_wait_read<0>();  // my previous reduction has finished reading my staging row
-                    if (live && c0 < dcols) {
+                    if (c0 >= dcols) continue;  // pure padding columns (warp-uniform)
+                    __syncwarp();  // previous piece fully read before it is overwritten
+                    if (live) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4)
                             *reinterpret_cast<float4 *>(srow + 4 * i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                        fence_proxy_async_smem();
-                        bulk_reduce_add_f32(dst + c0, srow_u32, (uint32_t)min(EPI_COLS, dcols - c0) * 4u);
-                        bulk_commit();
+                    }
+                    __syncwarp();
+                    const int col = c * NCMAX + c0 + 4 * piece;
+                    if (col < a.d) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int row = 4 * i + sub;
+                            if (live_mask >> row & 1u) {
+                                const float4 x = *reinterpret_cast<const float4 *>(wstage + row * EPI_PITCH + 16 * piece);
+                                red_add_v4(a.num + grow[i] + col, x.x, x.y, x.z, x.w);
+                            }
+                        }
                     }
                 }
                 tc_fence_before();
@@ -331,7 +347,6 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(Smem::rows_free + slot));
         }
-        bulk_wait_all<0>();
         if (a.stats) {
 #pragma unroll
             for (int o = 16; o; o >>= 1) live_rows += __shfl_xor_sync(0xffffffffu, live_rows, o);
@@ -365,42 +380,51 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
         }
     } else if (warp == kMmaWarp) {
         // ======================================= MMA =========================================
-        if (lane == 0) {
-            int stage = 0, use = 0;
-            for (int q = 0;; ++q) {
-                const int slot = q % RING;
-                mbar_wait(bar(Smem::ctrl_full + slot), (q / RING) & 1);
-                const int unit = ctrl[slot];
-                mbar_arrive(bar(Smem::ctrl_empty + slot));
-                if (unit < 0) break;
-                for (int c = 0; c < a.nchunks; ++c) {
-                    const int u = q * a.nchunks + c, ab = u & 1;
-                    const int ncols = min(NCMAX, a.dp - c * NCMAX);
-                    const uint32_t idesc = umma_idesc_bf16(MB, ncols, true, true);
-                    const uint32_t b_lbo = (uint32_t)(ncols / 8) * 128, b_part = (uint32_t)ncols * KSL * 2;
-                    if (u >= 2) mbar_wait(bar(Smem::acc_empty + ab), ((u >> 1) - 1) & 1);
+        // The whole warp runs this loop converged and every operand below is warp-uniform, so the
+        // tcgen05 instructions are issued straight from uniform registers by one elected lane.
+        // (Issuing from a divergent `if (lane == 0)` makes ptxas wrap each UTCHMMA/UTCBAR in an
+        // ELECT/BRA.U.ANY serialisation loop: ~630 cycles of issue overhead per 384-cycle K-slice.)
+        int stage = 0, use = 0;
+        const uint64_t a_hi0 = umma_smem_desc(sbase + Smem::w_hi, A_LBO, A_SBO);
+        const uint64_t a_lo0 = umma_smem_desc(sbase + Smem::w_lo, A_LBO, A_SBO);
+        constexpr uint64_t kAStep = (2 * A_LBO) >> 4;  // start-address field advance per 16-pixel K-slice
+        for (int q = 0;; ++q) {
+            const int slot = q % RING;
+            mbar_wait(bar(Smem::ctrl_full + slot), (q / RING) & 1);
+            const int unit = ctrl[slot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(Smem::ctrl_empty + slot));
+            if (unit < 0) break;
+            for (int c = 0; c < a.nchunks; ++c) {
+                const int u = q * a.nchunks + c, ab = u & 1;
+                const int ncols = min(NCMAX, a.dp - c * NCMAX);
+                const uint32_t idesc = umma_idesc_bf16(MB, ncols, true, true);
+                const uint32_t b_lbo = (uint32_t)(ncols / 8) * 128, b_part = (uint32_t)ncols * KSL * 2;
+                const uint64_t b_hi0 = umma_smem_desc(sbase + Smem::fring, b_lbo, 128);
+                const uint64_t b_lo0 = umma_smem_desc(sbase + Smem::fring + b_part, b_lbo, 128);
+                if (u >= 2) mbar_wait(bar(Smem::acc_empty + ab), ((u >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + (uint32_t)(ab * NCMAX);
+                const bool last = (c == a.nchunks - 1);
+#pragma unroll 1
+                for (int ks = 0; ks < kTilePix / KSL; ++ks) {
+                    if (c == 0 && (ks & 1) == 0) mbar_wait(bar(Smem::w_full + (ks >> 1)), q & 1);
+                    mbar_wait(bar(Smem::f_full + stage), use & 1);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem + (uint32_t)(ab * NCMAX);
-                    const bool last = (c == a.nchunks - 1);
-                    for (int ks = 0; ks < kTilePix / KSL; ++ks) {
-                        if (c == 0 && (ks & 1) == 0) mbar_wait(bar(Smem::w_full + (ks >> 1)), q & 1);
-                        mbar_wait(bar(Smem::f_full + stage), use & 1);
-                        tc_fence_after();
-                        const uint32_t a_off = (uint32_t)ks * 2 * A_LBO;
-                        const uint64_t a_hi = umma_smem_desc(sbase + Smem::w_hi + a_off, A_LBO, A_SBO);
-                        const uint64_t a_lo = umma_smem_desc(sbase + Smem::w_lo + a_off, A_LBO, A_SBO);
-                        const uint32_t fb = sbase + Smem::fring + stage * STAGE_BYTES;
-                        const uint64_t b_hi = umma_smem_desc(fb, b_lbo, 128);
-                        const uint64_t b_lo = umma_smem_desc(fb + b_part, b_lbo, 128);
-                        umma_bf16(d_tmem, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
-                        umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
-                        umma_bf16(d_tmem, a_lo, b_hi, idesc, 1u);
+                    const uint64_t a_hi = a_hi0 + (uint64_t)ks * kAStep, a_lo = a_lo0 + (uint64_t)ks * kAStep;
+                    const uint64_t boff = (uint64_t)((stage * STAGE_BYTES) >> 4);
+                    if (elect_one()) {
+                        umma_bf16(d_tmem, a_hi, b_hi0 + boff, idesc, ks > 0 ? 1u : 0u);
+                        umma_bf16(d_tmem, a_hi, b_lo0 + boff, idesc, 1u);
+                        umma_bf16(d_tmem, a_lo, b_hi0 + boff, idesc, 1u);
                         umma_commit(bar(Smem::f_empty + stage));
                         if (last && (ks & 1)) umma_commit(bar(Smem::w_free + (ks >> 1)));
-                        if (++stage == NSTAGE) { stage = 0; ++use; }
                     }
-                    umma_commit(bar(Smem::acc_full + ab));
+                    __syncwarp();
+                    if (++stage == NSTAGE) { stage = 0; ++use; }
                 }
+                if (elect_one()) umma_commit(bar(Smem::acc_full + ab));
+                __syncwarp();
             }
         }
     }
@@ -469,9 +493,17 @@ __global__ void __launch_bounds__(256) fpack_planar_kernel(const float *__restri
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int x = span * 32 + lane;
     const bool xok = x < W;
-    for (int n = warp; n < ncols; n += 8) {
-        const int col = c * NCMAX + n;
-        slab[n][lane] = (xok && col < d) ? __ldg(F + y * sH + x + col * sD) : 0.0f;
+    // 8 independent 128-byte row loads in flight per warp before the first use (memory-level parallelism)
+    for (int n0 = warp; n0 < ncols; n0 += 64) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int n = n0 + 8 * u, col = c * NCMAX + n;
+            v[u] = (xok && n < ncols && col < d) ? __ldg(F + y * sH + x + col * sD) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (n0 + 8 * u < ncols) slab[n0 + 8 * u][lane] = v[u];
     }
     __syncthreads();
     const int ty = y / kTile, ks = y % kTile;
