@@ -43,14 +43,17 @@ class BackProjector:
         self.n_views = 0
         self.last_view: Optional[View] = None
         self.kernel_events = None  # set to [] to record (start, end) CUDA events around the fused kernel
+        # the feature re-layout depends only on F: it runs on a side stream, overlapping projection/binning
+        self.overlap_pack = True
+        self._side = None
+        self._tc_done = None
 
     # -- one view -------------------------------------------------------------------------
     def add_view(self, viewmat, K, width, height, feats: torch.Tensor, **cam_kw) -> View:
         assert feats.shape[-1] == self.d, f"feature dim {feats.shape[-1]} != {self.d}"
         cam = make_camera(viewmat, K, width, height, **cam_kw)
-        view = View(self.scene, cam, self.cap, self._ws, self.tile_cull)
-        self._ws, self.cap = view.ws, view.cap  # keep (possibly grown) workspace for the next view
-        fp = None
+        main = torch.cuda.current_stream(self.device)
+        fp, kernel = None, self.kernel
         if self.kernel != L.KERNEL_SIMT:
             need = fpack_bytes(cam.width, cam.height, self.d)
             if need:
@@ -59,12 +62,27 @@ class BackProjector:
                 fp = self._fpack
             elif self.kernel == L.KERNEL_TC:
                 raise RuntimeError(f"tcgen05 kernel does not support D={self.d}")
+        if fp is not None and self.overlap_pack:
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+            # order: after the previous view's kernel has finished reading fpack, and after F is ready
+            self._side.wait_stream(main)
+            sH, sW, sD = feats.stride()
+            with torch.cuda.device(self.device):
+                L.check(L.lib().gwbp_pack_features(cam.width, cam.height, feats.data_ptr(), sH, sW, sD, self.d,
+                                                   fp.data_ptr(), int(self._side.cuda_stream)), "gwbp_pack_features")
+            feats.record_stream(self._side)
+            kernel = (L.KERNEL_TC if kernel == L.KERNEL_AUTO else kernel) | L.KERNEL_FPACK_READY
+        view = View(self.scene, cam, self.cap, self._ws, self.tile_cull)
+        self._ws, self.cap = view.ws, view.cap  # keep (possibly grown) workspace for the next view
+        if kernel & L.KERNEL_FPACK_READY:
+            main.wait_stream(self._side)
         if self.kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(torch.cuda.current_stream(self.device))
-        view.backproject(feats, self.num, self.den, self.kernel, fp, self._stats)
+            e0.record(main)
+        view.backproject(feats, self.num, self.den, kernel, fp, self._stats)
         if self.kernel_events is not None:
-            e1.record(torch.cuda.current_stream(self.device))
+            e1.record(main)
             self.kernel_events.append((e0, e1))
         self.n_views += 1
         self.last_view = view

@@ -140,9 +140,22 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     return launch_offsets(info->n_isects, cd.tw * cd.th, w.tkeys[sorted], w.offsets, st);
 }
 
+int gwbp_debug_set_trace(void *buf, size_t bytes) {
+    tc_set_trace(buf, bytes);
+    return 0;
+}
+
 size_t gwbp_fpack_bytes(int32_t width, int32_t height, int32_t d) {
     if (width <= 0 || height <= 0 || !tc_supported(d)) return 0;
     return fpack_bytes(width, height, d);
+}
+
+int gwbp_pack_features(int32_t width, int32_t height, const float *F, int64_t sH, int64_t sW, int64_t sD, int32_t d,
+                       void *fpack, void *stream) {
+    GWBP_REQUIRE(width > 0 && height > 0, "pack_features: bad image size");
+    GWBP_REQUIRE(tc_supported(d), "pack_features: tcgen05 path does not support D=%d", d);
+    GWBP_REQUIRE(F && fpack, "pack_features: NULL pointer");
+    return launch_fpack(width, height, F, sH, sW, sD, d, fpack, (cudaStream_t)stream);
 }
 
 int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws,
@@ -158,12 +171,13 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam, const
     const TileCtx t = tile_ctx(cam, ws, L, info);
     cudaStream_t st = (cudaStream_t)stream;
     if (info->n_isects == 0) return 0;
-    int k = kernel;
+    int k = kernel & 0xff;
     if (k == GWBP_KERNEL_AUTO) k = (tc_supported(d) && fpack) ? GWBP_KERNEL_TC : GWBP_KERNEL_SIMT;
     if (k == GWBP_KERNEL_TC) {
         GWBP_REQUIRE(tc_supported(d), "tcgen05 back-projection does not support D=%d", d);
         GWBP_REQUIRE(fpack != nullptr, "tcgen05 back-projection needs the fpack buffer (gwbp_fpack_bytes)");
-        return launch_backproject_tc(t, F, sH, sW, sD, d, num, den, fpack, (long long *)stats, st);
+        return launch_backproject_tc(t, F, sH, sW, sD, d, num, den, fpack, (kernel & GWBP_KERNEL_FPACK_READY) != 0,
+                                     (long long *)stats, st);
     }
     GWBP_REQUIRE(k == GWBP_KERNEL_SIMT, "unknown kernel id %d", kernel);
     return launch_backproject_simt(t, F, sH, sW, sD, d, num, den, (long long *)stats, st);

@@ -30,6 +30,8 @@
 //
 // The feature map is re-laid-out once per view by fpack_kernel (fp32 [H,W,D], any strides ->
 // bf16 hi/lo, tile-major, already in UMMA core-matrix order) so the producer needs no tensor map.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -42,13 +44,13 @@ namespace {
 constexpr int MB = 128;             // Gaussians per batch = UMMA M
 constexpr int NCMAX = 256;          // columns per work unit = UMMA N (max)
 constexpr int KSL = 16;             // pixels per K-slice (= one tile row) = one UMMA K step for bf16
-constexpr int NSTAGE = 4;           // feature ring depth (16 KB stages)
+constexpr int NSTAGE = 5;           // feature ring depth (16 KB stages): bytes in flight bound the MMA rate
 constexpr int STAGE_BYTES = NCMAX * KSL * 2 * 2;  // hi + lo = 16 KB
-constexpr int RING = 4;             // batches in flight between ALU and epilogue
+constexpr int RING = 3;             // batches in flight between ALU and epilogue
 constexpr uint32_t A_SBO = 128, A_LBO = (MB / 8) * 128;  // W^T: 16 row-groups of 8 Gaussians per K-group
 constexpr int W_PART_BYTES = (kTilePix / 8) * A_LBO;     // 64 KB per hi / lo part
-constexpr int EPI_COLS = 32;                             // columns per epilogue piece (128 B per row)
-constexpr int EPI_PITCH = EPI_COLS * 4 + 16;             // padded row pitch: conflict-free 16-byte stores
+constexpr int EPI_COLS = 16;                             // columns per epilogue piece (64 B per row)
+constexpr int EPI_PITCH = EPI_COLS * 4 + 16;             // padded row pitch (80 B): conflict-free 16-byte stores
 
 constexpr int kEpiWarp0 = 8, kProducerWarp = 13, kMmaWarp = 14, kThreads = 480;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -77,7 +79,8 @@ struct Smem {
     static constexpr int tmem_slot = bars + nbars * 8;
     static constexpr int total = tmem_slot + 16;
 };
-static_assert(Smem::total + 64 <= 232448, "shared memory budget (227 KB) exceeded");
+static_assert(RING <= 8, "ctrl[8] is the work-queue slot");
+static_assert(Smem::total + 256 <= 232448, "shared memory budget (227 KB) exceeded");
 
 __device__ __forceinline__ int bar_red_popc_alu(bool pred) {
     int cnt;
@@ -97,11 +100,29 @@ __device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2, what __expf l
 }
 __device__ __forceinline__ void bar_sync_alu() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// Optional event trace (debug/profiling only: gwbp_debug_set_trace).  CTA 0 records
+// (role, event, batch, chunk, clock64) tuples: roles 0/1 = ALU warp 0/7, 2 = epilogue warp 0, 3 = MMA.
+constexpr int kTraceRoles = 4, kTraceCap = 4096;
+// Tile visiting order.  Work units are handed out in bands of kBand tile rows, column-major inside a band,
+// so that the ~148 tiles in flight form a compact block: the (typically 2x2..3x3) tiles that touch one
+// Gaussian are processed close together in time and their row reductions merge in the 126 MB L2 instead
+// of each costing a DRAM read-modify-write of the 2 KB accumulator row.
+constexpr int kBand = 8;
+__device__ __forceinline__ int unit_to_tile(int unit, int tw, int th) {
+    const int per_band = kBand * tw;
+    const int band = unit / per_band, r = unit - band * per_band;
+    const int hb = min(kBand, th - band * kBand);
+    const int tx = r / hb, ty = band * kBand + (r - tx * hb);
+    return ty * tw + tx;
+}
+
 struct TcArgs {
+    unsigned long long *trace;  // [kTraceRoles][kTraceCap][2] or nullptr
     TileCtx t;
     const uint8_t *fpack;
     float *num, *den;
     int d, dp, nchunks, nunits;
+    int debug;  // GWBP_TC_DEBUG env (experiments only): 1 = skip the accumulator reductions
     int *unit_counter;
     long long *stats;
 };
@@ -110,13 +131,13 @@ struct TcArgs {
 // work unit = tile: every CTA pulls tiles from a global counter
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ int s_unit;
+    extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     auto bar = [&](int i) -> uint32_t { return sbase + Smem::bars + 8 * i; };
     RowInfo *rows = reinterpret_cast<RowInfo *>(smem + Smem::rows);
     volatile int *ctrl = reinterpret_cast<volatile int *>(smem + Smem::ctrl);
+    volatile int &s_unit = ctrl[8];  // work-queue broadcast slot (ALU warps only)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Smem::tmem_slot);
 
     if (tid == 0) {
@@ -136,6 +157,15 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    int trace_n = 0;
+    auto trace = [&](int role, int ev, int q, int c) {
+        if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_n < kTraceCap) {
+            unsigned long long *p = a.trace + ((size_t)role * kTraceCap + trace_n) * 2;
+            p[0] = ((unsigned long long)ev << 48) | ((unsigned long long)(c & 0xffff) << 32) | (unsigned)q;
+            p[1] = (unsigned long long)clock64();
+            ++trace_n;
+        }
+    };
 
     if (warp < 8) {
         // ======================================= ALU =========================================
@@ -149,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             const int unit = s_unit;
             bar_sync_alu();  // everyone has read s_unit before it is overwritten
             if (unit >= a.nunits) break;
-            const int tile = unit;
+            const int tile = unit_to_tile(unit, a.t.tw, a.t.th);
             const int ty = tile / a.t.tw, tx = tile % a.t.tw;
             const int s = a.t.offsets[tile], e = a.t.offsets[tile + 1];
             const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
@@ -165,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             }
             for (int b = s; b < e; b += MB, ++q) {
                 if (bar_red_popc_alu(!done) == 0) break;  // also: every warp is done reading gbuf of batch q-1
+                if (warp == 0 || warp == 7) trace(warp ? 1 : 0, 0, q, 0);
                 const int slot = q % RING;
                 if (q >= RING) mbar_wait(bar(Smem::rows_free + slot), ((q / RING) - 1) & 1);
                 if (tid < MB) {
@@ -190,6 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                     r1 = a.t.grec[2 * (int64_t)id + 1];
                 }
                 if (q >= 1) mbar_wait(bar(Smem::w_free + warp), (q - 1) & 1);
+                if (warp == 0 || warp == 7) trace(warp ? 1 : 0, 1, q, 0);
                 walked += min(MB, e - b);
                 if (__all_sync(0xffffffffu, done)) {
                     // this warp's 32 pixels are finished: its slab of W is all zero
@@ -266,6 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                     mbar_arrive(bar(Smem::w_full + warp));
                     mbar_arrive(bar(Smem::rows_ready + slot));
                 }
+                if (warp == 0 || warp == 7) trace(warp ? 1 : 0, 2, q, 0);
             }
         }
         // exit sentinel for the other roles
@@ -286,14 +319,14 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
         // ===================================== epilogue ======================================
         // TMEM lane = Gaussian row, but a reduction wants one ROW contiguous per instruction (measured:
         // 2.6 TB/s coalesced vs 0.6 TB/s for per-lane rows, profiles/r01_probe.txt).  So each warp stages
-        // its 32 rows x 32 columns in padded smem and re-reads them row-wise: 8 lanes x 16 B = one 128-byte
-        // row piece, 4 rows per `red.global.add.v4.f32` instruction.
+        // its 32 rows x 16 columns in padded smem and re-reads them row-wise: 4 lanes x 16 B = one 64-byte
+        // row piece, 8 rows per `red.global.add.v4.f32` instruction.
         const int quarter = warp & 3;
         const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
         const int r = 32 * quarter + lane;
         uint8_t *wstage = smem + Smem::stage_out + (32 * quarter) * EPI_PITCH;  // this warp's 32 staging rows
         uint8_t *srow = wstage + lane * EPI_PITCH;
-        const int sub = lane >> 3, piece = lane & 7;  // row-in-group / 16-byte piece of the 128-byte row
+        const int sub = lane >> 2, piece = lane & 3;  // row-in-group (8 rows per instruction) / 16-byte piece of the 64-byte row
         long long live_rows = 0;
         for (int q = 0;; ++q) {
             const int slot = q % RING;
@@ -303,35 +336,41 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             const float dn = rows[slot].den[r];
             const bool live = (gid >= 0) && (dn > 0.0f);
             const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-            // the 8 rows this lane will reduce (rows 4*i + sub) and their accumulator rows
-            int64_t grow[8];
+            // the 4 rows this lane will reduce (rows 8*i + sub) and their accumulator rows
+            int64_t grow[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) grow[i] = (int64_t)__shfl_sync(0xffffffffu, gid, 4 * i + sub) * a.d;
+            for (int i = 0; i < 4; ++i) grow[i] = (int64_t)__shfl_sync(0xffffffffu, gid, 8 * i + sub) * a.d;
             for (int c = 0; c < a.nchunks; ++c) {
                 const int u = q * a.nchunks + c, ab = u & 1;
                 const int ncols = min(NCMAX, a.dp - c * NCMAX);   // padded columns of this chunk
                 const int dcols = min(NCMAX, a.d - c * NCMAX);    // real columns of this chunk
                 mbar_wait(bar(Smem::acc_full + ab), (u >> 1) & 1);
                 tc_fence_after();
-                for (int c0 = 0; c0 < ncols; c0 += EPI_COLS) {
+                if (quarter == 0) trace(2, 0, q, c);
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
                     float v[32];
                     tmem_ld32(tmem + lane_base + (uint32_t)(ab * NCMAX + c0), v);
-                    if (c0 >= dcols) continue;  // pure padding columns (warp-uniform)
-                    __syncwarp();  // previous piece fully read before it is overwritten
-                    if (live) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            *reinterpret_cast<float4 *>(srow + 4 * i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    }
-                    __syncwarp();
-                    const int col = c * NCMAX + c0 + 4 * piece;
-                    if (col < a.d) {
+                    for (int hc = 0; hc < 2; ++hc) {  // two 16-column (64-byte) pieces per TMEM load
+                        const int cb = c0 + 16 * hc;
+                        if (cb >= dcols) continue;  // pure padding columns (warp-uniform)
+                        __syncwarp();  // previous piece fully read before it is overwritten
+                        if (live) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int row = 4 * i + sub;
-                            if (live_mask >> row & 1u) {
-                                const float4 x = *reinterpret_cast<const float4 *>(wstage + row * EPI_PITCH + 16 * piece);
-                                red_add_v4(a.num + grow[i] + col, x.x, x.y, x.z, x.w);
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4 *>(srow + 4 * i) =
+                                    make_float4(v[16 * hc + i], v[16 * hc + i + 1], v[16 * hc + i + 2], v[16 * hc + i + 3]);
+                        }
+                        __syncwarp();
+                        const int col = c * NCMAX + cb + 4 * piece;
+                        if (col < a.d) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int row = 8 * i + sub;
+                                if (live_mask >> row & 1u) {
+                                    const float4 x = *reinterpret_cast<const float4 *>(wstage + row * EPI_PITCH + 16 * piece);
+                                    if (!(a.debug & 1)) red_add_v4(a.num + grow[i] + col, x.x, x.y, x.z, x.w);
+                                }
                             }
                         }
                     }
@@ -339,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(Smem::acc_empty + ab));
+                if (quarter == 0) trace(2, 1, q, c);
             }
             if (live) {
                 atomicAdd(a.den + gid, dn);
@@ -363,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 const int unit = ctrl[slot];
                 mbar_arrive(bar(Smem::ctrl_empty + slot));
                 if (unit < 0) break;
-                const uint8_t *tbase = a.fpack + unit * tile_bytes;
+                const uint8_t *tbase = a.fpack + unit_to_tile(unit, a.t.tw, a.t.th) * tile_bytes;
                 for (int c = 0; c < a.nchunks; ++c) {
                     const int ncols = min(NCMAX, a.dp - c * NCMAX);
                     const uint32_t bytes = (uint32_t)ncols * KSL * 4;  // hi + lo
@@ -404,6 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 const uint64_t b_lo0 = umma_smem_desc(sbase + Smem::fring + b_part, b_lbo, 128);
                 if (u >= 2) mbar_wait(bar(Smem::acc_empty + ab), ((u >> 1) - 1) & 1);
                 tc_fence_after();
+                trace(3, 0, q, c);
                 const uint32_t d_tmem = tmem + (uint32_t)(ab * NCMAX);
                 const bool last = (c == a.nchunks - 1);
 #pragma unroll 1
@@ -425,6 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 }
                 if (elect_one()) umma_commit(bar(Smem::acc_full + ab));
                 __syncwarp();
+                trace(3, 1, q, c);
             }
         }
     }
@@ -531,6 +573,11 @@ __global__ void __launch_bounds__(256) fpack_planar_kernel(const float *__restri
 
 }  // namespace
 
+static unsigned long long *g_trace = nullptr;
+void tc_set_trace(void *buf, size_t bytes) {
+    g_trace = (buf && bytes >= (size_t)kTraceRoles * kTraceCap * 16) ? (unsigned long long *)buf : nullptr;
+}
+
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // 16-byte row pieces for the bulk reduction need D % 4 == 0; tiny D is not worth a GEMM
@@ -541,33 +588,47 @@ size_t fpack_bytes(int W, int H, int d) {
     return tiles * kTilePix * (size_t)round_up(d, 16) * 4;
 }
 
+// feature re-layout only (may run on a side stream, concurrently with projection / binning of the same view)
+int launch_fpack(int W, int H, const float *F, int64_t sH, int64_t sW, int64_t sD, int d, void *fpack, cudaStream_t st) {
+    const int tw = (W + kTile - 1) / kTile, th = (H + kTile - 1) / kTile, ntiles = tw * th;
+    if (ntiles == 0) return 0;
+    GWBP_REQUIRE(((uintptr_t)fpack & 127) == 0, "fpack must be 128-byte aligned");
+    const int dp = round_up(d, 16), nchunks = (dp + NCMAX - 1) / NCMAX;
+    if (sW == 1 && sD != 1) {
+        // rows of the last tile row beyond H are never written by the planar kernel: they are only
+        // ever multiplied by zero weights, but must not hold NaN/Inf bit patterns -> clear once per view
+        if (H % kTile)
+            GWBP_CUDA_OK(cudaMemsetAsync((uint8_t *)fpack + (size_t)(th - 1) * tw * kTilePix * dp * 4, 0,
+                                         (size_t)tw * kTilePix * dp * 4, st));
+        dim3 grid((W + 31) / 32, H, nchunks);
+        fpack_planar_kernel<<<grid, 256, 0, st>>>(F, sH, sD, W, H, tw, d, dp, nchunks, (uint8_t *)fpack);
+    } else {
+        fpack_kernel<<<ntiles * nchunks, 256, 0, st>>>(F, sH, sW, sD, W, H, tw, d, dp, nchunks, (uint8_t *)fpack);
+    }
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t sW, int64_t sD, int d, float *num,
-                          float *den, void *fpack, long long *stats, cudaStream_t st) {
+                          float *den, void *fpack, bool fpack_ready, long long *stats, cudaStream_t st) {
     const int ntiles = t.tw * t.th;
     if (ntiles == 0) return 0;
     GWBP_REQUIRE(((uintptr_t)fpack & 127) == 0, "fpack must be 128-byte aligned");
     GWBP_REQUIRE(((uintptr_t)num & 15) == 0, "num must be 16-byte aligned");
     const int dp = round_up(d, 16), nchunks = (dp + NCMAX - 1) / NCMAX;
-    if (sW == 1 && sD != 1) {
-        // rows of the last tile row beyond H are never written by the planar kernel: they are only
-        // ever multiplied by zero weights, but must not hold NaN/Inf bit patterns -> clear once per view
-        if (t.H % kTile)
-            GWBP_CUDA_OK(cudaMemsetAsync((uint8_t *)fpack + (size_t)(t.th - 1) * t.tw * kTilePix * dp * 4, 0,
-                                         (size_t)t.tw * kTilePix * dp * 4, st));
-        dim3 grid((t.W + 31) / 32, t.H, nchunks);
-        fpack_planar_kernel<<<grid, 256, 0, st>>>(F, sH, sD, t.W, t.H, t.tw, d, dp, nchunks, (uint8_t *)fpack);
-    } else {
-        fpack_kernel<<<ntiles * nchunks, 256, 0, st>>>(F, sH, sW, sD, t.W, t.H, t.tw, d, dp, nchunks, (uint8_t *)fpack);
-    }
-    GWBP_CUDA_OK(cudaGetLastError());
+    if (!fpack_ready)
+        if (int rc = launch_fpack(t.W, t.H, F, sH, sW, sD, d, fpack, st)) return rc;
 
     TcArgs a;
+    a.trace = g_trace;
     a.t = t;
     a.fpack = (const uint8_t *)fpack;
     a.num = num; a.den = den;
     a.d = d; a.dp = dp; a.nchunks = nchunks; a.nunits = ntiles;
     a.unit_counter = (int *)t.scratch;
     a.stats = stats;
+    static const int dbg = getenv("GWBP_TC_DEBUG") ? atoi(getenv("GWBP_TC_DEBUG")) : 0;
+    a.debug = dbg;
     GWBP_CUDA_OK(cudaMemsetAsync(a.unit_counter, 0, sizeof(int), st));
     static bool attr_set = false;
     if (!attr_set) {

@@ -121,8 +121,10 @@ int launch_mask(const float *x, int64_t rows, int d, const float *text, int p, i
 // tcgen05 path (backproject_tc.cu)
 size_t fpack_bytes(int W, int H, int d);
 bool tc_supported(int d);
+void tc_set_trace(void *buf, size_t bytes);
+int launch_fpack(int W, int H, const float *F, int64_t sH, int64_t sW, int64_t sD, int d, void *fpack, cudaStream_t st);
 int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t sW, int64_t sD, int d,
-                          float *num, float *den, void *fpack, long long *stats, cudaStream_t st);
+                          float *num, float *den, void *fpack, bool fpack_ready, long long *stats, cudaStream_t st);
 
 // ---- device helpers ------------------------------------------------------------------------
 // One Gaussian against one pixel, gsplat rasterize_to_pixels_fwd semantics.

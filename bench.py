@@ -252,8 +252,15 @@ def run_ours(args, cfg):
         # + the feature map once + one (D+1)-float accumulator update per non-zero row
         algo_bytes = walked * 36.0 + fmap_bytes + rows * (d + 1) * 4.0
         achieved = algo_bytes / (ms_kernel * 1e-3) / 1e9 if ms_kernel > 0 else 0.0
+        traffic = None
+        try:  # dram__bytes_read+write of the same kernel from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                traffic = json.load(f).get(f"{args.config}:{'simt' if args.kernel == 'simt' else 'tc'}")
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                    "traffic": None, "peak_source": src, "kernel": "fused composite+contract+accumulate",
+                    "traffic": traffic, "peak_source": src,
+                    "kernel": "bp_simt_kernel" if args.kernel == "simt" else "bp_tc_kernel (fused composite + tcgen05 contraction + accumulate)",
                     "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": algo_bytes,
                     "rows_nonzero_per_view": rows, "entries_walked_per_view": walked,
                     "n_vis": last.n_vis, "n_isects": last.n_isects}
@@ -270,7 +277,7 @@ def run_ours(args, cfg):
                            "l2": f"{pool_n} feature maps of {fmap_bytes / 1e9:.2f} GB cycled: every view's input "
                                  "is far larger than the 126 MB L2",
                            "parallelism": f"views sharded over {world} GPU(s), one all-reduce at the end"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (5 if args.kernel != "simt" else 4),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (7 if args.kernel != "simt" else 6),
                 "ms_views": ms_views, "allreduce_ms": ms_total - ms_views, "roofline": roofline,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

@@ -38,12 +38,13 @@ extern "C" {
 #endif
 
 #define GWBP_TILE 16
-#define GWBP_ABI_VERSION 3
+#define GWBP_ABI_VERSION 4
 
 /* kernel selection for gwbp_backproject_view */
 #define GWBP_KERNEL_AUTO 0
 #define GWBP_KERNEL_SIMT 1 /* fp32 CUDA-core contraction (truth kernel, any D) */
 #define GWBP_KERNEL_TC 2   /* tcgen05 split-bf16 contraction, fp32 TMEM accumulation */
+#define GWBP_KERNEL_FPACK_READY 0x100 /* OR-ed in: `fpack` was already filled by gwbp_pack_features */
 
 /* flags for gwbp_view_prepare */
 #define GWBP_PREPARE_GSPLAT_EXACT 0 /* intersection list == gsplat-1.4.0 isect_tiles (bounding-square test) */
@@ -110,8 +111,19 @@ int gwbp_pack_scene(int64_t n, const float *means, const float *quats, const flo
 int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam_host, void *ws, size_t ws_bytes,
                       int64_t cap_isects, int32_t flags, void *stream, gwbp_view_info *info_host);
 
+/* DEBUG/PROFILING ONLY: when set to a device buffer of >= 4*4096*16 bytes, CTA 0 of the next tcgen05
+ * back-projection launches records (role, event, batch, chunk, clock64) tuples into it; NULL disables. */
+int gwbp_debug_set_trace(void *buf, size_t bytes);
+
 /* bytes of the packed bf16 feature buffer the GWBP_KERNEL_TC path needs (0 if D unsupported) */
 size_t gwbp_fpack_bytes(int32_t width, int32_t height, int32_t d);
+
+/* Re-layout of one feature map for the tcgen05 path (fp32, element strides -> bf16 hi/lo, tile-major).
+ * gwbp_backproject_view does this itself unless GWBP_KERNEL_FPACK_READY is set; exposing it lets the
+ * caller run it on a second stream, concurrently with gwbp_view_prepare of the same view (it depends
+ * only on F). */
+int gwbp_pack_features(int32_t width, int32_t height, const float *F, int64_t sH, int64_t sW, int64_t sD, int32_t d,
+                       void *fpack, void *stream);
 
 /* num[n,d] += sum_p w(g,p) F[p,:]; den[n] += sum_p w(g,p) for the prepared view.
  * F: fp32, element strides (sH,sW,sD) -- both [H,W,D]-contiguous and the reference's permuted
