@@ -216,20 +216,54 @@ __global__ void __launch_bounds__(256) project_kernel(int64_t n, const float4 *_
         rec[2 * i + 1] = make_float4(con_x, con_y, con_z, __int_as_float(radius));
     }
     if (cam.cull) {
-        // Test every tile of the bounding rectangle ONCE: rectangles of <= 64 tiles keep the result as a
-        // bit mask for the emission pass; larger ones are counted (and later re-tested) by the whole warp.
+        // Test every tile of the bounding rectangle ONCE and keep the result as a bit mask for the emission
+        // pass (rectangles of <= 64 tiles; larger ones are counted and later re-tested by the whole warp).
+        // Rectangle sizes vary from 1 to 64 tiles inside a warp, so the (Gaussian, tile) pairs of the 32
+        // lanes are pooled and dealt out evenly: lane L tests pairs L, L+32, ... of the warp's list.
+        __shared__ float4 s_cg[8][32][2];
+        __shared__ int4 s_rc[8][32];        // x0, y0, bw, inclusive pair count
+        __shared__ unsigned s_mask[8][32][2];
+        const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5;
         const CullGauss cg = cull_setup(m2x, m2y, con_x, con_y, con_z, a.w);
         const int bw = x1 - x0;
         const bool big = ok && tiles > kMaskTiles;
+        const int mine = (ok && !big) ? (int)tiles : 0;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        s_cg[wip][lane][0] = make_float4(cg.gx, cg.gy, cg.A, cg.B);
+        s_cg[wip][lane][1] = make_float4(cg.C, cg.kx, cg.ky, cg.tau);
+        s_rc[wip][lane] = make_int4(x0, y0, bw, incl);
+        s_mask[wip][lane][0] = 0u;
+        s_mask[wip][lane][1] = 0u;
+        __syncwarp();
+        for (int p = lane; p < total; p += 32) {
+            int lo = 0, hi = 31;  // owner = first lane whose inclusive count exceeds p
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int mid = (lo + hi) >> 1;
+                if (s_rc[wip][mid].w > p) hi = mid; else lo = mid + 1;
+            }
+            const int4 rc = s_rc[wip][lo];
+            const int first = lo ? s_rc[wip][lo - 1].w : 0;
+            const int k = p - first;
+            const int row = (int)(((float)k + 0.5f) / (float)rc.z);  // k / bw for small non-negative ints
+            const int col = k - row * rc.z;
+            const float4 c0 = s_cg[wip][lo][0], c1 = s_cg[wip][lo][1];
+            CullGauss g;
+            g.gx = c0.x; g.gy = c0.y; g.A = c0.z; g.B = c0.w; g.C = c1.x; g.kx = c1.y; g.ky = c1.z; g.tau = c1.w;
+            if (tile_hit(g, rc.x + col, rc.y + row, cam.W, cam.H)) atomicOr(&s_mask[wip][lo][k >> 5], 1u << (k & 31));
+        }
+        __syncwarp();
         if (ok && !big) {
-            unsigned long long mk = 0ull, bit = 1ull;  // bit k <-> k-th tile of the rectangle, row-major
-            for (int ty = y0; ty < y1; ++ty)
-                for (int tx = x0; tx < x1; ++tx, bit <<= 1)
-                    if (tile_hit(cg, tx, ty, cam.W, cam.H)) mk |= bit;
-            mask[i] = mk;
+            const unsigned long long mk = ((unsigned long long)s_mask[wip][lane][1] << 32) | s_mask[wip][lane][0];
+            mask[i] = mk;  // bit k <-> k-th tile of the rectangle, row-major
             tiles = (unsigned)__popcll(mk);
         }
-        const int lane = threadIdx.x & 31;
         unsigned m = __ballot_sync(0xffffffffu, big);
         while (m) {
             const int src = __ffs(m) - 1;

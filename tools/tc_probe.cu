@@ -153,6 +153,31 @@ __global__ void __launch_bounds__(256) acc_lane_row_v4(float *tab, const int *ro
         for (int j = 0; j < ROW / 4; ++j) red_add_v4(dst + j * 4, 1.f, 2.f, 3.f, 4.f);
     }
 }
+// what tcgen05.ld.16x256b hands out: a quad of lanes holds 8 consecutive columns (32 B) of one row, 8 rows per warp
+__global__ void __launch_bounds__(256) acc_quad_sector_v2(float *tab, const int *rows, int nrows) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, sub = lane >> 2, q = lane & 3;
+    for (int r0 = warp * 8; r0 < nrows; r0 += nw * 8) {
+        const int r = r0 + sub;
+        if (r >= nrows) continue;
+        float *dst = tab + (size_t)rows[r] * ROW + 2 * q;
+#pragma unroll 8
+        for (int j = 0; j < ROW / 8; ++j)
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dst + 8 * j), "f"(1.f), "f"(2.f) : "memory");
+    }
+}
+// 4 lanes x 16 B = 64-byte row pieces, 8 rows per instruction (the current epilogue after a smem transpose)
+__global__ void __launch_bounds__(256) acc_8rows_64B(float *tab, const int *rows, int nrows) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, sub = lane >> 2, q = lane & 3;
+    for (int r0 = warp * 8; r0 < nrows; r0 += nw * 8) {
+        const int r = r0 + sub;
+        if (r >= nrows) continue;
+        float *dst = tab + (size_t)rows[r] * ROW + 4 * q;
+#pragma unroll 8
+        for (int j = 0; j < ROW / 16; ++j) red_add_v4(dst + 16 * j, 1.f, 2.f, 3.f, 4.f);
+    }
+}
 template <int BYTES>
 __global__ void __launch_bounds__(256) acc_bulk(float *tab, const int *rows, int nrows) {
     extern __shared__ __align__(128) uint8_t sm[];
@@ -209,6 +234,8 @@ static void run_acc_probe() {
     time_it("warp-per-row red.v4 (512B/instr)", [&] { acc_warp_row_v4<<<grid, 256>>>(tab, rows, nrows); });
     time_it("warp-per-row red.f32 (128B/instr)", [&] { acc_warp_row_scalar<<<grid, 256>>>(tab, rows, nrows); });
     time_it("lane-per-row red.v4 (scattered)", [&] { acc_lane_row_v4<<<grid, 256>>>(tab, rows, nrows); });
+    time_it("quad-per-sector red.v2 (8 rows/instr)", [&] { acc_quad_sector_v2<<<grid, 256>>>(tab, rows, nrows); });
+    time_it("8 rows x 64B red.v4 / instr", [&] { acc_8rows_64B<<<grid, 256>>>(tab, rows, nrows); });
     CK(cudaFuncSetAttribute(acc_bulk<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * ROW * 4));
     time_it("bulk reduce 2048B/row", [&] { acc_bulk<2048><<<grid, 256, 8 * ROW * 4>>>(tab, rows, nrows); });
     time_it("bulk reduce 8x256B/row", [&] { acc_bulk<256><<<grid, 256, 8 * ROW * 4>>>(tab, rows, nrows); });
