@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgwbp.so")
 
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 KERNEL_FPACK_READY = 0x100
 PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL = 0, 1
 
@@ -50,6 +50,8 @@ SIGNATURES = {
     "gwbp_fpack_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "gwbp_pack_features": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                      C.c_void_p, C.c_void_p]),
+    "gwbp_pack_features_lowres": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                            C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "gwbp_backproject_view": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.c_void_p, C.POINTER(ViewInfo),
                                         C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -50,7 +50,24 @@ class BackProjector:
 
     # -- one view -------------------------------------------------------------------------
     def add_view(self, viewmat, K, width, height, feats: torch.Tensor, **cam_kw) -> View:
+        """feats: the full-resolution [H,W,D] fp32 map (any strides), as the reference builds it."""
         assert feats.shape[-1] == self.d, f"feature dim {feats.shape[-1]} != {self.d}"
+        return self._add(viewmat, K, width, height, feats, None, cam_kw)
+
+    def add_view_lowres(self, viewmat, K, width, height, feats_low: torch.Tensor, mode: str = "bilinear",
+                        **cam_kw) -> View:
+        """feats_low: the ENCODER-resolution map [h,w,D] (any strides, e.g. `net_out[0].permute(1,2,0)`).
+        Equivalent to add_view(interpolate(feats_low, (H,W), mode)) (backproject.py:110-113 / :245-249) but
+        the upsample is fused into the feature re-layout pass and the [H,W,D] tensor is never built."""
+        assert feats_low.dim() == 3 and feats_low.shape[-1] == self.d and feats_low.dtype == torch.float32
+        assert mode in ("bilinear", "nearest"), mode
+        if not fpack_bytes(int(width), int(height), self.d) or self.kernel == L.KERNEL_SIMT:
+            up = torch.nn.functional.interpolate(feats_low.permute(2, 0, 1)[None], size=(int(height), int(width)),
+                                                 mode=mode)[0].permute(1, 2, 0)
+            return self._add(viewmat, K, width, height, up, None, cam_kw)
+        return self._add(viewmat, K, width, height, feats_low, mode, cam_kw)
+
+    def _add(self, viewmat, K, width, height, feats, lowres_mode, cam_kw) -> View:
         cam = make_camera(viewmat, K, width, height, **cam_kw)
         main = torch.cuda.current_stream(self.device)
         fp, kernel = None, self.kernel
@@ -62,25 +79,35 @@ class BackProjector:
                 fp = self._fpack
             elif self.kernel == L.KERNEL_TC:
                 raise RuntimeError(f"tcgen05 kernel does not support D={self.d}")
-        if fp is not None and self.overlap_pack:
+        if fp is not None and (self.overlap_pack or lowres_mode is not None):
             if self._side is None:
                 self._side = torch.cuda.Stream(self.device)
             # order: after the previous view's kernel has finished reading fpack, and after F is ready
-            self._side.wait_stream(main)
+            side = self._side if self.overlap_pack else main
+            side.wait_stream(main)
             sH, sW, sD = feats.stride()
             with torch.cuda.device(self.device):
-                L.check(L.lib().gwbp_pack_features(cam.width, cam.height, feats.data_ptr(), sH, sW, sD, self.d,
-                                                   fp.data_ptr(), int(self._side.cuda_stream)), "gwbp_pack_features")
-            feats.record_stream(self._side)
+                if lowres_mode is None:
+                    L.check(L.lib().gwbp_pack_features(cam.width, cam.height, feats.data_ptr(), sH, sW, sD, self.d,
+                                                       fp.data_ptr(), int(side.cuda_stream)), "gwbp_pack_features")
+                else:
+                    L.check(L.lib().gwbp_pack_features_lowres(
+                        cam.width, cam.height, feats.data_ptr(), feats.shape[0], feats.shape[1], sH, sW, sD,
+                        1 if lowres_mode == "nearest" else 0, self.d, fp.data_ptr(), int(side.cuda_stream)),
+                        "gwbp_pack_features_lowres")
+            feats.record_stream(side)
             kernel = (L.KERNEL_TC if kernel == L.KERNEL_AUTO else kernel) | L.KERNEL_FPACK_READY
         view = View(self.scene, cam, self.cap, self._ws, self.tile_cull)
         self._ws, self.cap = view.ws, view.cap  # keep (possibly grown) workspace for the next view
-        if kernel & L.KERNEL_FPACK_READY:
+        if kernel & L.KERNEL_FPACK_READY and self.overlap_pack:
             main.wait_stream(self._side)
         if self.kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(main)
-        view.backproject(feats, self.num, self.den, kernel, fp, self._stats)
+        if kernel & L.KERNEL_FPACK_READY:
+            view.backproject_packed(self.d, self.num, self.den, kernel, fp, self._stats)
+        else:
+            view.backproject(feats, self.num, self.den, kernel, fp, self._stats)
         if self.kernel_events is not None:
             e1.record(main)
             self.kernel_events.append((e0, e1))

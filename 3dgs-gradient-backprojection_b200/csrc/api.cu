@@ -158,6 +158,14 @@ int gwbp_pack_features(int32_t width, int32_t height, const float *F, int64_t sH
     return launch_fpack(width, height, F, sH, sW, sD, d, fpack, (cudaStream_t)stream);
 }
 
+int gwbp_pack_features_lowres(int32_t width, int32_t height, const float *S, int32_t src_h, int32_t src_w, int64_t sH,
+                              int64_t sW, int64_t sD, int32_t nearest, int32_t d, void *fpack, void *stream) {
+    GWBP_REQUIRE(width > 0 && height > 0, "pack_features_lowres: bad image size");
+    GWBP_REQUIRE(tc_supported(d), "pack_features_lowres: tcgen05 path does not support D=%d", d);
+    GWBP_REQUIRE(S && fpack, "pack_features_lowres: NULL pointer");
+    return launch_fpack_lowres(width, height, S, src_h, src_w, sH, sW, sD, nearest, d, fpack, (cudaStream_t)stream);
+}
+
 int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws,
                           const gwbp_view_info *info, const float *F, int64_t sH, int64_t sW, int64_t sD, int32_t d,
                           float *num, float *den, int32_t kernel, void *fpack, int64_t *stats, void *stream) {

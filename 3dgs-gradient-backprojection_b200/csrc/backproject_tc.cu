@@ -571,6 +571,80 @@ __global__ void __launch_bounds__(256) fpack_planar_kernel(const float *__restri
     }
 }
 
+
+// Fused upsample + re-layout.  The reference materialises
+//   F = interpolate(encoder_out[1,D,h,w], size=(H,W), mode="bilinear")      (backproject.py:110-112, 2.2 GB/view)
+// (mode="nearest" for the DINOv2 tokens, backproject.py:245-249) only to contract it once.  Here the
+// encoder-resolution map (118 MB at 240x240x512, L2-resident) is sampled on the fly with PyTorch's
+// align_corners=False arithmetic and written straight into the packed bf16 hi/lo layout.
+__global__ void __launch_bounds__(256) fpack_lowres_kernel(const float *__restrict__ S, int sh, int sw, int64_t ssh,
+                                                           int64_t ssw, int64_t ssd, int nearest, int W, int H, int tw,
+                                                           int d, int dp, int nchunks, uint8_t *__restrict__ out) {
+    __shared__ float slab[NCMAX][33];
+    const int span = blockIdx.x, y = blockIdx.y, c = blockIdx.z;
+    const int ncols = min(NCMAX, dp - c * NCMAX);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int x = span * 32 + lane;
+    const bool xok = x < W;
+    // source coordinates (torch area_pixel_compute_source_index, align_corners=False / nearest)
+    const float scale_y = (float)sh / (float)H, scale_x = (float)sw / (float)W;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    if (nearest) {
+        y0 = y1 = min((int)floorf((float)y * scale_y), sh - 1);
+        x0 = x1 = min((int)floorf((float)x * scale_x), sw - 1);
+        ly = lx = 0.0f;
+    } else {
+        const float fy = fmaxf(scale_y * ((float)y + 0.5f) - 0.5f, 0.0f);
+        const float fx = fmaxf(scale_x * ((float)x + 0.5f) - 0.5f, 0.0f);
+        y0 = min((int)fy, sh - 1); x0 = min((int)fx, sw - 1);
+        y1 = y0 + (y0 < sh - 1 ? 1 : 0); x1 = x0 + (x0 < sw - 1 ? 1 : 0);
+        ly = fy - (float)y0; lx = fx - (float)x0;
+    }
+    const int64_t o00 = y0 * ssh + x0 * ssw, o01 = y0 * ssh + x1 * ssw, o10 = y1 * ssh + x0 * ssw, o11 = y1 * ssh + x1 * ssw;
+    // 4 channels x 4 taps = 16 independent (L1/L2-resident) loads in flight per lane
+    for (int n0 = warp; n0 < ncols; n0 += 32) {
+        float t00[4], t01[4], t10[4], t11[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int n = n0 + 8 * u, col = c * NCMAX + n;
+            const bool okc = xok && n < ncols && col < d;
+            const float *p = S + (okc ? col : 0) * ssd;
+            t00[u] = okc ? __ldg(p + o00) : 0.0f;
+            t01[u] = okc ? __ldg(p + o01) : 0.0f;
+            t10[u] = okc ? __ldg(p + o10) : 0.0f;
+            t11[u] = okc ? __ldg(p + o11) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float top = (1.0f - lx) * t00[u] + lx * t01[u];
+            const float bot = (1.0f - lx) * t10[u] + lx * t11[u];
+            if (n0 + 8 * u < ncols) slab[n0 + 8 * u][lane] = (1.0f - ly) * top + ly * bot;
+        }
+    }
+    __syncthreads();
+    const int ty = y / kTile, ks = y % kTile;
+    const uint32_t lbo = (uint32_t)(ncols / 8) * 128, part = (uint32_t)ncols * KSL * 2;
+    for (int item = t; item < 32 * (ncols / 8); item += 256) {
+        const int px = item & 31, ng = item >> 5;
+        const int tx = span * 2 + (px >> 4), p = px & 15;
+        if (tx >= tw) continue;
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = slab[8 * ng + i][px];
+        uint4 hi, lo;
+        split_bf16x2(f[0], f[1], hi.x, lo.x);
+        split_bf16x2(f[2], f[3], hi.y, lo.y);
+        split_bf16x2(f[4], f[5], hi.z, lo.z);
+        split_bf16x2(f[6], f[7], hi.w, lo.w);
+        const int tile = ty * tw + tx;
+        uint8_t *blk = out + (int64_t)tile * kTilePix * dp * 4 + (int64_t)c * NCMAX * kTilePix * 4 + (int64_t)ks * part * 2;
+        const uint32_t off = (uint32_t)(p / 8) * lbo + (uint32_t)ng * 128 + (uint32_t)(p % 8) * 16;
+        *reinterpret_cast<uint4 *>(blk + off) = hi;
+        *reinterpret_cast<uint4 *>(blk + part + off) = lo;
+    }
+}
+
 }  // namespace
 
 static unsigned long long *g_trace = nullptr;
@@ -605,6 +679,22 @@ int launch_fpack(int W, int H, const float *F, int64_t sH, int64_t sW, int64_t s
     } else {
         fpack_kernel<<<ntiles * nchunks, 256, 0, st>>>(F, sH, sW, sD, W, H, tw, d, dp, nchunks, (uint8_t *)fpack);
     }
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_fpack_lowres(int W, int H, const float *S, int sh, int sw, int64_t ssh, int64_t ssw, int64_t ssd, int nearest,
+                        int d, void *fpack, cudaStream_t st) {
+    const int tw = (W + kTile - 1) / kTile, th = (H + kTile - 1) / kTile;
+    if (tw * th == 0) return 0;
+    GWBP_REQUIRE(((uintptr_t)fpack & 127) == 0, "fpack must be 128-byte aligned");
+    GWBP_REQUIRE(sh >= 1 && sw >= 1, "low-resolution map must be at least 1x1");
+    const int dp = round_up(d, 16), nchunks = (dp + NCMAX - 1) / NCMAX;
+    if (H % kTile)
+        GWBP_CUDA_OK(cudaMemsetAsync((uint8_t *)fpack + (size_t)(th - 1) * tw * kTilePix * dp * 4, 0,
+                                     (size_t)tw * kTilePix * dp * 4, st));
+    dim3 grid((W + 31) / 32, H, nchunks);
+    fpack_lowres_kernel<<<grid, 256, 0, st>>>(S, sh, sw, ssh, ssw, ssd, nearest, W, H, tw, d, dp, nchunks, (uint8_t *)fpack);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -123,6 +123,8 @@ size_t fpack_bytes(int W, int H, int d);
 bool tc_supported(int d);
 void tc_set_trace(void *buf, size_t bytes);
 int launch_fpack(int W, int H, const float *F, int64_t sH, int64_t sW, int64_t sD, int d, void *fpack, cudaStream_t st);
+int launch_fpack_lowres(int W, int H, const float *S, int sh, int sw, int64_t ssh, int64_t ssw, int64_t ssd, int nearest,
+                        int d, void *fpack, cudaStream_t st);
 int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t sW, int64_t sD, int d,
                           float *num, float *den, void *fpack, bool fpack_ready, long long *stats, cudaStream_t st);
 

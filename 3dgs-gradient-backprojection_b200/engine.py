@@ -172,6 +172,19 @@ class View:
                 stats.data_ptr() if stats is not None else None, _stream_ptr(self.scene.device)),
                 "gwbp_backproject_view")
 
+    def backproject_packed(self, d: int, num: torch.Tensor, den: torch.Tensor, kernel: int, fpack: torch.Tensor,
+                           stats: Optional[torch.Tensor] = None) -> None:
+        """Same as backproject() when `fpack` was already filled by gwbp_pack_features[_lowres]."""
+        assert kernel & L.KERNEL_FPACK_READY and fpack is not None
+        assert num.shape == (self.scene.n, d) and num.dtype == torch.float32 and num.is_contiguous()
+        assert den.shape == (self.scene.n,) and den.dtype == torch.float32 and den.is_contiguous()
+        with torch.cuda.device(self.scene.device):
+            L.check(L.lib().gwbp_backproject_view(
+                C.byref(self.scene.c), C.byref(self.cam), self.ws.data_ptr(), C.byref(self.info), fpack.data_ptr(),
+                0, 0, 0, d, num.data_ptr(), den.data_ptr(), kernel, fpack.data_ptr(),
+                stats.data_ptr() if stats is not None else None, _stream_ptr(self.scene.device)),
+                "gwbp_backproject_view")
+
     def render(self, colors: torch.Tensor, background: Optional[torch.Tensor] = None):
         """(render [H,W,D], alpha [H,W]) for colors [N,D] (row stride free, unit inner stride)."""
         _require_cuda(colors, "colors")

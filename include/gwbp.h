@@ -38,7 +38,7 @@ extern "C" {
 #endif
 
 #define GWBP_TILE 16
-#define GWBP_ABI_VERSION 4
+#define GWBP_ABI_VERSION 5
 
 /* kernel selection for gwbp_backproject_view */
 #define GWBP_KERNEL_AUTO 0
@@ -124,6 +124,13 @@ size_t gwbp_fpack_bytes(int32_t width, int32_t height, int32_t d);
  * only on F). */
 int gwbp_pack_features(int32_t width, int32_t height, const float *F, int64_t sH, int64_t sW, int64_t sD, int32_t d,
                        void *fpack, void *stream);
+
+/* Same, fused with the upsample the reference performs first (backproject.py:110-112 bilinear,
+ * :245-249 nearest): S is the ENCODER-resolution map [src_h, src_w, d] (element strides sH,sW,sD), sampled
+ * with torch.nn.functional.interpolate(align_corners=False) arithmetic.  The full-resolution [H,W,d] map
+ * (2.2 GB at config G) is never materialised. */
+int gwbp_pack_features_lowres(int32_t width, int32_t height, const float *S, int32_t src_h, int32_t src_w, int64_t sH,
+                              int64_t sW, int64_t sD, int32_t nearest, int32_t d, void *fpack, void *stream);
 
 /* num[n,d] += sum_p w(g,p) F[p,:]; den[n] += sum_p w(g,p) for the prepared view.
  * F: fp32, element strides (sH,sW,sD) -- both [H,W,D]-contiguous and the reference's permuted

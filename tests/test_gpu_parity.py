@@ -157,6 +157,27 @@ def test_tile_culling_does_not_change_the_accumulators(gwbp, case):
     assert torch.equal(d0 > 1e-12, d1 > 1e-12)
 
 
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+def test_fused_lowres_upsample_matches_materialised(gwbp, mode):
+    """add_view_lowres(enc_out) == add_view(F.interpolate(enc_out)) (backproject.py:110-113, :245-249)."""
+    S = gwbp.scene
+    W, H, d = 211, 137, 32
+    sc = S.make_scene(6000, 9)
+    vm, K = S.make_cameras(2, W, H, 9)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    args = (_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities), d)
+    a, b = gwbp.BackProjector(*args, kernel="tc"), gwbp.BackProjector(*args, kernel="tc")
+    for v in range(2):
+        low = torch.nn.functional.normalize(torch.randn(1, d, 24, 31, generator=g, device="cuda"), dim=1)
+        full = torch.nn.functional.interpolate(low, size=(H, W), mode=mode)[0].permute(1, 2, 0)
+        a.add_view(vm[v], K, W, H, full)
+        b.add_view_lowres(vm[v], K, W, H, low[0].permute(1, 2, 0), mode=mode)
+    assert torch.allclose(a.den, b.den, rtol=1e-5, atol=1e-9)  # same weights; only the atomic order differs
+    fa, fb = a.finalize(), b.finalize()
+    seen = a.den > 1e-6
+    assert float((fa[seen] - fb[seen]).norm(dim=1).max()) < 2e-5
+
+
 def test_feature_strides_do_not_matter(gwbp, case):
     sc, vm, K, feats = case
     a = _gpu_job(gwbp, sc, vm, K, 96, 64, feats, 8, "simt", contiguous=False)
