@@ -43,10 +43,12 @@ class BackProjector:
         self.n_views = 0
         self.last_view: Optional[View] = None
         self.kernel_events = None  # set to [] to record (start, end) CUDA events around the fused kernel
-        # the feature re-layout depends only on F: it runs on a side stream, overlapping projection/binning
-        self.overlap_pack = True
+        # The feature re-layout depends only on F, so it CAN run on a second stream next to projection/binning.
+        # Measured on B200 (config G) this buys nothing -- every kernel involved is an HBM-bound full grid --
+        # so the default keeps everything on the caller's stream.
+        self.overlap_pack = False
         self._side = None
-        self._tc_done = None
+        self._main = None
 
     # -- one view -------------------------------------------------------------------------
     def add_view(self, viewmat, K, width, height, feats: torch.Tensor, **cam_kw) -> View:
@@ -69,7 +71,7 @@ class BackProjector:
 
     def _add(self, viewmat, K, width, height, feats, lowres_mode, cam_kw) -> View:
         cam = make_camera(viewmat, K, width, height, **cam_kw)
-        main = torch.cuda.current_stream(self.device)
+        cur = torch.cuda.current_stream(self.device)
         fp, kernel = None, self.kernel
         if self.kernel != L.KERNEL_SIMT:
             need = fpack_bytes(cam.width, cam.height, self.d)
@@ -79,12 +81,20 @@ class BackProjector:
                 fp = self._fpack
             elif self.kernel == L.KERNEL_TC:
                 raise RuntimeError(f"tcgen05 kernel does not support D={self.d}")
-        if fp is not None and (self.overlap_pack or lowres_mode is not None):
-            if self._side is None:
-                self._side = torch.cuda.Stream(self.device)
-            # order: after the previous view's kernel has finished reading fpack, and after F is ready
-            side = self._side if self.overlap_pack else main
-            side.wait_stream(main)
+        overlap = fp is not None and self.overlap_pack
+        if overlap and self._side is None:
+            # The feature re-layout (a 69k-CTA, HBM-bound grid) depends only on F, the geometry pipeline
+            # (a dozen small kernels) only on the camera: run them concurrently.  The geometry stream gets
+            # the higher priority, otherwise its small grids queue behind the big one and nothing overlaps.
+            self._side = torch.cuda.Stream(self.device, priority=0)
+            self._main = torch.cuda.Stream(self.device, priority=-1)
+        main = self._main if overlap else cur
+        if overlap:
+            main.wait_stream(cur)
+        if fp is not None and (overlap or lowres_mode is not None):
+            side = self._side if overlap else main
+            if overlap:
+                side.wait_stream(main)  # previous view's kernel has finished reading fpack; F is ready
             sH, sW, sD = feats.stride()
             with torch.cuda.device(self.device):
                 if lowres_mode is None:
@@ -95,22 +105,26 @@ class BackProjector:
                         cam.width, cam.height, feats.data_ptr(), feats.shape[0], feats.shape[1], sH, sW, sD,
                         1 if lowres_mode == "nearest" else 0, self.d, fp.data_ptr(), int(side.cuda_stream)),
                         "gwbp_pack_features_lowres")
-            feats.record_stream(side)
+            if overlap:
+                feats.record_stream(side)
             kernel = (L.KERNEL_TC if kernel == L.KERNEL_AUTO else kernel) | L.KERNEL_FPACK_READY
-        view = View(self.scene, cam, self.cap, self._ws, self.tile_cull)
-        self._ws, self.cap = view.ws, view.cap  # keep (possibly grown) workspace for the next view
-        if kernel & L.KERNEL_FPACK_READY and self.overlap_pack:
-            main.wait_stream(self._side)
-        if self.kernel_events is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(main)
-        if kernel & L.KERNEL_FPACK_READY:
-            view.backproject_packed(self.d, self.num, self.den, kernel, fp, self._stats)
-        else:
-            view.backproject(feats, self.num, self.den, kernel, fp, self._stats)
-        if self.kernel_events is not None:
-            e1.record(main)
-            self.kernel_events.append((e0, e1))
+        with torch.cuda.stream(main):
+            view = View(self.scene, cam, self.cap, self._ws, self.tile_cull)
+            self._ws, self.cap = view.ws, view.cap  # keep (possibly grown) workspace for the next view
+            if overlap:
+                main.wait_stream(self._side)
+            if self.kernel_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(main)
+            if kernel & L.KERNEL_FPACK_READY:
+                view.backproject_packed(self.d, self.num, self.den, kernel, fp, self._stats)
+            else:
+                view.backproject(feats, self.num, self.den, kernel, fp, self._stats)
+            if self.kernel_events is not None:
+                e1.record(main)
+                self.kernel_events.append((e0, e1))
+        if overlap:
+            cur.wait_stream(main)  # results are ordered on the caller's stream, as for any other op
         self.n_views += 1
         self.last_view = view
         return view

@@ -327,3 +327,35 @@ def test_full_size_properties_config_G_shape(gwbp):
         view.backproject(G, num4, den4, gwbp.KERNEL_SIMT)
         lhs, rhs = float((r.double() * G.double()).sum()), float((X.double() * num4.double()).sum())
         assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs), float((r.double() * G.double()).abs().sum()) * 1e-2)
+
+
+def test_full_size_config_G_properties(gwbp):
+    """BASELINE config[1] at FULL size (5.8 M Gaussians, 1297x840, D=512, tcgen05 path), checked through
+    size-independent properties: sum(den_v) == sum(alpha_v); constant features => num == den * c;
+    linearity in F; tile culling keeps every contributing row."""
+    S = gwbp.scene
+    cfg = S.CONFIGS["G"]
+    W, H, d = cfg["width"], cfg["height"], cfg["d"]
+    sc = S.make_scene(cfg["n"], 0)
+    vm, K = S.make_cameras(cfg["views"], W, H, 0)
+    args = (_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities), d)
+    c = torch.linspace(-1, 1, d, device="cuda")
+    bp = gwbp.BackProjector(*args, kernel="tc", collect_stats=True)
+    view = bp.add_view(vm[7], K, W, H, c.expand(H, W, d))
+    den = bp.den - 1e-12
+    _, alpha = view.render(torch.ones(sc.n, 1, device="cuda"))
+    tot_a, tot_d = float(alpha.double().sum()), float(den.double().sum())
+    assert abs(tot_a - tot_d) <= 2e-4 * tot_a, (tot_a, tot_d)
+    seen = den > 1e-5
+    assert int(seen.sum()) > 50_000
+    assert float((bp.num[seen] / den[seen, None] - c[None]).abs().max()) < 2e-3
+    st = bp.stats()
+    # exact (gsplat) tile list gives the same live rows
+    bp2 = gwbp.BackProjector(*args, kernel="tc", collect_stats=True, tile_cull=False)
+    v2 = bp2.add_view(vm[7], K, W, H, c.expand(H, W, d))
+    assert bp2.stats()["rows_nonzero"] == st["rows_nonzero"] and v2.n_isects > view.n_isects
+    assert torch.allclose(bp2.den, bp.den, rtol=1e-4, atol=1e-9)
+    # linearity: F -> 2F doubles num, leaves den
+    bp3 = gwbp.BackProjector(*args, kernel="tc")
+    bp3.add_view(vm[7], K, W, H, (2 * c).expand(H, W, d))
+    assert torch.allclose(bp3.num[seen], 2 * bp.num[seen], rtol=2e-4, atol=1e-6)
