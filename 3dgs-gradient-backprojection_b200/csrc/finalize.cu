@@ -13,6 +13,9 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// rows of up to 32*kRegs floats are held in registers: ONE read and one write of HBM per element
+constexpr int kRegs = 32;
+
 __global__ void __launch_bounds__(256) finalize_kernel(const float *__restrict__ num, const float *__restrict__ den,
                                                        float *__restrict__ out, int64_t n, int d) {
     const int lane = threadIdx.x & 31;
@@ -21,6 +24,28 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float *__restrict__
     const float dn = den[row];
     const float *src = num + row * d;
     float *dst = out + row * d;
+    if (d <= 32 * kRegs) {
+        float q[kRegs];
+        float ss = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kRegs; ++j) {
+            const int k = lane + 32 * j;
+            q[j] = (k < d) ? src[k] / dn : 0.0f;
+            ss += q[j] * q[j];
+        }
+        ss = warp_sum(ss);
+        const float nrm = sqrtf(ss);
+#pragma unroll
+        for (int j = 0; j < kRegs; ++j) {
+            const int k = lane + 32 * j;
+            if (k < d) {
+                float v = q[j] / nrm;
+                if (isnan(v)) v = 0.0f;
+                dst[k] = v;
+            }
+        }
+        return;
+    }
     float ss = 0.0f;
     for (int j = lane; j < d; j += 32) {
         const float q = src[j] / dn;
@@ -59,18 +84,43 @@ __global__ void __launch_bounds__(256) mask_kernel(const float *__restrict__ x, 
     __syncthreads();
     for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < rows; row += (int64_t)gridDim.x * nwarps) {
         const float *src = x + row * d;
-        float ss = 0.0f;
-        for (int k = lane; k < d; k += 32) { const float v = src[k]; ss += v * v; }
-        ss = warp_sum(ss);
-        const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
         float best_pos = -INFINITY, best_neg = -INFINITY, s0 = 0.0f;
-        for (int j = 0; j < p; ++j) {
-            float dot = 0.0f;
-            for (int k = lane; k < d; k += 32) dot += (src[k] * inv) * stext[j * d + k];
-            dot = warp_sum(dot);
-            if (j == 0) s0 = dot;
-            if (j < npos) best_pos = fmaxf(best_pos, dot); else best_neg = fmaxf(best_neg, dot);
-            if (score && lane == 0) score[row * p + j] = dot;
+        if (d <= 32 * kRegs) {  // one HBM read of the row: keep it in registers
+            float q[kRegs];
+            float ss = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kRegs; ++j) {
+                const int k = lane + 32 * j;
+                q[j] = (k < d) ? src[k] : 0.0f;
+                ss += q[j] * q[j];
+            }
+            ss = warp_sum(ss);
+            const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+            for (int jp = 0; jp < p; ++jp) {
+                float dot = 0.0f;
+#pragma unroll
+                for (int j = 0; j < kRegs; ++j) {
+                    const int k = lane + 32 * j;
+                    if (k < d) dot += (q[j] * inv) * stext[jp * d + k];
+                }
+                dot = warp_sum(dot);
+                if (jp == 0) s0 = dot;
+                if (jp < npos) best_pos = fmaxf(best_pos, dot); else best_neg = fmaxf(best_neg, dot);
+                if (score && lane == 0) score[row * p + jp] = dot;
+            }
+        } else {
+            float ss = 0.0f;
+            for (int k = lane; k < d; k += 32) { const float v = src[k]; ss += v * v; }
+            ss = warp_sum(ss);
+            const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+            for (int j = 0; j < p; ++j) {
+                float dot = 0.0f;
+                for (int k = lane; k < d; k += 32) dot += (src[k] * inv) * stext[j * d + k];
+                dot = warp_sum(dot);
+                if (j == 0) s0 = dot;
+                if (j < npos) best_pos = fmaxf(best_pos, dot); else best_neg = fmaxf(best_neg, dot);
+                if (score && lane == 0) score[row * p + j] = dot;
+            }
         }
         if (lane == 0) {
             bool m = best_pos > best_neg;

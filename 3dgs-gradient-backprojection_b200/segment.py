@@ -25,8 +25,16 @@ def render_features(scene: PackedScene, features: torch.Tensor, viewmat, K, widt
     return view.render(features)
 
 
+def gaussian_scores(features: torch.Tensor, text_feat: torch.Tensor) -> torch.Tensor:
+    """[N,P] per-Gaussian scores f_g . normalise(t_j): view-independent, compute ONCE per query and pass it
+    to render_mask_2d(scores=...) for every view."""
+    t = torch.nn.functional.normalize(text_feat.to(features.device, torch.float32), dim=1)
+    return (features.to(torch.float32) @ t.T).contiguous()
+
+
 def render_mask_2d(scene: PackedScene, features: torch.Tensor, text_feat: torch.Tensor, n_pos: int, viewmat, K,
-                   width, height, exact_render: bool = True, **cam_kw) -> torch.Tensor:
+                   width, height, exact_render: bool = True, scores: Optional[torch.Tensor] = None,
+                   **cam_kw) -> torch.Tensor:
     """Per-pixel mask of one view (segment.py:209-224).
 
     exact_render=True  : render all D channels, then normalise / score / compare per pixel, exactly
@@ -34,12 +42,14 @@ def render_mask_2d(scene: PackedScene, features: torch.Tensor, text_feat: torch.
     exact_render=False : use linearity -- render the P per-Gaussian scores f_g . t_j instead of the
                          D features (P << D); the per-pixel normalisation is a positive scale common
                          to all P scores, so the compare is unchanged in exact arithmetic
-                         (SURVEY.md §9.7)."""
-    view = View(scene, make_camera(viewmat, K, width, height, **cam_kw))
+                         (SURVEY.md §9.7).  Pass `scores=gaussian_scores(features, text_feat)` to reuse
+                         them across views."""
+    # the mask does not need gsplat-exact `meta`, so the culled (shorter) intersection list is used
+    view = View(scene, make_camera(viewmat, K, width, height, **cam_kw), tile_cull=True)
     if exact_render:
         render, _ = view.render(features)
         return cosine_mask(render, text_feat, n_pos)
-    t = torch.nn.functional.normalize(text_feat.to(features.device, torch.float32), dim=1)
-    scores = (features.to(torch.float32) @ t.T).contiguous()
+    if scores is None:
+        scores = gaussian_scores(features, text_feat)
     rs, _ = view.render(scores)
     return rs[..., :n_pos].max(dim=2)[0] > rs[..., n_pos:].max(dim=2)[0]

@@ -206,7 +206,10 @@ def run_ours(args, cfg):
         step(args.warmup + i)
     e1.record()
     if world > 1:
-        gwbp.dist.allreduce_accumulators(bp.num, bp.den)
+        if args.collective == "allreduce":
+            gwbp.dist.allreduce_accumulators(bp.num, bp.den)
+        else:  # every rank keeps (and would finalise / save) its own rows of the feature field
+            gwbp.dist.reduce_scatter_accumulators(bp.num, bp.den)
     e2.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -306,7 +309,7 @@ def run_ours(args, cfg):
                 "config": {"workload": f"config {args.config}", **cfg, "kernel": args.kernel, "features": args.features,
                            "l2": f"{pool_n} feature maps of {fmap_bytes / 1e9:.2f} GB cycled: every view's input "
                                  "is far larger than the 126 MB L2",
-                           "parallelism": f"views sharded over {world} GPU(s), one all-reduce at the end"},
+                           "parallelism": f"views sharded over {world} GPU(s), one {args.collective} of (num, den) at the end"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (7 if args.kernel != "simt" else 6),
                 "ms_views": ms_views, "allreduce_ms": ms_total - ms_views, "roofline": roofline,
                 "cpu_baseline": cpu}
@@ -327,6 +330,8 @@ def main():
     ap.add_argument("--features", default="full", choices=["full", "lowres"],
                     help="full: [H,W,D] map resident in HBM (the BASELINE metric); lowres: encoder-resolution map, "
                          "bilinear upsample fused into the feature re-layout (not the headline)")
+    ap.add_argument("--collective", default="allreduce", choices=["allreduce", "reduce_scatter"],
+                    help="closing exchange of (num, den) for N > 1")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-oracle work (0 = skip)")
     args = ap.parse_args()

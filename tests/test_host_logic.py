@@ -57,6 +57,15 @@ def _worker(rank, world, port, out):
     gwbp.dist.allreduce_accumulators(num, den)
     ref_num, ref_den = per_view_num.sum(0), per_view_den.sum(0) + gwbp.DEN_EPS
     ok = torch.allclose(num, ref_num, atol=1e-6) and torch.allclose(den, ref_den, atol=1e-6)
+    # reduce-scatter variant: every rank ends with the global sums of its own row range
+    num2 = torch.zeros(n, d)
+    den2 = torch.full((n,), gwbp.DEN_EPS)
+    for v in gwbp.dist.shard_views(n_views, rank, world):
+        num2 += per_view_num[v]
+        den2 += per_view_den[v]
+    ns, ds, lo, hi = gwbp.dist.reduce_scatter_accumulators(num2, den2)
+    ok = ok and (hi - lo) == n // world and torch.allclose(ns, ref_num[lo:hi], atol=1e-6) and \
+        torch.allclose(ds, ref_den[lo:hi], atol=1e-6)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
