@@ -156,6 +156,19 @@ class BackProjector:
         """backproject.py:166-169."""
         return _finalize(self.num, self.den, out)
 
+    def save(self, path: str, prune: bool = True, with_index: bool = True) -> torch.Tensor:
+        """Write the feature field the way the reference does (backproject.py:330): ONE float32 tensor
+        [N_pruned, D] whose rows follow `prune_by_gradients`' mask (utils.py:257-268), so segment.py can
+        `torch.load` it unchanged.  with_index additionally writes `<path>.kept.pt` (the kept Gaussian
+        indices) so consumers need not re-derive the mask."""
+        feats = self.finalize()
+        keep = self.prune_mask() if prune else torch.ones_like(self.den, dtype=torch.bool)
+        out = feats[keep].contiguous()
+        torch.save(out, path)
+        if with_index:
+            torch.save(torch.nonzero(keep).flatten().to(torch.int64).cpu(), path + ".kept.pt")
+        return out
+
 
 def create_feature_field(means, quats, scales, opacities, K, width, height, views, feature_dim: int, **kw):
     """Functional mirror of `create_feature_field_lseg(splats)` with the encoder factored out:

@@ -80,3 +80,27 @@ def test_allreduce_accumulators_world2_gloo():
         [p.join(120) for p in procs]
         assert all(p.exitcode == 0 for p in procs)
         assert dict(out) == {0: True, 1: True}
+
+
+def test_sh_colour_evaluation_cpu(gwbp):
+    """sh.py (the sh_degree=3 branch, backproject.py:88-100): DC term, clamp, and invariance of the
+    degree-0/2 parts under direction reversal (odd bands flip sign)."""
+    import importlib
+    sh = importlib.import_module("3dgs-gradient-backprojection_b200.sh")
+    g = torch.Generator().manual_seed(0)
+    means = torch.randn(50, 3, generator=g)
+    coeffs = torch.randn(50, 16, 3, generator=g) * 0.3
+    vm = torch.eye(4)
+    vm[:3, 3] = torch.tensor([0.1, -0.2, 4.0])
+    c0 = sh.eval_sh_colors(0, means, coeffs, vm)
+    assert torch.allclose(c0, torch.clamp_min(0.28209479177387814 * coeffs[:, 0] + 0.5, 0), atol=1e-6)
+    c3 = sh.eval_sh_colors(3, means, coeffs, vm)
+    assert c3.shape == (50, 3) and bool((c3 >= 0).all())
+    only_even = coeffs.clone()
+    only_even[:, 1:4] = 0
+    only_even[:, 9:16] = 0
+    cam_pos = -(vm[:3, :3].T @ vm[:3, 3])
+    mirrored = 2 * cam_pos - means  # same distance, opposite viewing direction
+    a = sh.eval_sh_colors(3, means, only_even, vm)
+    b = sh.eval_sh_colors(3, mirrored, only_even, vm)
+    assert torch.allclose(a, b, atol=1e-5)
