@@ -526,38 +526,46 @@ __global__ void __launch_bounds__(256) fpack_kernel(const float *__restrict__ F,
 // Planar input ([D,H,W] buffer exposed as a permuted [H,W,D] view: sW == 1, the reference's layout,
 // backproject.py:110-113).  Only pixels are contiguous, so one CTA takes one image row x 32 pixels
 // (two tiles) x one column chunk: every warp load is 128 contiguous bytes of one channel.
+// One CTA = one image row x 256 pixels (16 tiles) x 32 channels: every channel row is read as 1 KB of contiguous
+// bytes (DRAM page locality; planes are megabytes apart) and written back as 2 KB runs of core matrices.
+constexpr int kPlanarCols = 32, kPlanarPix = 256;
 __global__ void __launch_bounds__(256) fpack_planar_kernel(const float *__restrict__ F, int64_t sH, int64_t sD,
                                                            int W, int H, int tw, int d, int dp, int nchunks,
                                                            uint8_t *__restrict__ out) {
-    __shared__ float slab[NCMAX][33];  // [channel][pixel], +1 pad: conflict-free both ways
-    const int span = blockIdx.x, y = blockIdx.y, c = blockIdx.z;
-    const int ncols = min(NCMAX, dp - c * NCMAX);
+    __shared__ float slab[kPlanarCols][kPlanarPix + 1];  // [channel][pixel], +1 pad: conflict-free both ways
+    constexpr int kSub = NCMAX / kPlanarCols;
+    const int span = blockIdx.x, y = blockIdx.y, c = blockIdx.z / kSub, sub = blockIdx.z % kSub;
+    const int ncols = min(NCMAX, dp - c * NCMAX);          // columns of this chunk (UMMA N)
+    const int n_lo = sub * kPlanarCols;                     // this CTA's columns [n_lo, n_hi) of the chunk
+    const int n_hi = min(ncols, n_lo + kPlanarCols);
+    if (n_lo >= n_hi) return;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int x = span * 32 + lane;
-    const bool xok = x < W;
-    // 8 independent 128-byte row loads in flight per warp before the first use (memory-level parallelism)
-    for (int n0 = warp; n0 < ncols; n0 += 64) {
-        float v[8];
+    const int xb = span * kPlanarPix;
+    // warp w owns channels w, w+8, ...; one channel row = kPlanarPix/32 independent 128-byte loads per lane
+    constexpr int kLoads = kPlanarPix / 32;
+    for (int n = n_lo + warp; n < n_hi; n += 8) {
+        const int col = c * NCMAX + n;
+        const float *src = F + y * sH + col * sD + xb;
+        float v[kLoads];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int n = n0 + 8 * u, col = c * NCMAX + n;
-            v[u] = (xok && n < ncols && col < d) ? __ldg(F + y * sH + x + col * sD) : 0.0f;
+        for (int k = 0; k < kLoads; ++k) {
+            const int px = lane + 32 * k;
+            v[k] = (col < d && xb + px < W) ? __ldg(src + px) : 0.0f;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (n0 + 8 * u < ncols) slab[n0 + 8 * u][lane] = v[u];
+        for (int k = 0; k < kLoads; ++k) slab[n - n_lo][lane + 32 * k] = v[k];
     }
     __syncthreads();
     const int ty = y / kTile, ks = y % kTile;
     const uint32_t lbo = (uint32_t)(ncols / 8) * 128, part = (uint32_t)ncols * KSL * 2;
-    // item = (pixel 0..31, 8-column group): one 16-byte core-matrix row, hi and lo
-    for (int item = t; item < 32 * (ncols / 8); item += 256) {
-        const int px = item & 31, ng = item >> 5;
-        const int tx = span * 2 + (px >> 4), p = px & 15;
+    // item = (pixel 0..127, 8-column group): one 16-byte core-matrix row, hi and lo
+    for (int item = t; item < kPlanarPix * ((n_hi - n_lo) / 8); item += 256) {
+        const int px = item % kPlanarPix, ngl = item / kPlanarPix, ng = n_lo / 8 + ngl;
+        const int tx = (xb + px) >> 4, p = px & 15;
         if (tx >= tw) continue;
         float f[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = slab[8 * ng + i][px];
+        for (int i = 0; i < 8; ++i) f[i] = slab[8 * ngl + i][px];
         uint4 hi, lo;
         split_bf16x2(f[0], f[1], hi.x, lo.x);
         split_bf16x2(f[2], f[3], hi.y, lo.y);
@@ -570,7 +578,6 @@ __global__ void __launch_bounds__(256) fpack_planar_kernel(const float *__restri
         *reinterpret_cast<uint4 *>(blk + part + off) = lo;
     }
 }
-
 
 // Fused upsample + re-layout.  The reference materialises
 //   F = interpolate(encoder_out[1,D,h,w], size=(H,W), mode="bilinear")      (backproject.py:110-112, 2.2 GB/view)
@@ -674,7 +681,7 @@ int launch_fpack(int W, int H, const float *F, int64_t sH, int64_t sW, int64_t s
         if (H % kTile)
             GWBP_CUDA_OK(cudaMemsetAsync((uint8_t *)fpack + (size_t)(th - 1) * tw * kTilePix * dp * 4, 0,
                                          (size_t)tw * kTilePix * dp * 4, st));
-        dim3 grid((W + 31) / 32, H, nchunks);
+        dim3 grid((W + kPlanarPix - 1) / kPlanarPix, H, nchunks * (NCMAX / kPlanarCols));
         fpack_planar_kernel<<<grid, 256, 0, st>>>(F, sH, sD, W, H, tw, d, dp, nchunks, (uint8_t *)fpack);
     } else {
         fpack_kernel<<<ntiles * nchunks, 256, 0, st>>>(F, sH, sW, sD, W, H, tw, d, dp, nchunks, (uint8_t *)fpack);
