@@ -91,7 +91,7 @@ class BackProjector:
         main = self._main if overlap else cur
         if overlap:
             main.wait_stream(cur)
-        if fp is not None and (overlap or lowres_mode is not None):
+        if fp is not None:  # re-layout first (own entry point, so the fused kernel can be timed on its own)
             side = self._side if overlap else main
             if overlap:
                 side.wait_stream(main)  # previous view's kernel has finished reading fpack; F is ready

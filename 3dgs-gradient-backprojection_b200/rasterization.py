@@ -21,8 +21,18 @@ from typing import Optional
 import torch
 
 from . import _lib as L
-from .engine import PackedScene, View, make_camera
+from .engine import PackedScene, View, fpack_bytes, make_camera
 from .sh import eval_sh_colors
+
+_FPACK_CACHE = {}  # device -> scratch for the tcgen05 path's feature re-layout (reused across calls)
+
+
+def _fpack_buffer(device, nbytes: int) -> torch.Tensor:
+    buf = _FPACK_CACHE.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _FPACK_CACHE[device] = buf
+    return buf
 
 
 class _CompositeColors(torch.autograd.Function):
@@ -49,7 +59,8 @@ class _CompositeColors(torch.autograd.Function):
             g = v_render.to(torch.float32)
             if 0 in g.stride():
                 g = g.contiguous()
-            view.backproject(g, num, den)
+            need = fpack_bytes(view.cam.width, view.cam.height, d)  # > 0 iff the tensor-core kernel takes this D
+            view.backproject(g, num, den, L.KERNEL_AUTO, _fpack_buffer(g.device, need) if need else None)
         return num, None, None
 
 
