@@ -727,11 +727,9 @@ int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t 
     static const int dbg = getenv("GWBP_TC_DEBUG") ? atoi(getenv("GWBP_TC_DEBUG")) : 0;
     a.debug = dbg;
     GWBP_CUDA_OK(cudaMemsetAsync(a.unit_counter, 0, sizeof(int), st));
-    static bool attr_set = false;
-    if (!attr_set) {
-        GWBP_CUDA_OK(cudaFuncSetAttribute(bp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-        attr_set = true;
-    }
+    // per-device function attribute: set on every launch (microseconds) so a process that drives several
+    // devices never launches with the default 48 KB limit
+    GWBP_CUDA_OK(cudaFuncSetAttribute(bp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
     const int grid = a.nunits < kNumSMs ? a.nunits : kNumSMs;
     bp_tc_kernel<<<grid, kThreads, Smem::total, st>>>(a);
     GWBP_CUDA_OK(cudaGetLastError());
