@@ -159,6 +159,8 @@ def run_ours(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0 must print ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
+        os.environ["NCCL_DEBUG"] = os.environ.get("GWBP_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     S = gwbp.scene
     W, H, d, V = cfg["width"], cfg["height"], cfg["d"], cfg["views"]
