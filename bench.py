@@ -193,6 +193,11 @@ def run_ours(args, cfg):
 
     for i in range(args.warmup):
         step(i)
+    if world > 1:  # warm-up of the closing exchange too (NCCL channel setup / buffer registration is lazy)
+        if args.collective == "allreduce":
+            gwbp.dist.allreduce_accumulators(bp.num, bp.den)
+        else:
+            gwbp.dist.reduce_scatter_accumulators(bp.num, bp.den)
     bp.reset()
     barrier()
 
