@@ -158,6 +158,11 @@ def run_ours(args, cfg):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # Rank 0 must print exactly ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun) write to
+    # fd 1 from native code, so everything else is routed to stderr and the JSON goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         # rank 0 must print ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
         os.environ["NCCL_DEBUG"] = os.environ.get("GWBP_NCCL_DEBUG", "WARN")
@@ -320,7 +325,8 @@ def run_ours(args, cfg):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (7 if args.kernel != "simt" else 6),
                 "ms_views": ms_views, "allreduce_ms": ms_total - ms_views, "roofline": roofline,
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
