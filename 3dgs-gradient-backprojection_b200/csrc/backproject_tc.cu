@@ -16,7 +16,7 @@
 //   warps 0-7   ALU      : thread = pixel.  Walk the tile's depth-sorted list 128 Gaussians at a time,
 //                          generate w = alpha*T (sequential T per pixel), write W^T as bf16 hi/lo
 //                          straight into the UMMA canonical layout (MN-major, SWIZZLE_NONE) in smem.
-//   warp 13     producer : streams the pre-packed bf16 hi/lo feature tile through a 4-stage smem ring
+//   warp 13     producer : streams the pre-packed bf16 hi/lo feature tile through a 5-stage smem ring
 //                          with cp.async.bulk (TMA engine), one 16-pixel K-slice x <=256 columns per stage.
 //   warp 14     MMA      : one thread issues tcgen05.mma; accumulators [128 x <=256] fp32 are double
 //                          buffered in the 512 TMEM columns so the epilogue of one batch overlaps the
