@@ -27,13 +27,22 @@ DEN_EPS = 1e-12  # backproject.py:63
 
 class BackProjector:
     def __init__(self, means, quats, scales, opacities, feature_dim: int, device=None, kernel: str = "auto",
-                 cap_isects: Optional[int] = None, collect_stats: bool = False, tile_cull: bool = True):
+                 cap_isects: Optional[int] = None, collect_stats: bool = False, tile_cull: bool = True,
+                 accumulate: str = "sum"):
+        """accumulate="sum": num += num_v, den += den_v, features = num/den (backproject.py:149-150,166).
+        accumulate="per_view_ratio": features += mean-scaled num_v / (mean-scaled den_v + 1e-12) per view
+        (affordance_transfer/demo_affordance_transfer.py:768-800); `num` then holds that sum."""
+        assert accumulate in ("sum", "per_view_ratio"), accumulate
+        self.accumulate = accumulate
         self.scene = PackedScene(means, quats, scales, opacities, device)
         self.device = self.scene.device
         self.d = int(feature_dim)
         n = self.scene.n
         self.num = torch.zeros(n, self.d, dtype=torch.float32, device=self.device)       # backproject.py:62
         self.den = torch.full((n,), DEN_EPS, dtype=torch.float32, device=self.device)    # backproject.py:63
+        if accumulate == "per_view_ratio":  # per-view scratch pair, kept all-zero between views
+            self.num_v = torch.zeros(n, self.d, dtype=torch.float32, device=self.device)
+            self.den_v = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.kernel = {"auto": L.KERNEL_AUTO, "simt": L.KERNEL_SIMT, "tc": L.KERNEL_TC}[kernel]
         self.cap = cap_isects
         self.tile_cull = bool(tile_cull)
@@ -116,10 +125,15 @@ class BackProjector:
             if self.kernel_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(main)
+            ratio = self.accumulate == "per_view_ratio"
+            num, den = (self.num_v, self.den_v) if ratio else (self.num, self.den)
             if kernel & L.KERNEL_FPACK_READY:
-                view.backproject_packed(self.d, self.num, self.den, kernel, fp, self._stats)
+                view.backproject_packed(self.d, num, den, kernel, fp, self._stats)
             else:
-                view.backproject(feats, self.num, self.den, kernel, fp, self._stats)
+                view.backproject(feats, num, den, kernel, fp, self._stats)
+            if ratio:  # `.mean()` losses: 1/(H*W*D) on num, 1/(H*W*3) on den (demo_affordance_transfer.py:768,790)
+                hw = float(cam.width) * float(cam.height)
+                view.ratio_accumulate(num, den, self.num, 1.0 / (hw * self.d), 1.0 / (hw * 3.0), DEN_EPS, self.den)
             if self.kernel_events is not None:
                 e1.record(main)
                 self.kernel_events.append((e0, e1))
@@ -153,7 +167,10 @@ class BackProjector:
         return self.den > DEN_EPS
 
     def finalize(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """backproject.py:166-169."""
+        """backproject.py:166-169.  In per_view_ratio mode: L2-normalised rows of the ratio sum
+        (demo_affordance_transfer.py:800), with never-seen rows 0 instead of the reference's NaN."""
+        if self.accumulate == "per_view_ratio":
+            return _finalize(self.num, torch.ones_like(self.den), out)
         return _finalize(self.num, self.den, out)
 
     def save(self, path: str, prune: bool = True, with_index: bool = True) -> torch.Tensor:

@@ -206,6 +206,43 @@ int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam, const void
     return launch_render_simt(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream);
 }
 
+int gwbp_render_pixels(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws, const gwbp_view_info *info,
+                       const float *colors, int64_t color_stride, int32_t d, const float *extra, const int32_t *xy,
+                       int32_t k, float *out, float *alpha, void *stream) {
+    GWBP_REQUIRE(scene && info, "render_pixels: NULL pointer");
+    GWBP_REQUIRE(k >= 0 && d >= 1, "render_pixels: bad shape (k=%d d=%d)", k, d);
+    if (k == 0) return 0;
+    GWBP_REQUIRE(xy && out, "render_pixels: NULL pointer");
+    const int od = d + (extra ? 1 : 0);
+    if (scene->n == 0 || info->n_isects == 0) {
+        GWBP_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)k * od, (cudaStream_t)stream));
+        if (alpha) GWBP_CUDA_OK(cudaMemsetAsync(alpha, 0, sizeof(float) * (size_t)k, (cudaStream_t)stream));
+        return 0;
+    }
+    GWBP_REQUIRE(ws && colors, "render_pixels: NULL pointer");
+    if (int rc = check_cam(cam)) return rc;
+    GWBP_REQUIRE(color_stride >= d, "color_stride (%lld) < d (%d)", (long long)color_stride, d);
+    gwbp_ws_layout L;
+    if (int rc = gwbp_workspace_layout(scene->n, cam->width, cam->height, info->cap_isects, &L)) return rc;
+    const TileCtx t = tile_ctx(cam, ws, L, info);
+    return launch_render_pixels(t, colors, color_stride, d, extra, xy, k, out, alpha, (cudaStream_t)stream);
+}
+
+int gwbp_ratio_accumulate(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws, const gwbp_view_info *info,
+                          float *num_v, float *den_v, float *acc, float *den_acc, int32_t d, float num_scale,
+                          float den_scale, float eps, void *stream) {
+    GWBP_REQUIRE(scene && info, "ratio_accumulate: NULL pointer");
+    GWBP_REQUIRE(d >= 1, "ratio_accumulate: bad shape (d=%d)", d);
+    if (scene->n == 0 || info->n_vis == 0) return 0;
+    GWBP_REQUIRE(ws && num_v && den_v && acc, "ratio_accumulate: NULL pointer");
+    if (int rc = check_cam(cam)) return rc;
+    gwbp_ws_layout L;
+    if (int rc = gwbp_workspace_layout(scene->n, cam->width, cam->height, info->cap_isects, &L)) return rc;
+    WsDev w = ws_view(const_cast<void *>(ws), L);
+    return launch_ratio_accumulate(w.grec, info->n_vis, num_v, den_v, acc, den_acc, d, num_scale, den_scale, eps,
+                                   (cudaStream_t)stream);
+}
+
 int gwbp_finalize(const float *num, const float *den, float *out, int64_t n, int32_t d, void *stream) {
     GWBP_REQUIRE(n >= 0 && d >= 1, "finalize: bad shape");
     if (n == 0) return 0;

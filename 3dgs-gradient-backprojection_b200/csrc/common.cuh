@@ -114,6 +114,10 @@ int launch_backproject_simt(const TileCtx &t, const float *F, int64_t sH, int64_
                             float *num, float *den, long long *stats, cudaStream_t st);
 int launch_render_simt(const TileCtx &t, const float *colors, int64_t cstride, int d, const float *bg,
                        float *render, float *alpha, cudaStream_t st);
+int launch_render_pixels(const TileCtx &t, const float *colors, int64_t cstride, int d, const float *extra,
+                         const int *xy, int k, float *out, float *alpha, cudaStream_t st);
+int launch_ratio_accumulate(const float4 *grec, int64_t n_vis, float *num_v, float *den_v, float *acc, float *den_acc,
+                            int d, float num_scale, float den_scale, float eps, cudaStream_t st);
 int launch_finalize(const float *num, const float *den, float *out, int64_t n, int d, cudaStream_t st);
 int launch_mask(const float *x, int64_t rows, int d, const float *text, int p, int npos, float thr,
                 int use_thr, uint8_t *mask, float *score, cudaStream_t st);

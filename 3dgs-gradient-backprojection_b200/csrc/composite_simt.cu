@@ -201,4 +201,96 @@ int launch_render_simt(const TileCtx &t, const float *colors, int64_t cstride, i
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// probe render: the same composite at a handful of pixels (one CTA per probe pixel).
+// alpha is evaluated for 128 Gaussians in parallel, the transmittance chain T is walked by one thread
+// (it is a 128-step scalar recurrence), then every thread accumulates its channels over the batch.
+// Same arithmetic and channel summation order as render_simt_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kProbeBatch = 128, kProbeRegs = 8;  // up to 256*8 = 2048 channels
+
+__global__ void __launch_bounds__(256) render_pixels_kernel(TileCtx t, const float *__restrict__ colors,
+                                                            int64_t cstride, int d, const float *__restrict__ extra,
+                                                            const int *__restrict__ xy, float *__restrict__ out,
+                                                            float *__restrict__ alpha_out) {
+    __shared__ float s_a[kProbeBatch], s_w[kProbeBatch];
+    __shared__ int s_gid[kProbeBatch];
+    __shared__ float s_T, s_extra;
+    __shared__ int s_done;
+    const int tid = threadIdx.x, probe = blockIdx.x;
+    const int xx = xy[2 * probe], yy = xy[2 * probe + 1];
+    const int od = d + (extra ? 1 : 0);
+    float acc[kProbeRegs];
+#pragma unroll
+    for (int j = 0; j < kProbeRegs; ++j) acc[j] = 0.0f;
+    const bool inside = xx >= 0 && yy >= 0 && xx < t.W && yy < t.H;
+    if (tid == 0) { s_T = 1.0f; s_extra = 0.0f; s_done = inside ? 0 : 1; }
+    __syncthreads();
+    if (inside) {
+        const int tile = (yy / kTile) * t.tw + xx / kTile;
+        const int s = t.offsets[tile], e = t.offsets[tile + 1];
+        const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
+        for (int b = s; b < e && !s_done; b += kProbeBatch) {
+            const int nb = min(kProbeBatch, e - b);
+            if (tid < nb) {
+                const int id = t.flatten[b + tid];
+                const float4 g0 = t.grec[2 * (int64_t)id], g1 = t.grec[2 * (int64_t)id + 1];
+                const float dx = g0.x - px, dy = g0.y - py;
+                const float sigma = 0.5f * (g1.x * dx * dx + g1.z * dy * dy) + g1.y * dx * dy;
+                const float a = fminf(kAlphaMax, g0.z * __expf(-sigma));
+                s_a[tid] = (sigma >= 0.0f && a >= kAlphaMin) ? a : 0.0f;
+                s_gid[tid] = __float_as_int(g0.w);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float T = s_T, ex = s_extra;
+                bool done = false;
+                for (int k = 0; k < nb; ++k) {
+                    float w = 0.0f;
+                    const float a = s_a[k];
+                    if (!done && a > 0.0f) {
+                        const float nT = T * (1.0f - a);
+                        if (nT <= kTMin) done = true;
+                        else { w = a * T; T = nT; }
+                    }
+                    s_w[k] = w;
+                    if (extra && w > 0.0f) ex += w * extra[s_gid[k]];
+                }
+                s_T = T; s_extra = ex; s_done = done ? 1 : 0;
+            }
+            __syncthreads();
+            for (int k = 0; k < nb; ++k) {
+                const float w = s_w[k];
+                if (w > 0.0f) {
+                    const float *row = colors + (int64_t)s_gid[k] * cstride;
+#pragma unroll
+                    for (int j = 0; j < kProbeRegs; ++j) {
+                        const int c = tid + 256 * j;
+                        if (c < d) acc[j] += w * __ldg(row + c);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kProbeRegs; ++j) {
+        const int c = tid + 256 * j;
+        if (c < d) out[(int64_t)probe * od + c] = acc[j];
+    }
+    if (tid == 0) {
+        if (extra) out[(int64_t)probe * od + d] = s_extra;
+        if (alpha_out) alpha_out[probe] = 1.0f - s_T;
+    }
+}
+
+int launch_render_pixels(const TileCtx &t, const float *colors, int64_t cstride, int d, const float *extra,
+                         const int *xy, int k, float *out, float *alpha, cudaStream_t st) {
+    if (k == 0) return 0;
+    GWBP_REQUIRE(d <= 256 * kProbeRegs, "render_pixels supports D <= %d (got %d)", 256 * kProbeRegs, d);
+    render_pixels_kernel<<<k, 256, 0, st>>>(t, colors, cstride, d, extra, xy, out, alpha);
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace gwbp

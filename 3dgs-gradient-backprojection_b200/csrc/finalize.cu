@@ -67,6 +67,41 @@ int launch_finalize(const float *num, const float *den, float *out, int64_t n, i
     return 0;
 }
 
+// Per-view-ratio accumulation over the Gaussians one view saw (packed records, depth order): one warp per
+// record.  Rows the view never touched hold zeros in (num_v, den_v) and contribute 0/(0+eps) = 0 in the
+// reference's dense expression, so skipping them is exact.
+__global__ void __launch_bounds__(256) ratio_accumulate_kernel(const float4 *__restrict__ grec, int64_t n_vis,
+                                                               float *__restrict__ num_v, float *__restrict__ den_v,
+                                                               float *__restrict__ acc, float *__restrict__ den_acc, int d,
+                                                               float num_scale, float den_scale, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n_vis) return;
+    const int64_t gid = __float_as_int(grec[2 * i].w);
+    const float dv = den_v[gid];
+    if (dv == 0.0f) return;  // warp-uniform
+    const float denom = den_scale * dv + eps;
+    float *src = num_v + gid * d, *dst = acc + gid * d;
+    for (int c = lane; c < d; c += 32) {
+        dst[c] += (num_scale * src[c]) / denom;
+        src[c] = 0.0f;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        den_v[gid] = 0.0f;
+        if (den_acc) den_acc[gid] += dv;
+    }
+}
+
+int launch_ratio_accumulate(const float4 *grec, int64_t n_vis, float *num_v, float *den_v, float *acc, float *den_acc,
+                            int d, float num_scale, float den_scale, float eps, cudaStream_t st) {
+    if (n_vis == 0) return 0;
+    ratio_accumulate_kernel<<<(unsigned)((n_vis + 7) / 8), 256, 0, st>>>(grec, n_vis, num_v, den_v, acc, den_acc,
+                                                                         d, num_scale, den_scale, eps);
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // text [p, d] is staged (normalised) in shared memory; p*d*4 bytes must fit (checked on the host)
 __global__ void __launch_bounds__(256) mask_kernel(const float *__restrict__ x, int64_t rows, int d,
                                                    const float *__restrict__ text, int p, int npos, float thr,

@@ -56,6 +56,7 @@ class PackedScene:
         assert scales.shape == (n, 3), scales.shape
         assert opacities.shape == (n,), opacities.shape
         self.n = n
+        self.means = means  # kept for per-Gaussian camera depth (render_mode "+D", click prompts)
         self.geo = torch.empty(max(40 * n, 16), dtype=torch.uint8, device=device)
         with torch.cuda.device(device):
             L.check(L.lib().gwbp_pack_scene(n, means.data_ptr(), quats.data_ptr(), scales.data_ptr(),
@@ -209,6 +210,55 @@ class View:
                     background.data_ptr() if background is not None else None, out.data_ptr(), alpha.data_ptr(),
                     _stream_ptr(self.scene.device)), "gwbp_render_view")
         return out, alpha
+
+
+    def render_pixels(self, colors: torch.Tensor, xy: torch.Tensor, extra: Optional[torch.Tensor] = None):
+        """The composite of `render` at probe pixels only: (out [k, D(+1)], alpha [k]) for xy [k,2] = (x, y).
+        `extra` [N] appends one more composited channel (camera depth -> render_mode="RGB+D").  Replaces the
+        513-channel full-frame render of the click prompt, of which one pixel is read
+        (click_and_segment.py:241-262)."""
+        _require_cuda(colors, "colors")
+        assert colors.dtype == torch.float32 and colors.dim() == 2 and colors.shape[0] == self.scene.n, \
+            f"colors must be [N={self.scene.n}, D] float32, got {tuple(colors.shape)} {colors.dtype}"
+        if colors.stride(1) != 1 or colors.stride(0) < colors.shape[1]:
+            colors = colors.contiguous()
+        d = colors.shape[1]
+        xy = torch.as_tensor(xy, device=colors.device).to(torch.int32).reshape(-1, 2).contiguous()
+        k = xy.shape[0]
+        if extra is not None:
+            extra = _f32c(extra, colors.device).reshape(-1)
+            assert extra.numel() == self.scene.n, "extra must be [N]"
+        out = torch.zeros(k, d + (extra is not None), dtype=torch.float32, device=colors.device)
+        alpha = torch.zeros(k, dtype=torch.float32, device=colors.device)
+        if k and self.n_isects:
+            with torch.cuda.device(self.scene.device):
+                L.check(L.lib().gwbp_render_pixels(
+                    C.byref(self.scene.c), C.byref(self.cam), self.ws.data_ptr(), C.byref(self.info),
+                    colors.data_ptr(), colors.stride(0), d, extra.data_ptr() if extra is not None else None,
+                    xy.data_ptr(), k, out.data_ptr(), alpha.data_ptr(), _stream_ptr(self.scene.device)),
+                    "gwbp_render_pixels")
+        return out, alpha
+
+    def ratio_accumulate(self, num_v: torch.Tensor, den_v: torch.Tensor, acc: torch.Tensor, num_scale: float,
+                         den_scale: float, eps: float = 1e-12, den_acc: Optional[torch.Tensor] = None) -> None:
+        """acc += (num_scale*num_v) / (den_scale*den_v + eps) on the rows this view saw; resets those rows of
+        (num_v, den_v) to zero (affordance_transfer/demo_affordance_transfer.py:768-796); den_acc [N] += den_v if given."""
+        n = self.scene.n
+        checks = [("num_v", num_v, (n, acc.shape[1])), ("den_v", den_v, (n,)), ("acc", acc, acc.shape)]
+        if den_acc is not None:
+            checks.append(("den_acc", den_acc, (n,)))
+        for name, t_, shape in checks:
+            _require_cuda(t_, name)
+            assert t_.dtype == torch.float32 and t_.is_contiguous() and tuple(t_.shape) == tuple(shape), \
+                f"{name}: expected contiguous float32 {tuple(shape)}, got {tuple(t_.shape)} {t_.dtype}"
+        assert acc.shape[0] == n
+        if self.n_vis:
+            with torch.cuda.device(self.scene.device):
+                L.check(L.lib().gwbp_ratio_accumulate(
+                    C.byref(self.scene.c), C.byref(self.cam), self.ws.data_ptr(), C.byref(self.info),
+                    num_v.data_ptr(), den_v.data_ptr(), acc.data_ptr(),
+                    den_acc.data_ptr() if den_acc is not None else None, acc.shape[1], float(num_scale),
+                    float(den_scale), float(eps), _stream_ptr(self.scene.device)), "gwbp_ratio_accumulate")
 
 
 def fpack_bytes(width: int, height: int, d: int) -> int:

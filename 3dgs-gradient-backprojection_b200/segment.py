@@ -53,3 +53,33 @@ def render_mask_2d(scene: PackedScene, features: torch.Tensor, text_feat: torch.
         scores = gaussian_scores(features, text_feat)
     rs, _ = view.render(scores)
     return rs[..., :n_pos].max(dim=2)[0] > rs[..., n_pos:].max(dim=2)[0]
+
+
+def click_prompt(scene: PackedScene, features: torch.Tensor, viewmat, K, width, height, xy, **cam_kw):
+    """What one click of click_and_segment.py extracts (:241-275): the L2-normalised rendered feature at
+    pixel(s) xy [k,2] = (x, y) (the prompt vector) and the world-space point under the click, un-projected
+    with the rendered depth channel of `render_mode="RGB+D"`.  The reference renders all 513 channels of the
+    whole frame for this; here only the clicked pixels are composited (gwbp_render_pixels).
+
+    Returns (prompt [k,D], xyz_world [k,3], alpha [k])."""
+    vm = torch.as_tensor(viewmat, dtype=torch.float32).cpu()
+    Kc = torch.as_tensor(K, dtype=torch.float32).cpu()
+    view = View(scene, make_camera(vm, Kc, width, height, **cam_kw), tile_cull=True)
+    dev = features.device
+    z_g = scene.means @ vm[2, :3].to(dev) + vm[2, 3].to(dev)  # camera-space depth per Gaussian (the +D channel)
+    xy = torch.as_tensor(xy, device=dev).reshape(-1, 2)
+    out, alpha = view.render_pixels(features, xy, extra=z_g)
+    prompt = torch.nn.functional.normalize(out[:, :-1], dim=-1)          # click_and_segment.py:275
+    Z = out[:, -1]
+    fx, fy, cx, cy = Kc[0, 0].item(), Kc[1, 1].item(), Kc[0, 2].item(), Kc[1, 2].item()
+    cam_pt = torch.stack([(xy[:, 0].float() - cx) / fx * Z, (xy[:, 1].float() - cy) / fy * Z, Z,
+                          torch.ones_like(Z)], dim=1)                    # :262-267
+    world = (torch.inverse(vm).to(dev) @ cam_pt.T).T[:, :3]              # :269
+    return prompt, world, alpha
+
+
+def click_mask3d(features: torch.Tensor, positive_prompts: torch.Tensor, negative_prompts: torch.Tensor):
+    """mask_3d of click_and_segment.py:317-321: max_j f.pos_j > max_j f.neg_j.  Prompts are unit vectors
+    (click_prompt) and feature rows are unit or zero, so the cosine compare of get_mask3d is the same test."""
+    text = torch.cat([positive_prompts, negative_prompts], 0)
+    return cosine_mask(features, text, positive_prompts.shape[0])

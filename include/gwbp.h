@@ -23,6 +23,10 @@
  *                            (backproject.py:127-131,145-151) INCLUDING the accumulation
  *                            `gaussian_features += grad; gaussian_denoms += grad0[:,0]` (:149-150)
  *   gwbp_render_view ....... rasterize_to_pixels forward for D-channel colours (segment.py:209-220)
+ *   gwbp_render_pixels ..... the `rasterization(features, render_mode="RGB+D")` call of the click prompt,
+ *                            of which only ONE pixel is read (click_and_segment.py:241-262)
+ *   gwbp_ratio_accumulate .. `gaussian_features += grad / (grad0[:,0:1] + 1e-12)` per view
+ *                            (affordance_transfer/demo_affordance_transfer.py:768-796)
  *   gwbp_finalize .......... backproject.py:166-169
  *   gwbp_mask3d ............ segment.py:52-58
  *   gwbp_mask2d ............ segment.py:221-224
@@ -38,7 +42,7 @@ extern "C" {
 #endif
 
 #define GWBP_TILE 16
-#define GWBP_ABI_VERSION 5
+#define GWBP_ABI_VERSION 6
 
 /* kernel selection for gwbp_backproject_view */
 #define GWBP_KERNEL_AUTO 0
@@ -144,6 +148,25 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam_host, 
 int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam_host, const void *ws,
                      const gwbp_view_info *info_host, const float *colors, int64_t color_stride, int32_t d,
                      const float *background, float *render, float *alpha, void *stream);
+
+/* The same composite evaluated at k probe pixels only: out[i, 0:d] = sum_g w(g,p_i) colors[g,:] and, if
+ * `extra` [n] != NULL, out[i, d] = sum_g w(g,p_i) extra[g] (e.g. camera depth: render_mode="RGB+D").
+ * xy: device int32 [k,2] (x, y); out: [k, d + (extra != NULL)]; alpha [k] optional.  A pixel outside the
+ * image yields zeros.  Replaces a full D-channel render when only clicked pixels are read
+ * (click_and_segment.py:241-262: 513 channels rendered, one pixel used). */
+int gwbp_render_pixels(const gwbp_scene *scene, const gwbp_camera *cam_host, const void *ws,
+                       const gwbp_view_info *info_host, const float *colors, int64_t color_stride, int32_t d,
+                       const float *extra, const int32_t *xy, int32_t k, float *out, float *alpha, void *stream);
+
+/* Per-view-ratio accumulation (affordance_transfer/demo_affordance_transfer.py:768-796):
+ *   acc[g,:] += (num_scale * num_v[g,:]) / (den_scale * den_v[g] + eps)   for every Gaussian the prepared view saw,
+ * after which num_v[g,:] and den_v[g] are reset to 0, so the per-view scratch pair is ready for the next
+ * view without a dense [n,d] pass.  den_acc [n] (optional) += den_v, which keeps the den > 0 prune mask
+ * available in this mode.  num_v/den_v must have been filled by gwbp_backproject_view for THIS view
+ * starting from zeros. */
+int gwbp_ratio_accumulate(const gwbp_scene *scene, const gwbp_camera *cam_host, const void *ws,
+                          const gwbp_view_info *info_host, float *num_v, float *den_v, float *acc, float *den_acc,
+                          int32_t d, float num_scale, float den_scale, float eps, void *stream);
 
 /* out[g,:] = normalise(num[g,:]/den[g]); NaN -> 0   (backproject.py:166-169); out may alias num */
 int gwbp_finalize(const float *num, const float *den, float *out, int64_t n, int32_t d, void *stream);

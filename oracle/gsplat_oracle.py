@@ -389,6 +389,23 @@ def finalize(num, den):
     return f
 
 
+def ratio_backproject(views_num_den, width, height, d, eps=1e-12):
+    """Per-view-ratio accumulation of affordance_transfer/demo_affordance_transfer.py:768-800:
+    both losses are `.mean()`s, so grad = num_v/(H*W*D) and grad0[:,0] = den_v/(H*W*3) (3-channel ones render);
+    features = sum_v grad / (grad0[:,0:1] + 1e-12), then L2-normalised rows (:800).
+    views_num_den: iterable of per-view (num_v [N,D], den_v [N]) as returned by backproject_view.  fp64."""
+    acc = None
+    hw = float(width) * float(height)
+    for num_v, den_v in views_num_den:
+        g = num_v.astype(np.float64) / (hw * d)
+        g0 = den_v.astype(np.float64) / (hw * 3.0)
+        r = g / (g0[:, None] + eps)
+        acc = r if acc is None else acc + r
+    with np.errstate(all="ignore"):
+        f = acc / np.linalg.norm(acc, axis=-1, keepdims=True)
+    return acc, f  # rows never seen are NaN in f, as in the reference
+
+
 def prune_mask(den_without_eps):
     """utils.py:236-257: a Gaussian survives iff its accumulated colour gradient is non-zero in
     at least one view, i.e. iff sum_v sum_p w > 0."""
@@ -408,6 +425,17 @@ def mask3d(features, text, n_pos, threshold=None):
     if threshold is not None:
         m = m & (score[:, 0] > threshold)
     return m, score
+
+
+def click_prompt(render_rgbd, viewmat, K, xy):
+    """click_and_segment.py:254-275 for one clicked pixel: `render_rgbd` [H,W,D+1] is the RGB+D render
+    (features + camera depth as last channel).  Returns (normalised prompt feature [D], world point [3])."""
+    x, y = int(xy[0]), int(xy[1])
+    out, Z = render_rgbd[y, x, :-1].astype(np.float64), float(render_rgbd[y, x, -1])
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    cam = np.array([(x - cx) / fx * Z, (y - cy) / fy * Z, Z, 1.0])
+    world = np.linalg.inv(viewmat.astype(np.float64)) @ cam
+    return _normalize(out[None], 1)[0], world[:3]
 
 
 def mask2d(render, text, n_pos):

@@ -405,3 +405,75 @@ def test_rasterization_backgrounds_depth_modes_and_sh(gwbp, coracle, case, tmp_p
     assert loaded.shape == (int(bp.prune_mask().sum()), 8) and loaded.dtype == torch.float32
     assert torch.equal(loaded.cpu(), saved.cpu()) and kept.numel() == loaded.shape[0]
     assert torch.allclose(loaded.norm(dim=1), torch.ones(loaded.shape[0], device=loaded.device), atol=1e-4)
+
+
+def test_probe_pixel_render_and_click_prompt(gwbp, coracle, noracle, case):
+    """gwbp_render_pixels == the full RGB+D render read at the clicked pixels (click_and_segment.py:241-275)."""
+    sc, vm, K, _ = case
+    rng = np.random.default_rng(5)
+    feats = rng.standard_normal((sc.n, 24)).astype(np.float32)
+    feats /= np.linalg.norm(feats, axis=1, keepdims=True)
+    z = (sc.means @ vm[0][2, :3] + vm[0][2, 3]).astype(np.float32)
+    cv = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[0], K, 96, 64)
+    r_o, a_o = cv.render(np.concatenate([feats, z[:, None]], 1))
+    xy = np.array([[0, 0], [95, 63], [48, 32], [17, 40], [80, 5], [33, 33], [-1, 3], [96, 10]], np.int32)
+    scene = gwbp.PackedScene(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities))
+    for cull in (False, True):
+        view = gwbp.View(scene, gwbp.make_camera(vm[0], K, 96, 64), tile_cull=cull)
+        out, alpha = view.render_pixels(_dev(feats), _dev(xy), extra=_dev(z))
+        out, alpha = out.double().cpu().numpy(), alpha.double().cpu().numpy()
+        assert out.shape == (8, 25)
+        for i, (x, y) in enumerate(xy):
+            if 0 <= x < 96 and 0 <= y < 64:
+                assert np.abs(out[i] - r_o[y, x]).max() < 1e-5 * max(1.0, np.abs(r_o[y, x]).max()), (i, cull)
+                assert abs(alpha[i] - a_o[y, x]) < 1e-5
+            else:
+                assert np.abs(out[i]).max() == 0.0 and alpha[i] == 0.0
+        # against our own full-frame render: same arithmetic
+        full, _ = view.render(torch.cat([_dev(feats), _dev(z)[:, None]], 1))
+        full = full.double().cpu().numpy()
+        for i, (x, y) in enumerate(xy[:6]):
+            assert np.abs(out[i] - full[y, x]).max() < 1e-6 * max(1.0, np.abs(full[y, x]).max())
+    # no `extra`: D columns
+    out2, _ = view.render_pixels(_dev(feats), _dev(xy[:3]))
+    assert out2.shape == (3, 24) and np.allclose(out2.cpu().numpy(), out[:3, :24], atol=1e-6)
+    # click prompt: normalised feature + un-projected world point, then the 3-D mask compare (:317-321)
+    covered = [i for i in range(6) if a_o[xy[i, 1], xy[i, 0]] > 0.5]
+    assert len(covered) >= 2
+    prompt, world, _ = gwbp.click_prompt(scene, _dev(feats), vm[0], K, 96, 64, xy[covered])
+    for j, i in enumerate(covered):
+        p_o, w_o = noracle.click_prompt(r_o, vm[0], K, xy[i])
+        assert np.abs(prompt[j].double().cpu().numpy() - p_o).max() < 1e-5
+        assert np.abs(world[j].double().cpu().numpy() - w_o).max() < 1e-3 * max(1.0, np.abs(w_o).max())
+    m = gwbp.click_mask3d(_dev(feats), prompt[:1], prompt[1:]).cpu().numpy()
+    s = feats.astype(np.float64) @ prompt.double().cpu().numpy().T
+    m_o = s[:, 0] > s[:, 1:].max(1)
+    assert ((m != m_o) & (np.abs(s[:, 0] - s[:, 1:].max(1)) > 1e-5)).sum() == 0
+
+
+@pytest.mark.parametrize("kernel,d", [("simt", 8), ("tc", 32)])
+def test_per_view_ratio_accumulation(gwbp, coracle, noracle, kernel, d):
+    """accumulate="per_view_ratio": features += grad/(grad0 + 1e-12) per view
+    (affordance_transfer/demo_affordance_transfer.py:768-800)."""
+    sc, vm, K, feats = small_case(gwbp.scene, n=3000, views=3, d=d, seed=4)
+    per_view = []
+    for v in range(3):
+        num = np.zeros((sc.n, d), np.float64)
+        den = np.zeros(sc.n, np.float64)
+        cv = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, 96, 64)
+        cv.backproject(np.asarray(feats[v]), num, den)
+        per_view.append((num, den))
+    acc_o, f_o = noracle.ratio_backproject(per_view, 96, 64, d)
+    bp = gwbp.BackProjector(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities), d, kernel=kernel,
+                            accumulate="per_view_ratio")
+    for v in range(3):
+        bp.add_view(vm[v], K, 96, 64, _feat_dev(feats[v]))
+    assert float(bp.num_v.abs().max()) == 0.0 and float(bp.den_v.abs().max()) == 0.0  # scratch left clean
+    den_total = sum(dv for _, dv in per_view)
+    assert np.array_equal(bp.prune_mask().cpu().numpy(), den_total > 0)
+    f = bp.finalize().double().cpu().numpy()
+    # rows whose per-view den is comparable to eps*(H*W*3) are dominated by the epsilon: keep well-seen rows
+    sel = np.all([(dv == 0) | (dv > 1e-4) for _, dv in per_view], axis=0) & (den_total > 1e-4)
+    rel, _ = row_rel_err(f[sel], f_o[sel])
+    assert sel.sum() > 100 and np.percentile(rel, 99.9) <= REL_TOL, (sel.sum(), np.percentile(rel, 99.9))
+    assert np.abs(f[den_total == 0]).max() == 0.0  # never-seen rows: 0 (the reference leaves NaN)

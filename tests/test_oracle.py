@@ -171,6 +171,32 @@ def test_pruned_gaussians_do_not_change_the_render(case, noracle, coracle):
         assert np.abs(full - pruned).max() < 1.0 / (255 * 2)  # utils.py:353-355
 
 
+def test_per_view_ratio_and_click_prompt_restatements(case, noracle, coracle):
+    """8f row 4.  (a) with ONE view the per-view ratio is a positive per-row rescale of num/den, so its
+    normalised rows equal finalize(num, den) wherever den >> eps*(H*W*3)
+    (demo_affordance_transfer.py:768-800 vs backproject.py:166-169).  (b) the un-projected click point
+    re-projects onto the clicked pixel at the rendered depth (click_and_segment.py:254-269)."""
+    sc, vm, K, feats = case
+    num = np.zeros((sc.n, 8), np.float64)
+    den = np.zeros(sc.n, np.float64)
+    cv = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[0], K, 96, 64)
+    cv.backproject(np.asarray(feats[0]), num, den)
+    _, f_ratio = noracle.ratio_backproject([(num, den)], 96, 64, 8)
+    f_sum = noracle.finalize(num, den + 1e-12)
+    sel = den > 1e-3
+    assert sel.sum() > 100 and np.abs(f_ratio[sel] - f_sum[sel]).max() < 1e-9
+    assert np.isnan(f_ratio[den == 0]).all()  # the reference leaves never-seen rows NaN in this mode
+    z = (sc.means @ vm[0][2, :3] + vm[0][2, 3]).astype(np.float32)
+    rgbd, alpha = cv.render(np.concatenate([sc.means.astype(np.float32), z[:, None]], 1))
+    ys, xs = np.nonzero(alpha > 0.9)
+    x, y = int(xs[len(xs) // 2]), int(ys[len(ys) // 2])
+    prompt, world = noracle.click_prompt(rgbd, vm[0], K, (x, y))
+    assert abs(np.linalg.norm(prompt) - 1.0) < 1e-12
+    cam = vm[0].astype(np.float64) @ np.append(world, 1.0)
+    assert abs(cam[2] - rgbd[y, x, -1]) < 1e-9
+    assert abs(K[0, 0] * cam[0] / cam[2] + K[0, 2] - x) < 1e-6 and abs(K[1, 1] * cam[1] / cam[2] + K[1, 2] - y) < 1e-6
+
+
 def test_edge_cases(gwbp, noracle, coracle):
     S = gwbp.scene
     vm, K = S.make_cameras(1, 40, 24, 0)
