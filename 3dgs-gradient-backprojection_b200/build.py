@@ -27,6 +27,7 @@ SOURCES = {
     "composite_simt.cu": [],
     "finalize.cu": [],
     "backproject_tc.cu": [],
+    "render_tc.cu": [],
 }
 
 

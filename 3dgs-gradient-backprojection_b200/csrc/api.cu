@@ -193,7 +193,7 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam, const
 
 int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws, const gwbp_view_info *info,
                      const float *colors, int64_t color_stride, int32_t d, const float *background, float *render,
-                     float *alpha, void *stream) {
+                     float *alpha, int32_t kernel, void *stream) {
     GWBP_REQUIRE(scene && info, "render_view: NULL pointer");
     if (scene->n == 0 || info->n_isects == 0) return 0;
     GWBP_REQUIRE(ws && colors && render, "render_view: NULL pointer");
@@ -203,6 +203,11 @@ int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam, const void
     gwbp_ws_layout L;
     if (int rc = gwbp_workspace_layout(scene->n, cam->width, cam->height, info->cap_isects, &L)) return rc;
     const TileCtx t = tile_ctx(cam, ws, L, info);
+    int k = kernel & 0xff;
+    if (k == GWBP_KERNEL_AUTO)
+        k = (d >= 64 && render_tc_supported(colors, color_stride, d)) ? GWBP_KERNEL_TC : GWBP_KERNEL_SIMT;
+    if (k == GWBP_KERNEL_TC) return launch_render_tc(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream);
+    GWBP_REQUIRE(k == GWBP_KERNEL_SIMT, "unknown kernel id %d", kernel);
     return launch_render_simt(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream);
 }
 

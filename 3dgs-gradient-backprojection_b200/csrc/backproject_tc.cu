@@ -658,6 +658,7 @@ static unsigned long long *g_trace = nullptr;
 void tc_set_trace(void *buf, size_t bytes) {
     g_trace = (buf && bytes >= (size_t)kTraceRoles * kTraceCap * 16) ? (unsigned long long *)buf : nullptr;
 }
+void *tc_trace_buffer() { return g_trace; }
 
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 

@@ -126,11 +126,17 @@ int launch_mask(const float *x, int64_t rows, int d, const float *text, int p, i
 size_t fpack_bytes(int W, int H, int d);
 bool tc_supported(int d);
 void tc_set_trace(void *buf, size_t bytes);
+void *tc_trace_buffer();  // debug buffer set by gwbp_debug_set_trace (nullptr = off)
 int launch_fpack(int W, int H, const float *F, int64_t sH, int64_t sW, int64_t sD, int d, void *fpack, cudaStream_t st);
 int launch_fpack_lowres(int W, int H, const float *S, int sh, int sw, int64_t ssh, int64_t ssw, int64_t ssd, int nearest,
                         int d, void *fpack, cudaStream_t st);
 int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t sW, int64_t sD, int d,
                           float *num, float *den, void *fpack, bool fpack_ready, long long *stats, cudaStream_t st);
+
+// tcgen05 forward render (render_tc.cu)
+bool render_tc_supported(const float *colors, int64_t cstride, int d);
+int launch_render_tc(const TileCtx &t, const float *colors, int64_t cstride, int d, const float *bg, float *render,
+                     float *alpha, cudaStream_t st);
 
 // ---- device helpers ------------------------------------------------------------------------
 // One Gaussian against one pixel, gsplat rasterize_to_pixels_fwd semantics.

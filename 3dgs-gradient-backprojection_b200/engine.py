@@ -186,8 +186,9 @@ class View:
                 stats.data_ptr() if stats is not None else None, _stream_ptr(self.scene.device)),
                 "gwbp_backproject_view")
 
-    def render(self, colors: torch.Tensor, background: Optional[torch.Tensor] = None):
-        """(render [H,W,D], alpha [H,W]) for colors [N,D] (row stride free, unit inner stride)."""
+    def render(self, colors: torch.Tensor, background: Optional[torch.Tensor] = None, kernel: int = L.KERNEL_AUTO):
+        """(render [H,W,D], alpha [H,W]) for colors [N,D] (row stride free, unit inner stride).
+        kernel: KERNEL_AUTO (tcgen05 for D >= 64), KERNEL_SIMT (fp32 CUDA cores) or KERNEL_TC."""
         _require_cuda(colors, "colors")
         assert colors.dtype == torch.float32 and colors.dim() == 2 and colors.shape[0] == self.scene.n, \
             f"colors must be [N={self.scene.n}, D] float32, got {tuple(colors.shape)} {colors.dtype}"
@@ -195,8 +196,9 @@ class View:
             colors = colors.contiguous()
         d = colors.shape[1]
         H, W = self.cam.height, self.cam.width
-        out = torch.zeros(H, W, d, dtype=torch.float32, device=colors.device)
-        alpha = torch.zeros(H, W, dtype=torch.float32, device=colors.device)
+        alloc = torch.empty if self.n_isects else torch.zeros  # the kernels write every pixel
+        out = alloc(H, W, d, dtype=torch.float32, device=colors.device)
+        alpha = alloc(H, W, dtype=torch.float32, device=colors.device)
         if background is not None:
             background = _f32c(background, colors.device).reshape(-1)
             assert background.numel() == d
@@ -208,7 +210,7 @@ class View:
                     C.byref(self.scene.c), C.byref(self.cam), self.ws.data_ptr(), C.byref(self.info),
                     colors.data_ptr(), colors.stride(0), d,
                     background.data_ptr() if background is not None else None, out.data_ptr(), alpha.data_ptr(),
-                    _stream_ptr(self.scene.device)), "gwbp_render_view")
+                    int(kernel), _stream_ptr(self.scene.device)), "gwbp_render_view")
         return out, alpha
 
 

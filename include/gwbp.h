@@ -42,9 +42,9 @@ extern "C" {
 #endif
 
 #define GWBP_TILE 16
-#define GWBP_ABI_VERSION 6
+#define GWBP_ABI_VERSION 7
 
-/* kernel selection for gwbp_backproject_view */
+/* kernel selection for gwbp_backproject_view and gwbp_render_view */
 #define GWBP_KERNEL_AUTO 0
 #define GWBP_KERNEL_SIMT 1 /* fp32 CUDA-core contraction (truth kernel, any D) */
 #define GWBP_KERNEL_TC 2   /* tcgen05 split-bf16 contraction, fp32 TMEM accumulation */
@@ -144,10 +144,14 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam_host, 
                           int32_t d, float *num, float *den, int32_t kernel, void *fpack, int64_t *stats,
                           void *stream);
 
-/* render[H,W,d] = sum_g w(g,p) colors[g,:] (+ (1-alpha) background), alpha[H,W] = 1-T */
+/* render[H,W,d] = sum_g w(g,p) colors[g,:] (+ (1-alpha) background), alpha[H,W] = 1-T.  Every in-image pixel
+ * of `render` and `alpha` is written (no pre-zeroing needed).  kernel: GWBP_KERNEL_SIMT = fp32 CUDA cores,
+ * weights regenerated per 32-channel chunk like gsplat; GWBP_KERNEL_TC = tcgen05 split-bf16 contraction, weights
+ * generated once per 256 channels (needs 32 <= d, d % 4 == 0, 16-byte aligned rows); AUTO picks TC when it can
+ * and d >= 64. */
 int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam_host, const void *ws,
                      const gwbp_view_info *info_host, const float *colors, int64_t color_stride, int32_t d,
-                     const float *background, float *render, float *alpha, void *stream);
+                     const float *background, float *render, float *alpha, int32_t kernel, void *stream);
 
 /* The same composite evaluated at k probe pixels only: out[i, 0:d] = sum_g w(g,p_i) colors[g,:] and, if
  * `extra` [n] != NULL, out[i, d] = sum_g w(g,p_i) extra[g] (e.g. camera depth: render_mode="RGB+D").

@@ -477,3 +477,33 @@ def test_per_view_ratio_accumulation(gwbp, coracle, noracle, kernel, d):
     rel, _ = row_rel_err(f[sel], f_o[sel])
     assert sel.sum() > 100 and np.percentile(rel, 99.9) <= REL_TOL, (sel.sum(), np.percentile(rel, 99.9))
     assert np.abs(f[den_total == 0]).max() == 0.0  # never-seen rows: 0 (the reference leaves NaN)
+
+
+@pytest.mark.parametrize("d,W,H", [(64, 96, 64), (128, 96, 64), (512, 100, 70), (100, 41, 37), (768, 64, 48)])
+def test_tcgen05_forward_render(gwbp, coracle, d, W, H):
+    """The tcgen05 forward render against the CPU oracle and the fp32 CUDA-core kernel (segment.py:209-220)."""
+    sc = gwbp.scene.make_scene(3000, 3)
+    vm, K = gwbp.scene.make_cameras(2, W, H, 3)
+    rng = np.random.default_rng(d)
+    feats = rng.standard_normal((sc.n, d)).astype(np.float32)
+    feats /= np.linalg.norm(feats, axis=1, keepdims=True)
+    bg = rng.uniform(0, 1, d).astype(np.float32)
+    scene = gwbp.PackedScene(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities))
+    for v, cull in ((0, False), (1, True)):
+        view = gwbp.View(scene, gwbp.make_camera(vm[v], K, W, H), tile_cull=cull)
+        r_tc, a_tc = view.render(_dev(feats), None, gwbp.KERNEL_TC)
+        r_si, a_si = view.render(_dev(feats), None, gwbp.KERNEL_SIMT)
+        r_o, a_o = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, W, H).render(feats)
+        scale = np.abs(r_o).max()
+        err = np.abs(r_tc.double().cpu().numpy() - r_o)
+        assert np.percentile(err, 99.9) < 1e-5 * max(1.0, scale) and err.max() < 1e-2, (err.max(), np.percentile(err, 99.9))
+        assert np.abs(a_tc.double().cpu().numpy() - a_o).max() < 1e-3
+        assert float((r_tc - r_si).abs().max()) < 2e-5 * max(1.0, scale)   # same weights, split-bf16 vs fp32 contraction
+        assert float((a_tc - a_si).abs().max()) < 1e-5  # ex2-based vs __expf-based alpha
+        # background term: render += T * bg
+        r_bg, _ = view.render(_dev(feats), _dev(bg), gwbp.KERNEL_TC)
+        want = r_tc + (1.0 - a_tc)[..., None] * _dev(bg)
+        assert float((r_bg - want).abs().max()) < 1e-5
+    # AUTO picks the tensor-core kernel for wide features and still renders RGB (D = 3) on CUDA cores
+    rgb, _ = view.render(_dev(feats[:, :3].copy()))
+    assert rgb.shape == (H, W, 3)

@@ -29,8 +29,16 @@ ms_exact, m_exact = timed(lambda i: gwbp.render_mask_2d(scene, feats, text, 1, v
 scores = gwbp.gaussian_scores(feats, text)  # once per query
 ms_lin, m_lin = timed(lambda i: gwbp.render_mask_2d(scene, feats, text, 1, vm[i], K, W, H, exact_render=False, scores=scores), nv)
 ms_3d, _ = timed(lambda i: gwbp.get_mask3d(feats, text, 1), 5)
+# forward render kernels alone, on one prepared view (prepare excluded): fp32 CUDA cores vs tcgen05
+view = gwbp.View(scene, gwbp.make_camera(vm[1], K, W, H), tile_cull=True)
+ms_simt, (r_simt, _) = timed(lambda i: view.render(feats, None, gwbp.KERNEL_SIMT), 3)
+ms_tc, (r_tc, _) = timed(lambda i: view.render(feats, None, gwbp.KERNEL_TC), 5)
+render_maxdiff = float((r_simt - r_tc).abs().max())
+del r_simt, r_tc
 diff = int((m_exact != m_lin).sum())
 out = {"config": "Q", "views_timed": nv, "ms_per_view_exact_render": ms_exact, "frames_per_s_exact": 1e3 / ms_exact,
        "ms_per_view_score_render": ms_lin, "frames_per_s_score_render": 1e3 / ms_lin, "mask3d_ms": ms_3d,
-       "mask3d_GBps": sc.n * d * 4 / ms_3d / 1e6, "pixels_differing_between_paths": diff, "pixels": W * H}
+       "mask3d_GBps": sc.n * d * 4 / ms_3d / 1e6, "pixels_differing_between_paths": diff, "pixels": W * H,
+       "render_kernel_ms_simt": ms_simt, "render_kernel_ms_tcgen05": ms_tc, "render_tc_vs_simt_max_abs_diff": render_maxdiff,
+       "render_output_GBps_tcgen05": W * H * d * 4 / ms_tc / 1e6}
 print(json.dumps(out))

@@ -122,6 +122,98 @@ static void run_umma_probe() {
     cudaFree(dA); cudaFree(dB); cudaFree(dD);
 }
 
+// (A2) same GEMM with B K-major (the forward render's W operand: element (n,k) = 8 consecutive k per 16-byte
+// core-matrix row): validates which of LBO/SBO is the K-direction stride for a K-major SWIZZLE_NONE operand.
+template <int N, int K>
+__global__ void __launch_bounds__(128) umma_probe_kmajor_b(const float *__restrict__ A, const float *__restrict__ B,
+                                                           float *__restrict__ D, int swap_lbo_sbo) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    constexpr uint32_t SBO_A = 128, LBO_A = 16 * 128;
+    constexpr uint32_t NSTR_B = 128, KSTR_B = (N / 8) * 128;  // N-group stride / K-group stride of B's core matrices
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + (K / 8) * LBO_A;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 128 * K; i += 128) {
+        const int m = i % 128, k = i / 128;
+        *reinterpret_cast<__nv_bfloat16 *>(sA + (m / 8) * SBO_A + (k / 8) * LBO_A + (k % 8) * 16 + (m % 8) * 2) =
+            __float2bfloat16(A[m * K + k]);
+    }
+    for (int i = tid; i < N * K; i += 128) {
+        const int n = i % N, k = i / N;
+        *reinterpret_cast<__nv_bfloat16 *>(sB + (n / 8) * NSTR_B + (k / 8) * KSTR_B + (n % 8) * 16 + (k % 8) * 2) =
+            __float2bfloat16(B[n * K + k]);
+    }
+    fence_proxy_async_smem();
+    if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_base));
+    if (tid == 0) {
+        mbar_init(smem_u32(&bar), 1);
+        mbar_init_fence();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, N, true, false);
+        for (int ks = 0; ks < K / 16; ++ks) {
+            const uint32_t a0 = smem_u32(sA) + ks * 2 * LBO_A, b0 = smem_u32(sB) + ks * 2 * KSTR_B;
+            const uint64_t da = umma_smem_desc(a0, LBO_A, SBO_A);
+            const uint64_t db = swap_lbo_sbo ? umma_smem_desc(b0, NSTR_B, KSTR_B) : umma_smem_desc(b0, KSTR_B, NSTR_B);
+            umma_bf16(tm, da, db, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bar));
+    }
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+    for (int c = 0; c < N; c += 32) {
+        float v[32];
+        tmem_ld32(tm + ((uint32_t)(32 * warp) << 16) + c, v);
+        for (int j = 0; j < 32; ++j)
+            if (c + j < N) D[(32 * warp + (tid & 31)) * N + c + j] = v[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tm);
+}
+
+template <int N, int K>
+static void run_umma_probe_kmajor_b(int swap) {
+    std::vector<float> A(128 * K), B(N * K), D(128 * N);
+    srand(2);
+    for (auto &x : A) x = (float)(rand() % 255 - 127) / 64.0f;
+    for (auto &x : B) x = (float)(rand() % 255 - 127) / 64.0f;
+    float *dA, *dB, *dD;
+    CK(cudaMalloc(&dA, A.size() * 4));
+    CK(cudaMalloc(&dB, B.size() * 4));
+    CK(cudaMalloc(&dD, D.size() * 4));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0, D.size() * 4));
+    const size_t smem = (size_t)(K / 8) * 16 * 128 + (size_t)(K / 8) * (N / 8) * 128;
+    CK(cudaFuncSetAttribute(umma_probe_kmajor_b<N, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_probe_kmajor_b<N, K><<<1, 128, smem>>>(dA, dB, dD, swap);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("[umma B K-major N=%d K=%d kdir-stride-in-%s] kernel error: %s\n", N, K, swap ? "SBO" : "LBO",
+               cudaGetErrorString(e));
+        exit(2);
+    }
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0;
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            double r = 0;
+            for (int k = 0; k < K; ++k) r += (double)A[m * K + k] * B[n * K + k];
+            maxerr = fmax(maxerr, fabs(r - D[m * N + n]));
+            maxref = fmax(maxref, fabs(r));
+        }
+    printf("[umma B K-major N=%d K=%d kdir-stride-in-%s] max|err|=%.4g (max|ref|=%.4g) %s\n", N, K,
+           swap ? "SBO" : "LBO", maxerr, maxref, maxerr < 1e-3 * maxref ? "MATCH" : "mismatch");
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+}
+
 // ------------------------------------------------------------------------------------------------
 // (B) scattered accumulation of 2 KB fp32 rows into a table much larger than L2
 // ------------------------------------------------------------------------------------------------
@@ -308,6 +400,11 @@ int main(int argc, char **argv) {
         run_umma_probe<64, 32>();
         run_umma_probe<16, 16>();
         run_umma_probe<112, 32>();
+    }
+    if (!strcmp(what, "kmajor")) {  // run each convention in its own process: the wrong one may fault
+        const int swap = argc > 2 ? atoi(argv[2]) : 0;
+        run_umma_probe_kmajor_b<256, 64>(swap);
+        run_umma_probe_kmajor_b<64, 32>(swap);
     }
     if (!strcmp(what, "all") || !strcmp(what, "acc")) run_acc_probe();
     if (!strcmp(what, "all") || !strcmp(what, "stream")) run_stream_probe();
