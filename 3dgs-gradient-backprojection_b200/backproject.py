@@ -58,6 +58,10 @@ class BackProjector:
         self.overlap_pack = False
         self._side = None
         self._main = None
+        self._copy_stream = None  # add_view_host(): upload stream, two staging buffers, the deferred view
+        self._stage = None
+        self._pending = None
+        self._host_seq = 0
 
     # -- one view -------------------------------------------------------------------------
     def add_view(self, viewmat, K, width, height, feats: torch.Tensor, **cam_kw) -> View:
@@ -77,6 +81,49 @@ class BackProjector:
                                                  mode=mode)[0].permute(1, 2, 0)
             return self._add(viewmat, K, width, height, up, None, cam_kw)
         return self._add(viewmat, K, width, height, feats_low, mode, cam_kw)
+
+    # -- host-resident feature maps: pipelined upload ------------------------------------
+    def add_view_host(self, viewmat, K, width, height, feats_host: torch.Tensor, lowres_mode: Optional[str] = None,
+                      **cam_kw) -> None:
+        """feats_host: a (pinned) HOST tensor in the reference's planar layout [D,H,W] (backproject.py:110-113), or,
+        with lowres_mode="bilinear"/"nearest", the encoder-resolution map [D,h,w] (:109).  The upload runs on a
+        copy stream into one of two device staging buffers while the PREVIOUS view is being back-projected, so the
+        PCIe transfer and the kernels overlap; the view is accumulated at the next add_view_host()/flush() (every
+        accessor of the accumulators flushes)."""
+        assert not feats_host.is_cuda and feats_host.dim() == 3 and feats_host.shape[0] == self.d
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        if self._stage is None:
+            self._stage = [None, None]
+        slot = self._host_seq & 1
+        self._host_seq += 1
+        buf = self._stage[slot]
+        if buf is None or buf.shape != feats_host.shape:
+            buf = self._stage[slot] = torch.empty(feats_host.shape, dtype=torch.float32, device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        self._copy_stream.wait_stream(cur)  # the kernels that last read this staging buffer are enqueued on `cur`
+        with torch.cuda.stream(self._copy_stream):
+            buf.copy_(feats_host, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        prev, self._pending = self._pending, (viewmat, K, width, height, buf, lowres_mode, cam_kw, ready)
+        if prev is not None:
+            self._run_pending(prev)
+
+    def _run_pending(self, item) -> None:
+        viewmat, K, width, height, buf, lowres_mode, cam_kw, ready = item
+        torch.cuda.current_stream(self.device).wait_event(ready)
+        feats = buf.permute(1, 2, 0)
+        if lowres_mode is None:
+            self.add_view(viewmat, K, width, height, feats, **cam_kw)
+        else:
+            self.add_view_lowres(viewmat, K, width, height, feats, lowres_mode, **cam_kw)
+
+    def flush(self) -> None:
+        """Accumulate the view add_view_host() is still holding back."""
+        prev, self._pending = self._pending, None
+        if prev is not None:
+            self._run_pending(prev)
 
     def _add(self, viewmat, K, width, height, feats, lowres_mode, cam_kw) -> View:
         cam = make_camera(viewmat, K, width, height, **cam_kw)
@@ -146,16 +193,19 @@ class BackProjector:
     # -- results --------------------------------------------------------------------------
     def raw(self):
         """(num [N,D], den [N]) -- den includes the reference's 1e-12 initial value."""
+        self.flush()
         return self.num, self.den
 
     def stats(self) -> dict:
         """Counters summed over all views so far (device -> host read)."""
         if self._stats is None:
             return {}
+        self.flush()
         s = self._stats.tolist()
         return {"rows_nonzero": s[0], "entries_walked": s[1]}
 
     def reset(self) -> None:
+        self._pending = None
         self.num.zero_()
         self.den.fill_(DEN_EPS)
         if self._stats is not None:
@@ -164,11 +214,13 @@ class BackProjector:
 
     def prune_mask(self) -> torch.Tensor:
         """== `gaussian_grads > 0` of prune_by_gradients (utils.py:257)."""
+        self.flush()
         return self.den > DEN_EPS
 
     def finalize(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """backproject.py:166-169.  In per_view_ratio mode: L2-normalised rows of the ratio sum
         (demo_affordance_transfer.py:800), with never-seen rows 0 instead of the reference's NaN."""
+        self.flush()
         if self.accumulate == "per_view_ratio":
             return _finalize(self.num, torch.ones_like(self.den), out)
         return _finalize(self.num, self.den, out)

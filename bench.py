@@ -244,17 +244,22 @@ def run_ours(args, cfg):
         host = [torch.empty(d, H, W, dtype=torch.float32).pin_memory() for _ in range(2)]
         for hbuf, src in zip(host, pool):
             hbuf.copy_(src.permute(2, 0, 1))  # the reference's planar layout (backproject.py:110-113)
-        stage = torch.empty(d, H, W, dtype=torch.float32, device=dev)
+        for i in range(2):  # untimed: allocates the two staging buffers
+            bp.add_view_host(vm[my_view(i)], K, W, H, host[i % 2])
+        bp.flush()
+        torch.cuda.synchronize(dev)
         bp.reset()
         barrier()
         t0 = time.perf_counter()
         d2h = 0
         for i in range(k2):
-            stage.copy_(host[i % 2], non_blocking=True)
-            v = my_view(i)
-            bp.add_view(vm[v], K, W, H, stage.permute(1, 2, 0))
-            res = bp._stats.cpu()  # the step's result: per-view counters (rows, entries walked)
+            # public host-facing call: pinned host map -> copy stream -> staging buffer, overlapped with the
+            # back-projection of the previous view (BackProjector.add_view_host)
+            bp.add_view_host(vm[my_view(i)], K, W, H, host[i % 2])
+            res = bp._stats.cpu()  # the step's result read: running counters (rows, entries walked)
             d2h = res.numel() * 8
+        bp.flush()
+        res = bp._stats.cpu()
         torch.cuda.synchronize(dev)
         secs = time.perf_counter() - t0
         tt = torch.tensor([secs], device=dev, dtype=torch.float64)
@@ -262,22 +267,27 @@ def run_ours(args, cfg):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * k2 / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": fmap_bytes + 100,
                "d2h_bytes_per_step": d2h, "steps": k2,
-               "note": "feature map copied from pinned host memory every view (PCIe-bound); the reference keeps "
-                       "it on the GPU, where it is produced by the encoder"}
-        del host, stage
+               "note": "feature map uploaded from pinned host memory every view, overlapped with the previous view's "
+                       "kernels (PCIe-bound: 2.23 GB/view); the reference keeps it on the GPU, where the encoder "
+                       "produces it"}
+        del host
+        bp._stage = None
         # extra (not the headline): the same loop fed with the ENCODER-resolution map the reference's driver
         # actually has (backproject.py:109: [512,h,w] before F.interpolate); the upsample is fused on the GPU
         try:
             hlow = [torch.nn.functional.normalize(torch.randn(d, enc, enc), dim=0).pin_memory() for _ in range(2)]
-            slow = torch.empty(d, enc, enc, dtype=torch.float32, device=dev)
+            for i in range(2):
+                bp.add_view_host(vm[my_view(i)], K, W, H, hlow[i % 2], lowres_mode="bilinear")
+            bp.flush()
+            torch.cuda.synchronize(dev)
             bp.reset()
             barrier()
             t0 = time.perf_counter()
             for i in range(k2):
-                slow.copy_(hlow[i % 2], non_blocking=True)
-                v = my_view(i)
-                bp.add_view_lowres(vm[v], K, W, H, slow.permute(1, 2, 0))
+                bp.add_view_host(vm[my_view(i)], K, W, H, hlow[i % 2], lowres_mode="bilinear")
                 res = bp._stats.cpu()
+            bp.flush()
+            res = bp._stats.cpu()
             torch.cuda.synchronize(dev)
             tt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
             if world > 1:

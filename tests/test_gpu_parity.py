@@ -507,3 +507,20 @@ def test_tcgen05_forward_render(gwbp, coracle, d, W, H):
     # AUTO picks the tensor-core kernel for wide features and still renders RGB (D = 3) on CUDA cores
     rgb, _ = view.render(_dev(feats[:, :3].copy()))
     assert rgb.shape == (H, W, 3)
+
+
+def test_pipelined_host_upload_matches_device_path(gwbp, case):
+    """add_view_host (copy stream + two staging buffers + deferred accumulation) == add_view on device tensors."""
+    sc, vm, K, feats = case
+    ref = _gpu_job(gwbp, sc, vm, K, 96, 64, feats, 8, kernel="simt")
+    bp = gwbp.BackProjector(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities), 8, kernel="simt",
+                            collect_stats=True)
+    for rep in range(2):  # 4 uploads through 2 staging buffers
+        for v in range(vm.shape[0]):
+            planar = torch.from_numpy(np.ascontiguousarray(np.transpose(feats[v], (2, 0, 1)))).pin_memory()
+            bp.add_view_host(vm[v], K, 96, 64, planar)
+    num, den = bp.raw()  # flushes the deferred view
+    assert bp.n_views == 2 * vm.shape[0]
+    assert torch.allclose(num, 2 * ref.num, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(den - 1e-12, 2 * (ref.den - 1e-12), rtol=1e-5, atol=1e-9)
+    assert bp.stats()["entries_walked"] == 2 * ref.stats()["entries_walked"]
