@@ -359,6 +359,26 @@ def test_full_size_config_G_properties(gwbp):
     bp3 = gwbp.BackProjector(*args, kernel="tc")
     bp3.add_view(vm[7], K, W, H, (2 * c).expand(H, W, d))
     assert torch.allclose(bp3.num[seen], 2 * bp.num[seen], rtol=2e-4, atol=1e-6)
+    del bp2, bp3
+    # forward render on tensor cores at full size.  (a) constant colours render to alpha * c;
+    # (b) adjointness with the back-projection: <render(X), G> == <X, backproject(G)>  (the two tcgen05 kernels
+    # are transposes of each other: segment.py:209-220 vs backproject.py:127-131)
+    r_c, a_c = view.render(c.expand(sc.n, d).contiguous(), None, gwbp.KERNEL_TC)
+    da = (a_c - alpha).abs()  # ex2-based vs __expf-based alpha: equal up to threshold flips (alpha ~ 1/255, T ~ 1e-4)
+    assert float((da > 1e-5).float().mean()) < 1e-4 and float(da.max()) < 2e-2, (float(da.max()), int((da > 1e-5).sum()))
+    assert float((r_c - a_c[..., None] * c).abs().max()) < 2e-4
+    del r_c
+    g = torch.Generator(device="cuda").manual_seed(3)
+    X = torch.randn(sc.n, d, device="cuda", generator=g)
+    G = torch.randn(H, W, d, device="cuda", generator=g)
+    r, _ = view.render(X, None, gwbp.KERNEL_TC)
+    lhs = float((r.double() * G.double()).sum())
+    scale = float(torch.linalg.vector_norm(r.double()) * torch.linalg.vector_norm(G.double()))
+    del r
+    bp.reset()
+    bp.add_view(vm[7], K, W, H, G)
+    rhs = float((X.double() * bp.num.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * scale, (lhs, rhs, scale)
 
 
 def test_rasterization_backgrounds_depth_modes_and_sh(gwbp, coracle, case, tmp_path):
