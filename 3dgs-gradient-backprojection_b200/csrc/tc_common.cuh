@@ -64,6 +64,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uin
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// (bulk reduce / commit / wait: used by tools/tc_probe.cu, which measured them against red.global.add.v4)
 __device__ __forceinline__ void bulk_reduce_add_f32(void *dst, uint32_t src_smem, uint32_t bytes) {
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
                  "r"(src_smem), "r"(bytes)
@@ -82,31 +83,6 @@ __device__ __forceinline__ void bulk_wait_all() {
 // vector reduction to global (sm_90+): one 16-byte fp32x4 add, no return value
 __device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-// L2 eviction-priority policies (createpolicy) and a vector reduction that carries one
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void red_add_v4_hint(float *dst, float a, float b, float c, float d, uint64_t policy) {
-    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst), "f"(a), "f"(b), "f"(c),
-                 "f"(d), "l"(policy)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar,
-                                              uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            dst_smem),
-        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-        : "memory");
 }
 
 // ---- TMEM -----------------------------------------------------------------------------------------
