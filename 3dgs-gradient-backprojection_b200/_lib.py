@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgwbp.so")
 
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC = 0, 1, 2
-ABI_VERSION = 7
+ABI_VERSION = 8
 KERNEL_FPACK_READY = 0x100
 PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL = 0, 1
 
@@ -35,7 +35,7 @@ class WsLayout(C.Structure):
 
 class ViewInfo(C.Structure):
     _fields_ = [("n_vis", C.c_int64), ("n_isects", C.c_int64), ("cap_isects", C.c_int64), ("tile_w", C.c_int32),
-                ("tile_h", C.c_int32), ("sorted_buf", C.c_int32), ("reserved", C.c_int32)]
+                ("tile_h", C.c_int32), ("sorted_buf", C.c_int32), ("tile_key_bytes", C.c_int32)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check it against include/gwbp.h

@@ -133,11 +133,13 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     const unsigned *order = w.dvals[dsel];
     if (int rc = launch_gather_counts(info->n_vis, order, w, st)) return rc;
     if (int rc = launch_scan_counts(info->n_vis, w, st)) return rc;
-    if (int rc = launch_emit(info->n_vis, cd, order, w, cap, st)) return rc;
+    const bool key16 = cd.tw * cd.th <= 65536;
+    info->tile_key_bytes = key16 ? 2 : 4;
+    if (int rc = launch_emit(info->n_vis, cd, order, w, cap, key16, st)) return rc;
     int sorted = 0;
-    if (int rc = launch_tile_sort(info->n_isects, tile_bits_for(cd.tw * cd.th), w, &sorted, st)) return rc;
+    if (int rc = launch_tile_sort(info->n_isects, tile_bits_for(cd.tw * cd.th), w, key16, &sorted, st)) return rc;
     info->sorted_buf = sorted;
-    return launch_offsets(info->n_isects, cd.tw * cd.th, w.tkeys[sorted], w.offsets, st);
+    return launch_offsets(info->n_isects, cd.tw * cd.th, w.tkeys[sorted], key16, w.offsets, st);
 }
 
 int gwbp_debug_set_trace(void *buf, size_t bytes) {

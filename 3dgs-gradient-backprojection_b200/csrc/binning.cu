@@ -65,12 +65,16 @@ int launch_scan_counts(int64_t n_vis, WsDev ws, cudaStream_t st) {
 }
 
 // stage 2: intersections (already in depth order) by tile id only -- stable, floor(log2(tiles))+1 bits
-int launch_tile_sort(int64_t n_isects, int tile_bits, WsDev ws, int *sorted_buf, cudaStream_t st) {
+int launch_tile_sort(int64_t n_isects, int tile_bits, WsDev ws, bool key16, int *sorted_buf, cudaStream_t st) {
+    if (key16)
+        return sort_pairs((unsigned short *)ws.tkeys[0], (unsigned short *)ws.tkeys[1], ws.tvals[0], ws.tvals[1], n_isects,
+                          tile_bits, ws, sorted_buf, st);
     return sort_pairs(ws.tkeys[0], ws.tkeys[1], ws.tvals[0], ws.tvals[1], n_isects, tile_bits, ws, sorted_buf, st);
 }
 
-__global__ void __launch_bounds__(256) offsets_kernel(int64_t n_isects, int n_tiles,
-                                                      const unsigned *__restrict__ keys, int *__restrict__ offsets) {
+template <typename KT>
+__global__ void __launch_bounds__(256) offsets_kernel(int64_t n_isects, int n_tiles, const KT *__restrict__ keys,
+                                                      int *__restrict__ offsets) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n_isects == 0) {
         if (i <= n_tiles) offsets[i] = 0;
@@ -84,9 +88,13 @@ __global__ void __launch_bounds__(256) offsets_kernel(int64_t n_isects, int n_ti
         for (int t = cur + 1; t <= n_tiles; ++t) offsets[t] = (int)n_isects;
 }
 
-int launch_offsets(int64_t n_isects, int n_tiles, const unsigned *keys, int *offsets, cudaStream_t st) {
+int launch_offsets(int64_t n_isects, int n_tiles, const void *keys, bool key16, int *offsets, cudaStream_t st) {
     const int64_t work = n_isects > 0 ? n_isects : (int64_t)n_tiles + 1;
-    offsets_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(n_isects, n_tiles, keys, offsets);
+    const unsigned blocks = (unsigned)((work + 255) / 256);
+    if (key16)
+        offsets_kernel<<<blocks, 256, 0, st>>>(n_isects, n_tiles, (const unsigned short *)keys, offsets);
+    else
+        offsets_kernel<<<blocks, 256, 0, st>>>(n_isects, n_tiles, (const unsigned *)keys, offsets);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -344,11 +344,12 @@ int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, cudaStr
 // (tile id, packed index) pair per tile it reaches.  A stable sort on the tile id alone then yields
 // exactly the order of gsplat's 64-bit (tile | depth) sort (ties: ascending packed index).
 // ---------------------------------------------------------------------------------------------
+template <typename KT>
 __global__ void __launch_bounds__(256) emit_kernel(int64_t n_vis, CamDev cam, const unsigned *__restrict__ order,
                                                    const unsigned *__restrict__ base2,
                                                    const float4 *__restrict__ grec, const int *__restrict__ radii,
                                                    const unsigned long long *__restrict__ pmask,
-                                                   unsigned *__restrict__ tkeys, int *__restrict__ tvals, int64_t cap) {
+                                                   KT *__restrict__ tkeys, int *__restrict__ tvals, int64_t cap) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     bool vis = i < n_vis;
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(256) emit_kernel(int64_t n_vis, CamDev cam, co
             while (row) {
                 const int k = __ffsll((long long)row) - 1;
                 row &= row - 1;
-                if (o < cap) { tkeys[o] = tbase + (unsigned)k; tvals[o] = pos; }
+                if (o < cap) { tkeys[o] = (KT)(tbase + (unsigned)k); tvals[o] = pos; }
                 ++o;
             }
         }
@@ -395,16 +396,22 @@ __global__ void __launch_bounds__(256) emit_kernel(int64_t n_vis, CamDev cam, co
             const bool hit = (k < snt) && (!cam.cull || tile_hit(sg, tx, ty, cam.W, cam.H));
             const unsigned hm = __ballot_sync(0xffffffffu, hit);
             const long long o = sbase + __popc(hm & ((1u << lane) - 1u));
-            if (hit && o < cap) { tkeys[o] = (unsigned)(ty * cam.tw + tx); tvals[o] = spos; }
+            if (hit && o < cap) { tkeys[o] = (KT)(ty * cam.tw + tx); tvals[o] = spos; }
             sbase += __popc(hm);
         }
     }
 }
 
-int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, cudaStream_t st) {
+int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, bool key16,
+                cudaStream_t st) {
     if (n_vis == 0) return 0;
-    emit_kernel<<<(unsigned)((n_vis + 255) / 256), 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.pmask,
-                                                               ws.tkeys[0], ws.tvals[0], cap);
+    const unsigned blocks = (unsigned)((n_vis + 255) / 256);
+    if (key16)
+        emit_kernel<unsigned short><<<blocks, 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.pmask,
+                                                            (unsigned short *)ws.tkeys[0], ws.tvals[0], cap);
+    else
+        emit_kernel<unsigned><<<blocks, 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.pmask,
+                                                      ws.tkeys[0], ws.tvals[0], cap);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }

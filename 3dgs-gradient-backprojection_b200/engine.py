@@ -132,7 +132,10 @@ class View:
         g = self.grec()
         nv, ni = self.n_vis, self.n_isects
         sb = self.info.sorted_buf
-        tiles = self._win(self.layout.tkeys1 if sb else self.layout.tkeys0, ni, torch.int32)
+        if self.info.tile_key_bytes == 2:  # uint16 tile ids
+            tiles = self._win(self.layout.tkeys1 if sb else self.layout.tkeys0, ni, torch.int16).to(torch.int64) & 0xFFFF
+        else:
+            tiles = self._win(self.layout.tkeys1 if sb else self.layout.tkeys0, ni, torch.int32)
         vals = self._win(self.layout.tvals1 if sb else self.layout.tvals0, ni, torch.int32)
         th, tw = self.info.tile_h, self.info.tile_w
         # gsplat's int64 keys (tile << 32 | depth bits), rebuilt from the two-stage sort's outputs

@@ -42,7 +42,7 @@ extern "C" {
 #endif
 
 #define GWBP_TILE 16
-#define GWBP_ABI_VERSION 7
+#define GWBP_ABI_VERSION 8
 
 /* kernel selection for gwbp_backproject_view and gwbp_render_view */
 #define GWBP_KERNEL_AUTO 0
@@ -83,7 +83,7 @@ typedef struct gwbp_ws_layout {
     size_t dvals0, dvals1;  /* uint32 [n]  packed index */
     size_t cnt2;      /* uint32 [n+1]   tile counts in depth order */
     size_t base2;     /* uint32 [n+1]   exclusive prefix of cnt2 */
-    size_t tkeys0, tkeys1;  /* uint32 [cap] tile id per intersection (sort double buffer) */
+    size_t tkeys0, tkeys1;  /* uint32|uint16 [cap] tile id per intersection (sort double buffer; see tile_key_bytes) */
     size_t tvals0, tvals1;  /* int32  [cap] flatten_ids: packed index per intersection */
     size_t offsets;   /* int32  [tiles+1] isect_offsets (+ terminator = n_isects) */
     size_t stats;     /* int64  [16]    device counters */
@@ -96,7 +96,7 @@ typedef struct gwbp_view_info {
     int64_t cap_isects; /* the capacity the workspace layout was computed with */
     int32_t tile_w, tile_h;
     int32_t sorted_buf; /* which of tkeys0/tkeys1, tvals0/tvals1 holds the sorted result */
-    int32_t reserved;
+    int32_t tile_key_bytes; /* 2 or 4: element size of the tkeys buffers (16-bit keys when tiles <= 65536) */
 } gwbp_view_info;
 
 /* counters filled by gwbp_backproject_view when `stats` != NULL (device int64[4]):

@@ -93,7 +93,9 @@ def test_integer_stages_bit_exact(gwbp, coracle, case, cull):
 
 def test_integer_stages_bit_exact_config_S_and_odd_sizes(gwbp, coracle):
     S = gwbp.scene
-    for (n, W, H, seed) in [(50_000, 256, 256, 0), (20_000, 333, 211, 3), (5_000, 17, 15, 4), (2_000, 1297, 840, 5)]:
+    # the last case has 257 x 257 = 66 049 tiles: tile ids no longer fit the 16-bit sort keys (32-bit key path)
+    for (n, W, H, seed) in [(50_000, 256, 256, 0), (20_000, 333, 211, 3), (5_000, 17, 15, 4), (2_000, 1297, 840, 5),
+                            (3_000, 4112, 4100, 6)]:
         sc = S.make_scene(n, seed)
         vm, K = S.make_cameras(2, W, H, seed)
         scene = gwbp.PackedScene(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities))
@@ -101,6 +103,7 @@ def test_integer_stages_bit_exact_config_S_and_odd_sizes(gwbp, coracle):
             view = gwbp.View(scene, gwbp.make_camera(vm[1], K, W, H), tile_cull=cull)
             e = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[1], K, W, H, cull=cull).export()
             m = view.meta()
+            assert view.info.tile_key_bytes == (2 if view.info.tile_w * view.info.tile_h <= 65536 else 4)
             assert np.array_equal(m["isect_ids"].cpu().numpy(), e["isect_ids"]), (n, W, H, cull)
             assert np.array_equal(m["flatten_ids"].cpu().numpy(), e["flatten_ids"]), (n, W, H, cull)
             assert np.array_equal(m["isect_offsets"].cpu().numpy()[0], e["isect_offsets"]), (n, W, H, cull)
