@@ -8,6 +8,7 @@ raises -- there is no CPU fallback.
 """
 from . import scene  # noqa: F401  (numpy-only, importable without the CUDA library)
 from . import dist  # noqa: F401
+from . import splats  # noqa: F401  (torch-only data-contract helpers)
 from ._lib import LIB_PATH, KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC  # noqa: F401
 from .backproject import BackProjector, create_feature_field, DEN_EPS  # noqa: F401
 from .engine import PackedScene, View, cosine_mask, finalize, make_camera, fpack_bytes  # noqa: F401
@@ -16,4 +17,4 @@ from .segment import (click_mask3d, click_prompt, gaussian_scores, get_mask3d, r
                       render_mask_2d)
 
 __all__ = ["rasterization", "BackProjector", "create_feature_field", "PackedScene", "View", "finalize",
-           "cosine_mask", "get_mask3d", "click_prompt", "click_mask3d", "render_features", "render_mask_2d", "make_camera", "scene", "dist"]
+           "cosine_mask", "get_mask3d", "click_prompt", "click_mask3d", "render_features", "render_mask_2d", "make_camera", "scene", "dist", "splats"]

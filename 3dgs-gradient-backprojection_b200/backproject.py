@@ -63,6 +63,13 @@ class BackProjector:
         self._pending = None
         self._host_seq = 0
 
+    @classmethod
+    def from_splats(cls, splats: dict, feature_dim: int, **kw) -> "BackProjector":
+        """From the reference's `splats` dict (utils.load_checkpoint): log-scales and opacity logits are
+        activated as in backproject.py:55-57."""
+        from .splats import activated
+        return cls(*activated(splats), feature_dim=feature_dim, **kw)
+
     # -- one view -------------------------------------------------------------------------
     def add_view(self, viewmat, K, width, height, feats: torch.Tensor, **cam_kw) -> View:
         """feats: the full-resolution [H,W,D] fp32 map (any strides), as the reference builds it."""

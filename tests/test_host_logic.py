@@ -104,3 +104,33 @@ def test_sh_colour_evaluation_cpu(gwbp):
     a = sh.eval_sh_colors(3, means, only_even, vm)
     b = sh.eval_sh_colors(3, mirrored, only_even, vm)
     assert torch.allclose(a, b, atol=1e-5)
+
+
+def test_splats_data_contract(gwbp):
+    """gsplat checkpoint <-> `splats` dict, activations, pruning, COLMAP pose -> viewmat."""
+    import torch
+    S = gwbp.splats
+    n = 7
+    g = torch.Generator().manual_seed(0)
+    ckpt = {"splats": {"means": torch.randn(n, 3, generator=g), "quats": torch.randn(n, 4, generator=g),
+                       "scales": torch.randn(n, 3, generator=g), "opacities": torch.randn(n, generator=g),
+                       "sh0": torch.randn(n, 1, 3, generator=g), "shN": torch.randn(n, 15, 3, generator=g)}}
+    ckpt["splats"]["means"].requires_grad_(True)
+    sp = S.splats_from_gsplat_checkpoint(ckpt)
+    assert set(sp) >= {"means", "rotation", "scaling", "opacity", "features_dc", "features_rest"}
+    assert not sp["means"].requires_grad and sp["active_sh_degree"] == 3      # utils.py:11-17,66
+    back = S.gsplat_checkpoint_from_splats(sp)
+    assert all(torch.equal(back["splats"][k], ckpt["splats"][k].detach()) for k in ckpt["splats"])
+    means, quats, scales, opac = S.activated(sp)
+    assert torch.equal(scales, torch.exp(sp["scaling"])) and torch.equal(opac, torch.sigmoid(sp["opacity"]))
+    assert quats is sp["rotation"] and means is sp["means"]
+    keep = torch.tensor([True, False, True, True, False, False, True])
+    sp["camera_matrix"] = S.camera_matrix(1000.0, 900.0, 640.0, 360.0, data_factor=4)
+    pr = S.prune_splats(sp, keep)
+    assert pr["means"].shape[0] == 4 and pr["features_rest"].shape == (4, 15, 3)
+    assert torch.equal(pr["opacity"], sp["opacity"][keep]) and pr["camera_matrix"] is sp["camera_matrix"]
+    assert torch.allclose(sp["camera_matrix"], torch.tensor([[250.0, 0, 160], [0, 225.0, 90], [0, 0, 1]]))
+    R = torch.tensor([[0.0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    vm = S.viewmat_from_rotation_translation(R.numpy(), [1.0, 2.0, 3.0])
+    assert vm.shape == (4, 4) and torch.equal(vm[:3, :3], R) and vm[:3, 3].tolist() == [1.0, 2.0, 3.0]
+    assert vm[3].tolist() == [0.0, 0.0, 0.0, 1.0]
