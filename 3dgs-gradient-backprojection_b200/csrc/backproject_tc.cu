@@ -652,6 +652,90 @@ __global__ void __launch_bounds__(256) fpack_lowres_kernel(const float *__restri
     }
 }
 
+// Faster variant for UPsampling (the reference's case: 240x240 -> 1297x840): one CTA = one tile row (16 image rows)
+// x 32 pixels x 64 channels.  The low-resolution window the CTA needs (a few rows x columns per channel) is staged
+// in shared memory once; a thread owns one pixel column and 8 channels, keeps the two horizontally interpolated
+// source rows it is between in registers and walks down the 16 output rows, so a source texel is fetched ~5x per
+// CTA instead of once per output element (the first version issued 4 global loads per element: 1.36 ms at config G).
+constexpr int kLowCh = 64, kLowSpan = 32, kLowMaxWin = 160;  // window texels per channel (+1 pad): 64*161*4 = 41 KB
+__global__ void __launch_bounds__(256) fpack_lowres_tile_kernel(const float *__restrict__ S, int sh, int sw, int64_t ssh,
+                                                                int64_t ssw, int64_t ssd, int nearest, int W, int H,
+                                                                int tw, int d, int dp, uint8_t *__restrict__ out) {
+    extern __shared__ float win[];  // [kLowCh][chs], chs = qy*qx | 1 (odd: conflict-free across channels)
+    const int span = blockIdx.x, ty = blockIdx.y, cb = blockIdx.z * kLowCh;
+    const int t = threadIdx.x, px = t & 31, g = t >> 5;
+    const float scale_y = (float)sh / (float)H, scale_x = (float)sw / (float)W;
+    auto src = [&](int o, float scale, int n_src, int &i0, int &i1, float &l) {
+        if (nearest) {
+            i0 = i1 = min((int)floorf((float)o * scale), n_src - 1);
+            l = 0.0f;
+        } else {  // torch area_pixel_compute_source_index, align_corners=False
+            const float f = fmaxf(scale * ((float)o + 0.5f) - 0.5f, 0.0f);
+            i0 = min((int)f, n_src - 1);
+            i1 = i0 + (i0 < n_src - 1 ? 1 : 0);
+            l = f - (float)i0;
+        }
+    };
+    // window of source rows / columns this CTA touches (uniform)
+    int ylo, yhi, xlo, xhi, tmp;
+    float ftmp;
+    src(ty * kTile, scale_y, sh, ylo, tmp, ftmp);
+    src(min(ty * kTile + kTile - 1, H - 1), scale_y, sh, tmp, yhi, ftmp);
+    src(span * kLowSpan, scale_x, sw, xlo, tmp, ftmp);
+    src(min(span * kLowSpan + kLowSpan - 1, W - 1), scale_x, sw, tmp, xhi, ftmp);
+    const int qy = yhi - ylo + 1, qx = xhi - xlo + 1, chs = (qy * qx) | 1;
+    for (int idx = t; idx < kLowCh * qy * qx; idx += 256) {
+        const int ch = idx / (qy * qx), r = idx - ch * (qy * qx);
+        const int yy = r / qx, xx = r - yy * qx;
+        const int col = cb + ch;
+        win[ch * chs + r] = col < d ? __ldg(S + col * ssd + (ylo + yy) * ssh + (xlo + xx) * ssw) : 0.0f;
+    }
+    __syncthreads();
+    const int x = span * kLowSpan + px;
+    const int tx = span * 2 + (px >> 4), p = px & 15;
+    if (tx >= tw || cb + 8 * g >= dp) return;
+    int x0, x1;
+    float lx;
+    src(min(x, W - 1), scale_x, sw, x0, x1, lx);
+    x0 -= xlo; x1 -= xlo;
+    const float *wch = win + (8 * g) * chs;
+    const int c = cb / NCMAX, ncols = min(NCMAX, dp - c * NCMAX), ng = (cb - c * NCMAX) / 8 + g;
+    const uint32_t lbo = (uint32_t)(ncols / 8) * 128, part = (uint32_t)ncols * KSL * 2;
+    uint8_t *tbase = out + (int64_t)(ty * tw + tx) * kTilePix * dp * 4 + (int64_t)c * NCMAX * kTilePix * 4 +
+                     (uint32_t)(p / 8) * lbo + (uint32_t)ng * 128 + (uint32_t)(p % 8) * 16;
+    float ha[8], hb[8];
+    int cur = -1;
+    for (int ks = 0; ks < kTile; ++ks) {
+        const int y = ty * kTile + ks;
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+        if (y < H && x < W) {
+            int y0, y1;
+            float ly;
+            src(y, scale_y, sh, y0, y1, ly);
+            if (y0 != cur) {  // uniform: a new pair of source rows, interpolated horizontally once
+                cur = y0;
+                const int ra = (y0 - ylo) * qx, rb = (y1 - ylo) * qx;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float *w = wch + j * chs;
+                    ha[j] = (1.0f - lx) * w[ra + x0] + lx * w[ra + x1];
+                    hb[j] = (1.0f - lx) * w[rb + x0] + lx * w[rb + x1];
+                }
+            }
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (1.0f - ly) * ha[j] + ly * hb[j];
+            split_bf16x2(v[0], v[1], hi.x, lo.x);
+            split_bf16x2(v[2], v[3], hi.y, lo.y);
+            split_bf16x2(v[4], v[5], hi.z, lo.z);
+            split_bf16x2(v[6], v[7], hi.w, lo.w);
+        }
+        uint8_t *blk = tbase + (int64_t)ks * part * 2;
+        *reinterpret_cast<uint4 *>(blk) = hi;
+        *reinterpret_cast<uint4 *>(blk + part) = lo;
+    }
+}
+
 }  // namespace
 
 static unsigned long long *g_trace = nullptr;
@@ -698,6 +782,18 @@ int launch_fpack_lowres(int W, int H, const float *S, int sh, int sw, int64_t ss
     GWBP_REQUIRE(((uintptr_t)fpack & 127) == 0, "fpack must be 128-byte aligned");
     GWBP_REQUIRE(sh >= 1 && sw >= 1, "low-resolution map must be at least 1x1");
     const int dp = round_up(d, 16), nchunks = (dp + NCMAX - 1) / NCMAX;
+    // window bound of the tile variant: rows/columns of the source one CTA touches
+    const int qy = (int)((double)kTile * sh / H) + 3, qx = (int)((double)kLowSpan * sw / W) + 3;
+    if (qy * qx <= kLowMaxWin) {
+        const size_t smem = (size_t)kLowCh * ((qy * qx) | 1) * sizeof(float);
+        GWBP_CUDA_OK(cudaFuncSetAttribute(fpack_lowres_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((W + kLowSpan - 1) / kLowSpan, th, (dp + kLowCh - 1) / kLowCh);
+        fpack_lowres_tile_kernel<<<grid, 256, smem, st>>>(S, sh, sw, ssh, ssw, ssd, nearest, W, H, tw, d, dp,
+                                                          (uint8_t *)fpack);
+        GWBP_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    // downsampling / huge windows: the per-element variant
     if (H % kTile)
         GWBP_CUDA_OK(cudaMemsetAsync((uint8_t *)fpack + (size_t)(th - 1) * tw * kTilePix * dp * 4, 0,
                                      (size_t)tw * kTilePix * dp * 4, st));
