@@ -15,7 +15,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // rows of up to 32*kRegs floats are held in registers: ONE read and one write of HBM per element
 constexpr int kRegs = 32;
+// VEC (template): float4 registers per lane on the vectorised paths -- 4 covers D <= 512, 8 covers D <= 1024
 
+template <int VEC>
 __global__ void __launch_bounds__(256) finalize_kernel(const float *__restrict__ num, const float *__restrict__ den,
                                                        float *__restrict__ out, int64_t n, int d) {
     const int lane = threadIdx.x & 31;
@@ -24,7 +26,40 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float *__restrict__
     const float dn = den[row];
     const float *src = num + row * d;
     float *dst = out + row * d;
-    if (d <= 32 * kRegs) {
+    if constexpr (VEC > 0) {  // launcher guarantees d % 4 == 0 and d <= 128 * VEC
+        // 16-byte loads, the row held in registers, and ONE division + one rsqrt-style reciprocal per row: the
+        // element-wise IEEE divisions of the first version made this pass instruction-bound (1.1 TB/s).
+        // x * (1/den) and q * (1/norm) differ from x/den, q/norm by <= 1 ulp each; NaN/inf propagate identically
+        // (den = 0 -> inf/NaN -> row of NaN -> 0, backproject.py:169).
+        const float rd = 1.0f / dn;
+        const int n4 = d >> 2;
+        float4 q[VEC];
+        float ss = 0.0f;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const int k = lane + 32 * j;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < n4) {
+                v = __ldg(reinterpret_cast<const float4 *>(src) + k);
+                v.x *= rd; v.y *= rd; v.z *= rd; v.w *= rd;
+            }
+            q[j] = v;
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        ss = warp_sum(ss);
+        const float rn = 1.0f / sqrtf(ss);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const int k = lane + 32 * j;
+            if (k < n4) {
+                float4 v = make_float4(q[j].x * rn, q[j].y * rn, q[j].z * rn, q[j].w * rn);
+                v.x = isnan(v.x) ? 0.0f : v.x; v.y = isnan(v.y) ? 0.0f : v.y;
+                v.z = isnan(v.z) ? 0.0f : v.z; v.w = isnan(v.w) ? 0.0f : v.w;
+                reinterpret_cast<float4 *>(dst)[k] = v;
+            }
+        }
+        return;
+    } else if (d <= 32 * kRegs) {
         float q[kRegs];
         float ss = 0.0f;
 #pragma unroll
@@ -45,24 +80,32 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float *__restrict__
             }
         }
         return;
-    }
-    float ss = 0.0f;
-    for (int j = lane; j < d; j += 32) {
-        const float q = src[j] / dn;
-        ss += q * q;
-    }
-    ss = warp_sum(ss);
-    const float nrm = sqrtf(ss);
-    for (int j = lane; j < d; j += 32) {
-        float v = (src[j] / dn) / nrm;
-        if (isnan(v)) v = 0.0f;
-        dst[j] = v;
+    } else {
+        float ss = 0.0f;
+        for (int j = lane; j < d; j += 32) {
+            const float q = src[j] / dn;
+            ss += q * q;
+        }
+        ss = warp_sum(ss);
+        const float nrm = sqrtf(ss);
+        for (int j = lane; j < d; j += 32) {
+            float v = (src[j] / dn) / nrm;
+            if (isnan(v)) v = 0.0f;
+            dst[j] = v;
+        }
     }
 }
 
 int launch_finalize(const float *num, const float *den, float *out, int64_t n, int d, cudaStream_t st) {
     if (n == 0 || d == 0) return 0;
-    finalize_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(num, den, out, n, d);
+    const unsigned blocks = (unsigned)((n + 7) / 8);
+    const bool vec = (d & 3) == 0 && (((uintptr_t)num | (uintptr_t)out) & 15) == 0;
+    if (vec && d <= 512)
+        finalize_kernel<4><<<blocks, 256, 0, st>>>(num, den, out, n, d);
+    else if (vec && d <= 1024)
+        finalize_kernel<8><<<blocks, 256, 0, st>>>(num, den, out, n, d);
+    else
+        finalize_kernel<0><<<blocks, 256, 0, st>>>(num, den, out, n, d);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -103,11 +146,12 @@ int launch_ratio_accumulate(const float4 *grec, int64_t n_vis, float *num_v, flo
 }
 
 // text [p, d] is staged (normalised) in shared memory; p*d*4 bytes must fit (checked on the host)
+template <int VEC>
 __global__ void __launch_bounds__(256) mask_kernel(const float *__restrict__ x, int64_t rows, int d,
                                                    const float *__restrict__ text, int p, int npos, float thr,
                                                    int use_thr, uint8_t *__restrict__ mask,
                                                    float *__restrict__ score) {
-    extern __shared__ float stext[];
+    extern __shared__ __align__(16) float stext[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int j = warp; j < p; j += nwarps) {
         float ss = 0.0f;
@@ -120,7 +164,37 @@ __global__ void __launch_bounds__(256) mask_kernel(const float *__restrict__ x, 
     for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < rows; row += (int64_t)gridDim.x * nwarps) {
         const float *src = x + row * d;
         float best_pos = -INFINITY, best_neg = -INFINITY, s0 = 0.0f;
-        if (d <= 32 * kRegs) {  // one HBM read of the row: keep it in registers
+        if constexpr (VEC > 0) {  // launcher guarantees d % 4 == 0 and d <= 128 * VEC
+            // 16-byte global and shared loads; the row norm is applied to the P dot products, not to the D elements
+            // (the scalar version spent 85 % of its issue slots on per-element work: 2.9 TB/s)
+            const int n4 = d >> 2;
+            const float4 *t4 = reinterpret_cast<const float4 *>(stext);
+            float4 q[VEC];
+            float ss = 0.0f;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const int k = lane + 32 * j;
+                q[j] = (k < n4) ? __ldg(reinterpret_cast<const float4 *>(src) + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ss += q[j].x * q[j].x + q[j].y * q[j].y + q[j].z * q[j].z + q[j].w * q[j].w;
+            }
+            ss = warp_sum(ss);
+            const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+            for (int jp = 0; jp < p; ++jp) {
+                float dot = 0.0f;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const int k = lane + 32 * j;
+                    if (k < n4) {
+                        const float4 tv = t4[jp * n4 + k];
+                        dot += q[j].x * tv.x + q[j].y * tv.y + q[j].z * tv.z + q[j].w * tv.w;
+                    }
+                }
+                dot = warp_sum(dot) * inv;
+                if (jp == 0) s0 = dot;
+                if (jp < npos) best_pos = fmaxf(best_pos, dot); else best_neg = fmaxf(best_neg, dot);
+                if (score && lane == 0) score[row * p + jp] = dot;
+            }
+        } else if (d <= 32 * kRegs) {  // one HBM read of the row: keep it in registers
             float q[kRegs];
             float ss = 0.0f;
 #pragma unroll
@@ -171,11 +245,20 @@ int launch_mask(const float *x, int64_t rows, int d, const float *text, int p, i
     const size_t smem = (size_t)p * d * sizeof(float);
     GWBP_REQUIRE(p >= 1 && npos >= 1 && npos <= p, "mask: need 1 <= npos <= p (npos=%d p=%d)", npos, p);
     GWBP_REQUIRE(smem <= 200 * 1024, "mask: %d prompts x %d dims do not fit in shared memory", p, d);
-    if (smem > 48 * 1024)
-        GWBP_CUDA_OK(cudaFuncSetAttribute(mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) {
+        GWBP_CUDA_OK(cudaFuncSetAttribute(mask_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GWBP_CUDA_OK(cudaFuncSetAttribute(mask_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GWBP_CUDA_OK(cudaFuncSetAttribute(mask_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     int64_t blocks = (rows + 7) / 8;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    mask_kernel<<<(unsigned)blocks, 256, smem, st>>>(x, rows, d, text, p, npos, thr, use_thr, mask, score);
+    const bool vec = (d & 3) == 0 && ((uintptr_t)x & 15) == 0;
+    if (vec && d <= 512)
+        mask_kernel<4><<<(unsigned)blocks, 256, smem, st>>>(x, rows, d, text, p, npos, thr, use_thr, mask, score);
+    else if (vec && d <= 1024)
+        mask_kernel<8><<<(unsigned)blocks, 256, smem, st>>>(x, rows, d, text, p, npos, thr, use_thr, mask, score);
+    else
+        mask_kernel<0><<<(unsigned)blocks, 256, smem, st>>>(x, rows, d, text, p, npos, thr, use_thr, mask, score);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
