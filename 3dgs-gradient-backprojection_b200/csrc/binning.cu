@@ -72,25 +72,45 @@ int launch_tile_sort(int64_t n_isects, int tile_bits, WsDev ws, bool key16, int 
     return sort_pairs(ws.tkeys[0], ws.tkeys[1], ws.tvals[0], ws.tvals[1], n_isects, tile_bits, ws, sorted_buf, st);
 }
 
+// offsets[t] = first sorted position whose tile id >= t; offsets[n_tiles] = n_isects.  Each thread scans kPer
+// consecutive keys (the list is sorted, so tile boundaries are where neighbours differ).
 template <typename KT>
 __global__ void __launch_bounds__(256) offsets_kernel(int64_t n_isects, int n_tiles, const KT *__restrict__ keys,
                                                       int *__restrict__ offsets) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int kPer = 16 / sizeof(KT) * 2;  // two 16-byte loads per thread
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kPer;
     if (n_isects == 0) {
-        if (i <= n_tiles) offsets[i] = 0;
+        for (int64_t t = i0; t < i0 + kPer; ++t)
+            if (t <= n_tiles) offsets[t] = 0;
         return;
     }
-    if (i >= n_isects) return;
-    const int cur = (int)keys[i];
-    const int prev = i ? (int)keys[i - 1] : -1;
-    for (int t = prev + 1; t <= cur; ++t) offsets[t] = (int)i;
-    if (i == n_isects - 1)
-        for (int t = cur + 1; t <= n_tiles; ++t) offsets[t] = (int)n_isects;
+    if (i0 >= n_isects) return;
+    KT k[kPer];
+    if (i0 + kPer <= n_isects) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(keys + i0);  // 16-byte aligned: i0 % kPer == 0
+        *reinterpret_cast<uint4 *>(&k[0]) = __ldg(src);
+        *reinterpret_cast<uint4 *>(&k[kPer / 2]) = __ldg(src + 1);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) k[j] = i0 + j < n_isects ? keys[i0 + j] : (KT)0;
+    }
+    int prev = i0 ? (int)keys[i0 - 1] : -1;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int64_t i = i0 + j;
+        if (i >= n_isects) break;
+        const int cur = (int)k[j];
+        for (int t = prev + 1; t <= cur; ++t) offsets[t] = (int)i;
+        prev = cur;
+        if (i == n_isects - 1)
+            for (int t = cur + 1; t <= n_tiles; ++t) offsets[t] = (int)n_isects;
+    }
 }
 
 int launch_offsets(int64_t n_isects, int n_tiles, const void *keys, bool key16, int *offsets, cudaStream_t st) {
     const int64_t work = n_isects > 0 ? n_isects : (int64_t)n_tiles + 1;
-    const unsigned blocks = (unsigned)((work + 255) / 256);
+    const int per = key16 ? 16 : 8;  // keys per thread (offsets_kernel::kPer)
+    const unsigned blocks = (unsigned)((work + 256 * per - 1) / (256 * per));
     if (key16)
         offsets_kernel<<<blocks, 256, 0, st>>>(n_isects, n_tiles, (const unsigned short *)keys, offsets);
     else
