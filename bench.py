@@ -355,6 +355,7 @@ def main():
                          "bilinear upsample fused into the feature re-layout (not the headline)")
     ap.add_argument("--collective", default="allreduce", choices=["allreduce", "reduce_scatter"],
                     help="closing exchange of (num, den) for N > 1")
+    ap.add_argument("--d", type=int, default=0, help="override the config's feature width (experiments only)")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-oracle work (0 = skip)")
     args = ap.parse_args()
@@ -362,6 +363,8 @@ def main():
     import gwbp
 
     cfg = dict(gwbp.scene.CONFIGS[args.config])
+    if args.d:
+        cfg["d"] = args.d
     if args.impl == "reference":
         run_reference(args, cfg)
     else:
