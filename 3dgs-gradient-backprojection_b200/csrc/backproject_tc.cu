@@ -49,8 +49,9 @@ constexpr int STAGE_BYTES = NCMAX * KSL * 2 * 2;  // hi + lo = 16 KB
 constexpr int RING = 3;             // batches in flight between ALU and epilogue
 constexpr uint32_t A_SBO = 128, A_LBO = (MB / 8) * 128;  // W^T: 16 row-groups of 8 Gaussians per K-group
 constexpr int W_PART_BYTES = (kTilePix / 8) * A_LBO;     // 64 KB per hi / lo part
-constexpr int EPI_COLS = 16;                             // columns per epilogue piece (64 B per row)
-constexpr int EPI_PITCH = EPI_COLS * 4 + 16;             // padded row pitch (80 B): conflict-free 16-byte stores
+constexpr int EPI_COLS = 32;                             // columns per epilogue piece (128 B per row)
+constexpr int EPI_ROWS = 16;                             // rows staged per round and warp (half of the warp's 32)
+constexpr int EPI_PITCH = EPI_COLS * 4 + 16;             // padded row pitch (144 B): conflict-free 16-byte stores
 
 constexpr int kEpiWarp0 = 8, kProducerWarp = 13, kMmaWarp = 14, kThreads = 480;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -66,8 +67,8 @@ struct Smem {
     static constexpr int w_hi = 0;
     static constexpr int w_lo = W_PART_BYTES;
     static constexpr int fring = 2 * W_PART_BYTES;
-    static constexpr int stage_out = fring + NSTAGE * STAGE_BYTES;   // epilogue staging: 128 rows x EPI_PITCH
-    static constexpr int gbuf = stage_out + MB * EPI_PITCH;          // 128 x 2 float4
+    static constexpr int stage_out = fring + NSTAGE * STAGE_BYTES;   // epilogue staging: 4 warps x EPI_ROWS x EPI_PITCH
+    static constexpr int gbuf = stage_out + 4 * EPI_ROWS * EPI_PITCH;  // 128 x 2 float4
     static constexpr int rows = gbuf + MB * 32;
     static constexpr int ctrl = rows + RING * (int)sizeof(RowInfo);  // int[RING]
     static constexpr int bars = ctrl + 64;
@@ -122,7 +123,8 @@ struct TcArgs {
     const uint8_t *fpack;
     float *num, *den;
     int d, dp, nchunks, nunits;
-    int debug;  // GWBP_TC_DEBUG env (experiments only): 1 = skip the accumulator reductions
+    int debug;  // GWBP_TC_DEBUG env (experiments only): 1 = skip the accumulator reductions, 2 = every CTA re-reads one
+                // packed tile (features always L2-resident: wrong results, timing only)
     int *unit_counter;
     long long *stats;
 };
@@ -319,14 +321,14 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
         // ===================================== epilogue ======================================
         // TMEM lane = Gaussian row, but a reduction wants one ROW contiguous per instruction (measured:
         // 2.6 TB/s coalesced vs 0.6 TB/s for per-lane rows, profiles/r01_probe.txt).  So each warp stages
-        // its 32 rows x 16 columns in padded smem and re-reads them row-wise: 4 lanes x 16 B = one 64-byte
-        // row piece, 8 rows per `red.global.add.v4.f32` instruction.
+        // 16 of its rows x 32 columns in padded smem and re-reads them row-wise: 8 lanes x 16 B = one 128-byte
+        // row piece, 4 rows per `red.global.add.v4.f32` instruction.
         const int quarter = warp & 3;
         const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
         const int r = 32 * quarter + lane;
-        uint8_t *wstage = smem + Smem::stage_out + (32 * quarter) * EPI_PITCH;  // this warp's 32 staging rows
-        uint8_t *srow = wstage + lane * EPI_PITCH;
-        const int sub = lane >> 2, piece = lane & 3;  // row-in-group (8 rows per instruction) / 16-byte piece of the 64-byte row
+        uint8_t *wstage = smem + Smem::stage_out + (EPI_ROWS * quarter) * EPI_PITCH;  // this warp's 16 staging rows
+        uint8_t *srow = wstage + (lane & 15) * EPI_PITCH;
+        const int rsub = lane >> 3, piece = lane & 7;  // row-in-group (4 rows per instruction) / 16-byte piece of the 128-byte row
         long long live_rows = 0;
         for (int q = 0;; ++q) {
             const int slot = q % RING;
@@ -336,40 +338,36 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             const float dn = rows[slot].den[r];
             const bool live = (gid >= 0) && (dn > 0.0f);
             const unsigned live_mask = __ballot_sync(0xffffffffu, live);
-            // the 4 rows this lane will reduce (rows 8*i + sub) and their accumulator rows
-            int64_t grow[4];
+            // the 8 rows this lane will reduce (rows 4*i + rsub) and their accumulator rows
+            int64_t grow[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) grow[i] = (int64_t)__shfl_sync(0xffffffffu, gid, 8 * i + sub) * a.d;
+            for (int i = 0; i < 8; ++i) grow[i] = (int64_t)__shfl_sync(0xffffffffu, gid, 4 * i + rsub) * a.d;
             for (int c = 0; c < a.nchunks; ++c) {
                 const int u = q * a.nchunks + c, ab = u & 1;
                 const int ncols = min(NCMAX, a.dp - c * NCMAX);   // padded columns of this chunk
-                const int dcols = min(NCMAX, a.d - c * NCMAX);    // real columns of this chunk
                 mbar_wait(bar(Smem::acc_full + ab), (u >> 1) & 1);
                 tc_fence_after();
                 if (quarter == 0) trace(2, 0, q, c);
                 for (int c0 = 0; c0 < ncols; c0 += 32) {
                     float v[32];
                     tmem_ld32(tmem + lane_base + (uint32_t)(ab * NCMAX + c0), v);
+                    const int col = c * NCMAX + c0 + 4 * piece;
 #pragma unroll
-                    for (int hc = 0; hc < 2; ++hc) {  // two 16-column (64-byte) pieces per TMEM load
-                        const int cb = c0 + 16 * hc;
-                        if (cb >= dcols) continue;  // pure padding columns (warp-uniform)
-                        __syncwarp();  // previous piece fully read before it is overwritten
-                        if (live) {
+                    for (int half = 0; half < 2; ++half) {  // lanes 0-15, then lanes 16-31 stage their rows
+                        __syncwarp();  // previous round fully read before it is overwritten
+                        if (live && (lane >> 4) == half) {
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                *reinterpret_cast<float4 *>(srow + 4 * i) =
-                                    make_float4(v[16 * hc + i], v[16 * hc + i + 1], v[16 * hc + i + 2], v[16 * hc + i + 3]);
+                            for (int i = 0; i < 32; i += 4)
+                                *reinterpret_cast<float4 *>(srow + 4 * i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                         }
                         __syncwarp();
-                        const int col = c * NCMAX + cb + 4 * piece;
                         if (col < a.d) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const int row = 8 * i + sub;
+                                const int row = 16 * half + 4 * i + rsub;
                                 if (live_mask >> row & 1u) {
-                                    const float4 x = *reinterpret_cast<const float4 *>(wstage + row * EPI_PITCH + 16 * piece);
-                                    if (!(a.debug & 1)) red_add_v4(a.num + grow[i] + col, x.x, x.y, x.z, x.w);
+                                    const float4 x = *reinterpret_cast<const float4 *>(wstage + (4 * i + rsub) * EPI_PITCH + 16 * piece);
+                                    if (!(a.debug & 1)) red_add_v4(a.num + grow[4 * half + i] + col, x.x, x.y, x.z, x.w);
                                 }
                             }
                         }
@@ -403,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 const int unit = ctrl[slot];
                 mbar_arrive(bar(Smem::ctrl_empty + slot));
                 if (unit < 0) break;
-                const uint8_t *tbase = a.fpack + unit_to_tile(unit, a.t.tw, a.t.th) * tile_bytes;
+                const uint8_t *tbase = a.fpack + ((a.debug & 2) ? blockIdx.x : unit_to_tile(unit, a.t.tw, a.t.th)) * tile_bytes;
                 for (int c = 0; c < a.nchunks; ++c) {
                     const int ncols = min(NCMAX, a.dp - c * NCMAX);
                     const uint32_t bytes = (uint32_t)ncols * KSL * 4;  // hi + lo
