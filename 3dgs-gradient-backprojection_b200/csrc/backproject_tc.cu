@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                         *reinterpret_cast<uint4 *>(smem + Smem::w_lo + j * A_SBO + wslab) = z;
                     }
                 } else {
-#pragma unroll 1
+#pragma unroll 2
                     for (int j = 0; j < MB / 16; ++j) {
                         // 16 Gaussians per step: alpha evaluation is independent across Gaussians (ILP);
                         // only the T update is a serial chain
