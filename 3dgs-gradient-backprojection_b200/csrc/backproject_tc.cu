@@ -108,12 +108,12 @@ constexpr int kTraceRoles = 4, kTraceCap = 4096;
 // so that the ~148 tiles in flight form a compact block: the (typically 2x2..3x3) tiles that touch one
 // Gaussian are processed close together in time and their row reductions merge in the 126 MB L2 instead
 // of each costing a DRAM read-modify-write of the 2 KB accumulator row.
-constexpr int kBand = 8;
-__device__ __forceinline__ int unit_to_tile(int unit, int tw, int th) {
-    const int per_band = kBand * tw;
+constexpr int kBand = 4;   // measured at config G: 2 -> 1.063, 4 -> 1.056, 8 -> 1.082, 16 -> 1.092 ms, whole image -> 1.096
+__device__ __forceinline__ int unit_to_tile(int unit, int tw, int th, int kband) {
+    const int per_band = kband * tw;
     const int band = unit / per_band, r = unit - band * per_band;
-    const int hb = min(kBand, th - band * kBand);
-    const int tx = r / hb, ty = band * kBand + (r - tx * hb);
+    const int hb = min(kband, th - band * kband);
+    const int tx = r / hb, ty = band * kband + (r - tx * hb);
     return ty * tw + tx;
 }
 
@@ -125,6 +125,7 @@ struct TcArgs {
     int d, dp, nchunks, nunits;
     int debug;  // GWBP_TC_DEBUG env (experiments only): 1 = skip the accumulator reductions, 2 = every CTA re-reads one
                 // packed tile (features always L2-resident: wrong results, timing only)
+    int band;   // tile rows per band of the visiting order (kBand; GWBP_TC_BAND overrides for experiments)
     int *unit_counter;
     long long *stats;
 };
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             const int unit = s_unit;
             bar_sync_alu();  // everyone has read s_unit before it is overwritten
             if (unit >= a.nunits) break;
-            const int tile = unit_to_tile(unit, a.t.tw, a.t.th);
+            const int tile = unit_to_tile(unit, a.t.tw, a.t.th, a.band);
             const int ty = tile / a.t.tw, tx = tile % a.t.tw;
             const int s = a.t.offsets[tile], e = a.t.offsets[tile + 1];
             const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 const int unit = ctrl[slot];
                 mbar_arrive(bar(Smem::ctrl_empty + slot));
                 if (unit < 0) break;
-                const uint8_t *tbase = a.fpack + ((a.debug & 2) ? blockIdx.x : unit_to_tile(unit, a.t.tw, a.t.th)) * tile_bytes;
+                const uint8_t *tbase = a.fpack + ((a.debug & 2) ? blockIdx.x : unit_to_tile(unit, a.t.tw, a.t.th, a.band)) * tile_bytes;
                 for (int c = 0; c < a.nchunks; ++c) {
                     const int ncols = min(NCMAX, a.dp - c * NCMAX);
                     const uint32_t bytes = (uint32_t)ncols * KSL * 4;  // hi + lo
@@ -821,6 +822,8 @@ int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t 
     a.stats = stats;
     static const int dbg = getenv("GWBP_TC_DEBUG") ? atoi(getenv("GWBP_TC_DEBUG")) : 0;
     a.debug = dbg;
+    static const int band_env = getenv("GWBP_TC_BAND") ? atoi(getenv("GWBP_TC_BAND")) : kBand;
+    a.band = band_env > 0 ? band_env : kBand;
     GWBP_CUDA_OK(cudaMemsetAsync(a.unit_counter, 0, sizeof(int), st));
     // per-device function attribute: set on every launch (microseconds) so a process that drives several
     // devices never launches with the default 48 KB limit

@@ -1,9 +1,9 @@
 mkdir -p gpurun_out
-for dbg in $DBGS; do
-GWBP_TC_DEBUG=$dbg timeout 600 python bench.py --steps 48 --e2e-steps 0 --cpu-budget 0 --pool 4 > gpurun_out/dbg_$dbg.json 2> gpurun_out/dbg.err
+for v in $VALS; do
+env $VAR=$v timeout 600 python bench.py --steps 48 --e2e-steps 0 --cpu-budget 0 --pool 4 > gpurun_out/dbg_$v.json 2> gpurun_out/dbg.err
 python - <<PY
 import json
-d=json.loads(open("gpurun_out/dbg_$dbg.json").read())
-print("debug=$dbg", round(d["value"],1), "views/s; kernel_ms", round(d["roofline"]["kernel_ms"],4))
+d=json.loads(open("gpurun_out/dbg_$v.json").read())
+print("$VAR=$v", round(d["value"],1), "views/s; kernel_ms", round(d["roofline"]["kernel_ms"],4))
 PY
 done
