@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgwbp.so")
 
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC = 0, 1, 2
-ABI_VERSION = 8
+ABI_VERSION = 9
 KERNEL_FPACK_READY = 0x100
 PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL = 0, 1
 
@@ -27,7 +27,7 @@ class Camera(C.Structure):
 
 
 class WsLayout(C.Structure):
-    _fields_ = [(k, C.c_size_t) for k in ("total", "cnt", "scan", "rec", "mask", "grec", "pmask", "radii",
+    _fields_ = [(k, C.c_size_t) for k in ("total", "cnt", "scan", "rec", "mask", "grec", "erec", "radii",
                                           "tiles_per_gauss", "dkeys0", "dkeys1", "dvals0", "dvals1", "cnt2", "base2",
                                           "tkeys0", "tkeys1", "tvals0", "tvals1", "offsets", "stats", "cub_tmp",
                                           "cub_tmp_bytes")]

@@ -68,7 +68,7 @@ int gwbp_workspace_layout(int64_t n, int32_t width, int32_t height, int64_t cap,
     L->rec = o; o = align_up(o + sizeof(float4) * 2 * n1);
     L->mask = o; o = align_up(o + sizeof(unsigned long long) * n1);
     L->grec = o; o = align_up(o + sizeof(float4) * 2 * n1);
-    L->pmask = o; o = align_up(o + sizeof(unsigned long long) * n1);
+    L->erec = o; o = align_up(o + sizeof(uint4) * n1);
     L->radii = o; o = align_up(o + sizeof(int) * n1);
     L->tiles_per_gauss = o; o = align_up(o + sizeof(int) * n1);
     L->dkeys0 = o; o = align_up(o + sizeof(unsigned) * n1);

@@ -49,7 +49,8 @@ struct CamDev {
 
 // Typed view of the caller's workspace.
 struct WsDev {
-    unsigned long long *cnt, *scan, *mask, *pmask;
+    unsigned long long *cnt, *scan, *mask;
+    uint4 *erec;
     float4 *rec, *grec;
     int *radii, *tiles_per_gauss;
     unsigned *dkeys[2], *dvals[2];  // depth sort of the visible Gaussians
@@ -68,7 +69,7 @@ inline WsDev ws_view(void *base, const gwbp_ws_layout &L) {
     w.cnt = (unsigned long long *)(b + L.cnt);
     w.scan = (unsigned long long *)(b + L.scan);
     w.mask = (unsigned long long *)(b + L.mask);
-    w.pmask = (unsigned long long *)(b + L.pmask);
+    w.erec = (uint4 *)(b + L.erec);
     w.rec = (float4 *)(b + L.rec);
     w.grec = (float4 *)(b + L.grec);
     w.radii = (int *)(b + L.radii);

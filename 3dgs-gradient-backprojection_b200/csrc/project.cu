@@ -294,13 +294,18 @@ int launch_project(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cuda
 
 // ---------------------------------------------------------------------------------------------
 // compaction of the visible Gaussians (ascending index = gsplat's packed order) + depth-sort input
+// + the 16-byte emission record the emission pass gathers in depth order:
+//   .x/.y = tile-hit mask (bit k <-> k-th tile of the rectangle, row-major; all tiles set without culling)
+//   .z    = x0 | y0 << 12 | (bw - 1) << 24, or kErecBig for rectangles of more than 64 tiles
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) compact_kernel(int64_t n, int cull, const unsigned long long *__restrict__ cnt,
+constexpr unsigned kErecBig = 0x80000000u;
+
+__global__ void __launch_bounds__(256) compact_kernel(int64_t n, CamDev cam, const unsigned long long *__restrict__ cnt,
                                                       const unsigned long long *__restrict__ scan,
                                                       const float4 *__restrict__ rec,
                                                       const unsigned long long *__restrict__ mask,
                                                       float4 *__restrict__ grec, int *__restrict__ radii,
-                                                      int *__restrict__ tpg, unsigned long long *__restrict__ pmask,
+                                                      int *__restrict__ tpg, uint4 *__restrict__ erec,
                                                       unsigned *__restrict__ dkeys, unsigned *__restrict__ dvals) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -310,17 +315,26 @@ __global__ void __launch_bounds__(256) compact_kernel(int64_t n, int cull, const
     const float4 r0 = rec[2 * i], r1 = rec[2 * i + 1];
     grec[2 * (int64_t)pos] = make_float4(r0.x, r0.y, r0.z, __int_as_float((int)i));
     grec[2 * (int64_t)pos + 1] = make_float4(r1.x, r1.y, r1.z, r0.w);
-    radii[pos] = __float_as_int(r1.w);
+    const int radius = __float_as_int(r1.w);
+    radii[pos] = radius;
     tpg[pos] = (int)(c & 0xffffffffull);
-    if (cull) pmask[pos] = mask[i];
+    int x0, x1, y0, y1;
+    tile_rect(r0.x, r0.y, radius, cam.tw, cam.th, x0, x1, y0, y1);
+    const int bw = x1 - x0, ntiles = (y1 - y0) * bw;
+    uint4 er = make_uint4(0u, 0u, kErecBig, 0u);
+    if (ntiles <= kMaskTiles) {
+        const unsigned long long mk = cam.cull ? mask[i] : (ntiles >= 64 ? ~0ull : ((1ull << ntiles) - 1ull));
+        er = make_uint4((unsigned)mk, (unsigned)(mk >> 32), (unsigned)x0 | ((unsigned)y0 << 12) | ((unsigned)(bw - 1) << 24), 0u);
+    }
+    erec[pos] = er;
     dkeys[pos] = __float_as_uint(r0.w);  // depth > 0: the bit pattern orders like the value
     dvals[pos] = (unsigned)pos;
 }
 
 int launch_compact(int64_t n, const CamDev &cam, WsDev ws, cudaStream_t st) {
     if (n == 0) return 0;
-    compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, cam.cull, ws.cnt, ws.scan, ws.rec, ws.mask, ws.grec,
-                                                              ws.radii, ws.tiles_per_gauss, ws.pmask, ws.dkeys[0],
+    compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, cam, ws.cnt, ws.scan, ws.rec, ws.mask, ws.grec,
+                                                              ws.radii, ws.tiles_per_gauss, ws.erec, ws.dkeys[0],
                                                               ws.dvals[0]);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
@@ -348,56 +362,65 @@ template <typename KT>
 __global__ void __launch_bounds__(256) emit_kernel(int64_t n_vis, CamDev cam, const unsigned *__restrict__ order,
                                                    const unsigned *__restrict__ base2,
                                                    const float4 *__restrict__ grec, const int *__restrict__ radii,
-                                                   const unsigned long long *__restrict__ pmask,
+                                                   const uint4 *__restrict__ erec,
                                                    KT *__restrict__ tkeys, int *__restrict__ tvals, int64_t cap) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    bool vis = i < n_vis;
-    int x0 = 0, x1 = 0, y0 = 0, y1 = 0, pos = 0;
+    const bool vis = i < n_vis;
+    int pos = 0;
     long long base = 0;
-    CullGauss cg = {};
+    uint4 er = make_uint4(0u, 0u, 0u, 0u);
     if (vis) {
         pos = (int)order[i];
         base = base2[i];
-        const float4 r0 = grec[2 * (int64_t)pos], r1 = grec[2 * (int64_t)pos + 1];
-        tile_rect(r0.x, r0.y, radii[pos], cam.tw, cam.th, x0, x1, y0, y1);
-        if (cam.cull) cg = cull_setup(r0.x, r0.y, r1.x, r1.y, r1.z, r0.z);
+        er = erec[pos];  // the only gather for rectangles of <= 64 tiles
     }
-    const int bw = x1 - x0;
-    const int ntiles = (y1 - y0) * bw;
-    const bool big = vis && ntiles > kMaskTiles;
+    const bool big = vis && (er.z & kErecBig);
     if (vis && !big) {
         long long o = base;
-        unsigned long long mk = cam.cull ? pmask[pos] : ~0ull;
-        for (int ty = y0; ty < y1; ++ty) {
-            unsigned long long row = mk & ((bw < 64) ? ((1ull << bw) - 1ull) : ~0ull);
+        unsigned long long mk = ((unsigned long long)er.y << 32) | er.x;
+        const int x0 = (int)(er.z & 0xfffu), bw = (int)((er.z >> 24) & 0x3fu) + 1;
+        unsigned tbase = (unsigned)((int)((er.z >> 12) & 0xfffu) * cam.tw + x0);
+        const unsigned long long rowmask = (bw < 64) ? ((1ull << bw) - 1ull) : ~0ull;
+        while (mk) {
+            unsigned long long row = mk & rowmask;
             mk = (bw < 64) ? (mk >> bw) : 0ull;
-            const unsigned tbase = (unsigned)(ty * cam.tw + x0);
             while (row) {
                 const int k = __ffsll((long long)row) - 1;
                 row &= row - 1;
                 if (o < cap) { tkeys[o] = (KT)(tbase + (unsigned)k); tvals[o] = pos; }
                 ++o;
             }
+            tbase += (unsigned)cam.tw;
         }
     }
     unsigned m = __ballot_sync(0xffffffffu, big);
-    while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const CullGauss sg = shfl_cull(cg, src);
-        const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
-        const int sbw = __shfl_sync(0xffffffffu, bw, src), snt = __shfl_sync(0xffffffffu, ntiles, src);
-        const int spos = __shfl_sync(0xffffffffu, pos, src);
-        long long sbase = __shfl_sync(0xffffffffu, base, src);
-        for (int k0 = 0; k0 < snt; k0 += 32) {  // ordered warp compaction
-            const int k = k0 + lane;
-            const int ty = sy0 + k / sbw, tx = sx0 + k % sbw;
-            const bool hit = (k < snt) && (!cam.cull || tile_hit(sg, tx, ty, cam.W, cam.H));
-            const unsigned hm = __ballot_sync(0xffffffffu, hit);
-            const long long o = sbase + __popc(hm & ((1u << lane) - 1u));
-            if (hit && o < cap) { tkeys[o] = (KT)(ty * cam.tw + tx); tvals[o] = spos; }
-            sbase += __popc(hm);
+    if (m) {  // rare: rectangles of more than 64 tiles are re-tested and emitted by the whole warp
+        int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+        CullGauss cg = {};
+        if (big) {
+            const float4 r0 = grec[2 * (int64_t)pos], r1 = grec[2 * (int64_t)pos + 1];
+            tile_rect(r0.x, r0.y, radii[pos], cam.tw, cam.th, x0, x1, y0, y1);
+            if (cam.cull) cg = cull_setup(r0.x, r0.y, r1.x, r1.y, r1.z, r0.z);
+        }
+        const int bw = x1 - x0, ntiles = (y1 - y0) * bw;
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const CullGauss sg = shfl_cull(cg, src);
+            const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
+            const int sbw = __shfl_sync(0xffffffffu, bw, src), snt = __shfl_sync(0xffffffffu, ntiles, src);
+            const int spos = __shfl_sync(0xffffffffu, pos, src);
+            long long sbase = __shfl_sync(0xffffffffu, base, src);
+            for (int k0 = 0; k0 < snt; k0 += 32) {  // ordered warp compaction
+                const int k = k0 + lane;
+                const int ty = sy0 + k / sbw, tx = sx0 + k % sbw;
+                const bool hit = (k < snt) && (!cam.cull || tile_hit(sg, tx, ty, cam.W, cam.H));
+                const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                const long long o = sbase + __popc(hm & ((1u << lane) - 1u));
+                if (hit && o < cap) { tkeys[o] = (KT)(ty * cam.tw + tx); tvals[o] = spos; }
+                sbase += __popc(hm);
+            }
         }
     }
 }
@@ -407,10 +430,10 @@ int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev w
     if (n_vis == 0) return 0;
     const unsigned blocks = (unsigned)((n_vis + 255) / 256);
     if (key16)
-        emit_kernel<unsigned short><<<blocks, 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.pmask,
+        emit_kernel<unsigned short><<<blocks, 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.erec,
                                                             (unsigned short *)ws.tkeys[0], ws.tvals[0], cap);
     else
-        emit_kernel<unsigned><<<blocks, 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.pmask,
+        emit_kernel<unsigned><<<blocks, 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.erec,
                                                       ws.tkeys[0], ws.tvals[0], cap);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;

@@ -42,7 +42,7 @@ extern "C" {
 #endif
 
 #define GWBP_TILE 16
-#define GWBP_ABI_VERSION 8
+#define GWBP_ABI_VERSION 9
 
 /* kernel selection for gwbp_backproject_view and gwbp_render_view */
 #define GWBP_KERNEL_AUTO 0
@@ -76,7 +76,7 @@ typedef struct gwbp_ws_layout {
     size_t rec;       /* float4 [2*n]   unpacked projection records */
     size_t mask;      /* uint64 [n]     unpacked tile-hit masks (tile culling) */
     size_t grec;      /* float4 [2*n]   packed records: (mean2d.xy, opacity, gaussian_id bits), (conic.xyz, depth) */
-    size_t pmask;     /* uint64 [n]     packed tile-hit masks */
+    size_t erec;      /* uint4 [n]      emission records of the visible Gaussians: tile-hit mask, packed rectangle */
     size_t radii;     /* int32  [n]     packed radii */
     size_t tiles_per_gauss; /* int32 [n] packed */
     size_t dkeys0, dkeys1;  /* uint32 [n]  depth bits of the visible Gaussians (sort double buffer) */
