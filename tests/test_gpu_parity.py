@@ -384,6 +384,41 @@ def test_full_size_config_G_properties(gwbp):
     assert abs(lhs - rhs) <= 1e-5 * scale, (lhs, rhs, scale)
 
 
+def test_full_size_config_M_properties(gwbp):
+    """BASELINE config[4] at FULL size on one GPU (6 M Gaussians, 1920x1080, D = 768: three column chunks on the
+    tcgen05 path), through size-independent properties: sum(den_v) == sum(alpha_v); constant features =>
+    num == den * c; and view-shard additivity -- two ranks' (num, den) add up to the single-process result,
+    which is all the closing all-reduce of the multi-GPU job relies on (dist.py)."""
+    S = gwbp.scene
+    cfg = S.CONFIGS["M"]
+    W, H, d = cfg["width"], cfg["height"], cfg["d"]
+    sc = S.make_scene(cfg["n"], 0)
+    vm, K = S.make_cameras(cfg["views"], W, H, 0)
+    args = (_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities), d)
+    c = torch.linspace(-1, 1, d, device="cuda")
+    planar = c[:, None, None].expand(d, H, W).contiguous()  # the reference's layout: [D,H,W] viewed as [H,W,D]
+    F = planar.permute(1, 2, 0)
+    both = gwbp.BackProjector(*args, kernel="tc")
+    both.add_view(vm[0], K, W, H, F)
+    view = both.add_view(vm[500], K, W, H, F)
+    r0, r1 = gwbp.BackProjector(*args, kernel="tc"), gwbp.BackProjector(*args, kernel="tc")
+    r0.add_view(vm[0], K, W, H, F)
+    v1 = r1.add_view(vm[500], K, W, H, F)
+    den1 = r1.den - 1e-12
+    _, alpha = v1.render(torch.ones(sc.n, 1, device="cuda"))
+    tot_a, tot_d = float(alpha.double().sum()), float(den1.double().sum())
+    assert abs(tot_a - tot_d) <= 2e-4 * tot_a, (tot_a, tot_d)
+    seen = den1 > 1e-5
+    assert int(seen.sum()) > 50_000
+    assert float((r1.num[seen] / den1[seen, None] - c[None]).abs().max()) < 2e-3
+    den_sum = r0.den + r1.den - 1e-12  # the initial 1e-12 is counted once (dist.allreduce_accumulators)
+    assert torch.allclose(den_sum, both.den, rtol=1e-5, atol=1e-9)
+    r0.num += r1.num
+    assert torch.allclose(r0.num, both.num, rtol=1e-4, atol=1e-6)
+    assert view.n_isects == v1.n_isects
+
+
+
 def test_rasterization_backgrounds_depth_modes_and_sh(gwbp, coracle, case, tmp_path):
     """The remaining kwargs the reference passes to `rasterization`: backgrounds (affordance demo :918),
     render_mode="RGB+D" (click_and_segment.py:251) / "RGB+ED", sh_degree=3 (backproject.py:99)."""
