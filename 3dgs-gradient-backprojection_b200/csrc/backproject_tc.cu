@@ -523,58 +523,42 @@ __global__ void __launch_bounds__(256) fpack_kernel(const float *__restrict__ F,
 
 
 // Planar input ([D,H,W] buffer exposed as a permuted [H,W,D] view: sW == 1, the reference's layout,
-// backproject.py:110-113).  Only pixels are contiguous, so one CTA takes one image row x 32 pixels
-// (two tiles) x one column chunk: every warp load is 128 contiguous bytes of one channel.
-// One CTA = one image row x 256 pixels (16 tiles) x 32 channels: every channel row is read as 1 KB of contiguous
-// bytes (DRAM page locality; planes are megabytes apart) and written back as 2 KB runs of core matrices.
-constexpr int kPlanarCols = 32, kPlanarPix = 256;
-__global__ void __launch_bounds__(256) fpack_planar_kernel(const float *__restrict__ F, int64_t sH, int64_t sD,
-                                                           int W, int H, int tw, int d, int dp, int nchunks,
-                                                           uint8_t *__restrict__ out) {
-    __shared__ float slab[kPlanarCols][kPlanarPix + 1];  // [channel][pixel], +1 pad: conflict-free both ways
-    constexpr int kSub = NCMAX / kPlanarCols;
-    const int span = blockIdx.x, y = blockIdx.y, c = blockIdx.z / kSub, sub = blockIdx.z % kSub;
-    const int ncols = min(NCMAX, dp - c * NCMAX);          // columns of this chunk (UMMA N)
-    const int n_lo = sub * kPlanarCols;                     // this CTA's columns [n_lo, n_hi) of the chunk
-    const int n_hi = min(ncols, n_lo + kPlanarCols);
-    if (n_lo >= n_hi) return;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int xb = span * kPlanarPix;
-    // warp w owns channels w, w+8, ...; one channel row = kPlanarPix/32 independent 128-byte loads per lane
-    constexpr int kLoads = kPlanarPix / 32;
-    for (int n = n_lo + warp; n < n_hi; n += 8) {
-        const int col = c * NCMAX + n;
-        const float *src = F + y * sH + col * sD + xb;
-        float v[kLoads];
+// backproject.py:110-113).  lane = pixel: a CTA takes 256 consecutive pixels of one image row x 64 channels.  A lane
+// loads its pixel's 64 channel values (each warp load = 128 contiguous bytes of one channel row, the CTA's 8 warps
+// 1 KB: DRAM page locality, the planes are megabytes apart), splits them and writes 16-byte core-matrix rows; 8
+// consecutive lanes write 128 contiguous bytes, the eight 8-channel groups of a thread 1 KB.  No shared memory: the
+// transposition is free because a lane gathers its own pixel's channels.  64 independent loads in flight per thread;
+// measured at config G (tools/pack_bench.py): 0.739 ms = 6.04 TB/s read + write, 94 % of the measured copy peak
+// (the previous version staged [channel][pixel] slabs in shared memory: 0.863 ms; 128 px x 32 ch: 0.805;
+// 256 x 32: 0.777; 512 x 32: 0.766; 128 x 16: 0.794).
+template <int kPix, int kCols>
+__global__ void __launch_bounds__(kPix) fpack_planar_kernel(const float *__restrict__ F, int64_t sH, int64_t sD,
+                                                               int W, int H, int tw, int d, int dp,
+                                                               uint8_t *__restrict__ out) {
+    const int x = blockIdx.x * kPix + threadIdx.x, y = blockIdx.y, col0 = blockIdx.z * kCols;
+    const int tx = x >> 4, p = x & 15;
+    if (tx >= tw) return;
+    const int c = col0 / NCMAX, ncols = min(NCMAX, dp - c * NCMAX), n0 = col0 - c * NCMAX;
+    const int ngroups = min(kCols, ncols - n0) / 8;  // 8-channel groups of this block that exist in the chunk
+    const bool ok = x < W;
+    const float *src = F + (int64_t)y * sH + x + (int64_t)col0 * sD;
+    float v[kCols];
 #pragma unroll
-        for (int k = 0; k < kLoads; ++k) {
-            const int px = lane + 32 * k;
-            v[k] = (col < d && xb + px < W) ? __ldg(src + px) : 0.0f;
-        }
-#pragma unroll
-        for (int k = 0; k < kLoads; ++k) slab[n - n_lo][lane + 32 * k] = v[k];
-    }
-    __syncthreads();
-    const int ty = y / kTile, ks = y % kTile;
+    for (int i = 0; i < kCols; ++i) v[i] = (ok && col0 + i < d) ? __ldcs(src + (int64_t)i * sD) : 0.0f;
     const uint32_t lbo = (uint32_t)(ncols / 8) * 128, part = (uint32_t)ncols * KSL * 2;
-    // item = (pixel 0..127, 8-column group): one 16-byte core-matrix row, hi and lo
-    for (int item = t; item < kPlanarPix * ((n_hi - n_lo) / 8); item += 256) {
-        const int px = item % kPlanarPix, ngl = item / kPlanarPix, ng = n_lo / 8 + ngl;
-        const int tx = (xb + px) >> 4, p = px & 15;
-        if (tx >= tw) continue;
-        float f[8];
+    uint8_t *blk = out + (int64_t)((y >> 4) * tw + tx) * kTilePix * dp * 4 + (int64_t)c * NCMAX * kTilePix * 4 +
+                   (int64_t)(y & 15) * part * 2 + (uint32_t)(p >> 3) * lbo + (uint32_t)(n0 / 8) * 128 + (uint32_t)(p & 7) * 16;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = slab[8 * ngl + i][px];
-        uint4 hi, lo;
-        split_bf16x2(f[0], f[1], hi.x, lo.x);
-        split_bf16x2(f[2], f[3], hi.y, lo.y);
-        split_bf16x2(f[4], f[5], hi.z, lo.z);
-        split_bf16x2(f[6], f[7], hi.w, lo.w);
-        const int tile = ty * tw + tx;
-        uint8_t *blk = out + (int64_t)tile * kTilePix * dp * 4 + (int64_t)c * NCMAX * kTilePix * 4 + (int64_t)ks * part * 2;
-        const uint32_t off = (uint32_t)(p / 8) * lbo + (uint32_t)ng * 128 + (uint32_t)(p % 8) * 16;
-        *reinterpret_cast<uint4 *>(blk + off) = hi;
-        *reinterpret_cast<uint4 *>(blk + part + off) = lo;
+    for (int g = 0; g < kCols / 8; ++g) {
+        if (g < ngroups) {
+            uint4 hi, lo;
+            split_bf16x2(v[8 * g + 0], v[8 * g + 1], hi.x, lo.x);
+            split_bf16x2(v[8 * g + 2], v[8 * g + 3], hi.y, lo.y);
+            split_bf16x2(v[8 * g + 4], v[8 * g + 5], hi.z, lo.z);
+            split_bf16x2(v[8 * g + 6], v[8 * g + 7], hi.w, lo.w);
+            *reinterpret_cast<uint4 *>(blk + g * 128) = hi;
+            *reinterpret_cast<uint4 *>(blk + part + g * 128) = lo;
+        }
     }
 }
 
@@ -765,8 +749,9 @@ int launch_fpack(int W, int H, const float *F, int64_t sH, int64_t sW, int64_t s
         if (H % kTile)
             GWBP_CUDA_OK(cudaMemsetAsync((uint8_t *)fpack + (size_t)(th - 1) * tw * kTilePix * dp * 4, 0,
                                          (size_t)tw * kTilePix * dp * 4, st));
-        dim3 grid((W + kPlanarPix - 1) / kPlanarPix, H, nchunks * (NCMAX / kPlanarCols));
-        fpack_planar_kernel<<<grid, 256, 0, st>>>(F, sH, sD, W, H, tw, d, dp, nchunks, (uint8_t *)fpack);
+        constexpr int kPix = 256, kCols = 64;
+        dim3 grid((tw * kTile + kPix - 1) / kPix, H, (dp + kCols - 1) / kCols);
+        fpack_planar_kernel<kPix, kCols><<<grid, kPix, 0, st>>>(F, sH, sD, W, H, tw, d, dp, (uint8_t *)fpack);
     } else {
         fpack_kernel<<<ntiles * nchunks, 256, 0, st>>>(F, sH, sW, sD, W, H, tw, d, dp, nchunks, (uint8_t *)fpack);
     }
