@@ -743,7 +743,7 @@ int launch_fpack(int W, int H, const float *F, int64_t sH, int64_t sW, int64_t s
     if (ntiles == 0) return 0;
     GWBP_REQUIRE(((uintptr_t)fpack & 127) == 0, "fpack must be 128-byte aligned");
     const int dp = round_up(d, 16), nchunks = (dp + NCMAX - 1) / NCMAX;
-    if (sW == 1 && sD != 1) {
+    if (sW == 1 && sD != 1 && H <= 65535) {  // (grid.y = H)
         // rows of the last tile row beyond H are never written by the planar kernel: they are only
         // ever multiplied by zero weights, but must not hold NaN/Inf bit patterns -> clear once per view
         if (H % kTile)

@@ -188,6 +188,48 @@ def test_feature_strides_do_not_matter(gwbp, case):
     assert torch.allclose(a.num, b.num, rtol=1e-5, atol=1e-6) and torch.allclose(a.den, b.den, rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("d", [48, 272])
+def test_tcgen05_feature_layouts_agree(gwbp, d):
+    """The tensor-core path re-lays-out F itself: the reference's planar [D,H,W] view (lane = pixel kernel), a
+    contiguous [H,W,D] tensor and an arbitrary strided view (generic kernel) must give the same accumulators, and
+    agree with the CUDA-core kernel that reads F in place.  Odd image size: partial tiles in x and y; d = 272: a
+    second, 16-column chunk."""
+    S = gwbp.scene
+    W, H = 211, 137
+    sc = S.make_scene(5000, 13)
+    vm, K = S.make_cameras(2, W, H, 13)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    args = (_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities), d)
+    planar = [torch.randn(d, H, W, generator=g, device="cuda") for _ in range(2)]
+    wide = [torch.zeros(H, 2 * W, d + 3, device="cuda") for _ in range(2)]
+    for v in range(2):
+        wide[v][:, ::2, 1:d + 1] = planar[v].permute(1, 2, 0)
+    layouts = {
+        "planar": [p.permute(1, 2, 0) for p in planar],
+        "contiguous": [p.permute(1, 2, 0).contiguous() for p in planar],
+        "strided": [w[:, ::2, 1:d + 1] for w in wide],
+    }
+    ref = gwbp.BackProjector(*args, kernel="simt")
+    for v in range(2):
+        ref.add_view(vm[v], K, W, H, layouts["planar"][v])
+    seen = ref.den > 1e-6
+    first = None
+    for name, maps in layouts.items():
+        assert (maps[0].stride(1) == 1) == (name == "planar")
+        bp = gwbp.BackProjector(*args, kernel="tc")
+        for v in range(2):
+            bp.add_view(vm[v], K, W, H, maps[v])
+        if first is None:  # tensor cores vs CUDA cores: split-bf16 contraction, threshold flips aside
+            first = bp
+            err = (bp.num[seen] - ref.num[seen]).norm(dim=1) / ref.num[seen].norm(dim=1).clamp_min(1e-6)
+            assert float(torch.quantile(err, 0.999)) < REL_TOL, float(torch.quantile(err, 0.999))
+            assert int((err > REL_TOL).sum()) <= max(2, int(2e-4 * int(seen.sum())))
+        else:  # same packed operand whatever the input layout: only the order of the atomic adds differs
+            assert torch.allclose(bp.den, first.den, rtol=1e-5, atol=1e-9), name
+            assert torch.allclose(bp.num, first.num, rtol=1e-4, atol=1e-5), name
+
+
+
 def test_rasterization_autograd_reproduces_reference_loop(gwbp, coracle, noracle, case):
     """The reference's own code shape (backproject.py:62-72,115-151) on our `rasterization`."""
     sc, vm, K, feats = case
