@@ -21,15 +21,15 @@
 //   warp 14     MMA      : one thread issues tcgen05.mma; accumulators [128 x <=256] fp32 are double
 //                          buffered in the 512 TMEM columns so the epilogue of one batch overlaps the
 //                          MMAs of the next.
-//   warps 8-11  epilogue : tcgen05.ld the accumulator (lane = Gaussian row), transpose 32x32 pieces
+//   warps 8-11  epilogue : tcgen05.ld the accumulator (lane = Gaussian row), transpose 16-row x 32-column pieces
 //                          through padded smem and reduce them into num[N,D] with row-contiguous
 //                          red.global.add.v4.f32 (measured 2.6 TB/s of payload on scattered 2 KB rows vs
 //                          0.6 TB/s for per-lane rows -- profiles/r01_probe.txt).
 // The W buffer (128 KB) is single: warp w re-fills its 32-pixel slab for batch q+1 as soon as the MMA
 // of batch q's LAST column chunk has consumed it (per-warp mbarriers), so generation and MMA overlap.
 //
-// The feature map is re-laid-out once per view by fpack_kernel (fp32 [H,W,D], any strides ->
-// bf16 hi/lo, tile-major, already in UMMA core-matrix order) so the producer needs no tensor map.
+// The feature map is re-laid-out once per view by fpack_planar_kernel / fpack_kernel (fp32 [H,W,D], any strides
+// -> bf16 hi/lo, tile-major, already in UMMA core-matrix order) so the producer needs no tensor map.
 #include <stdlib.h>
 
 #include "common.cuh"
