@@ -28,6 +28,7 @@ SOURCES = {
     "finalize.cu": [],
     "backproject_tc.cu": [],
     "render_tc.cu": [],
+    "render_tc_wc.cu": [],
 }
 
 

@@ -1,6 +1,7 @@
 // extern "C" surface of libgwbp.so (see include/gwbp.h for the contract and the reference
 // call sites each entry point replaces).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -39,6 +40,8 @@ static TileCtx tile_ctx(const gwbp_camera *cam, const void *ws, const gwbp_ws_la
     t.flatten = w.tvals[info->sorted_buf];
     t.offsets = w.offsets;
     t.scratch = w.stats;
+    t.dead = (char *)const_cast<void *>(ws) + L.cnt;
+    t.dead_bytes = L.grec - L.cnt;
     t.W = cam->width; t.H = cam->height;
     t.tw = info->tile_w; t.th = info->tile_h;
     return t;
@@ -208,7 +211,11 @@ int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam, const void
     int k = kernel & 0xff;
     if (k == GWBP_KERNEL_AUTO)
         k = (d >= 64 && render_tc_supported(colors, color_stride, d)) ? GWBP_KERNEL_TC : GWBP_KERNEL_SIMT;
-    if (k == GWBP_KERNEL_TC) return launch_render_tc(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream);
+    if (k == GWBP_KERNEL_TC) {
+        static const int wcache = getenv("GWBP_RENDER_WCACHE") ? atoi(getenv("GWBP_RENDER_WCACHE")) : 0;
+        return wcache ? launch_render_tc_wc(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream)
+                      : launch_render_tc(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream);
+    }
     GWBP_REQUIRE(k == GWBP_KERNEL_SIMT, "unknown kernel id %d", kernel);
     return launch_render_simt(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream);
 }
