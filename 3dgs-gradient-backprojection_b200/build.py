@@ -28,7 +28,6 @@ SOURCES = {
     "finalize.cu": [],
     "backproject_tc.cu": [],
     "render_tc.cu": [],
-    "render_tc_wc.cu": [],
 }
 
 

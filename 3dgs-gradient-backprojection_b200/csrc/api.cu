@@ -211,11 +211,7 @@ int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam, const void
     int k = kernel & 0xff;
     if (k == GWBP_KERNEL_AUTO)
         k = (d >= 64 && render_tc_supported(colors, color_stride, d)) ? GWBP_KERNEL_TC : GWBP_KERNEL_SIMT;
-    if (k == GWBP_KERNEL_TC) {
-        static const int wcache = getenv("GWBP_RENDER_WCACHE") ? atoi(getenv("GWBP_RENDER_WCACHE")) : 0;
-        return wcache ? launch_render_tc_wc(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream)
-                      : launch_render_tc(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream);
-    }
+    if (k == GWBP_KERNEL_TC) return launch_render_tc(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream);
     GWBP_REQUIRE(k == GWBP_KERNEL_SIMT, "unknown kernel id %d", kernel);
     return launch_render_simt(t, colors, color_stride, d, background, render, alpha, (cudaStream_t)stream);
 }

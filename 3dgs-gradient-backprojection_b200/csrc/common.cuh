@@ -141,8 +141,6 @@ int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t 
 bool render_tc_supported(const float *colors, int64_t cstride, int d);
 int launch_render_tc(const TileCtx &t, const float *colors, int64_t cstride, int d, const float *bg, float *render,
                      float *alpha, cudaStream_t st);
-int launch_render_tc_wc(const TileCtx &t, const float *colors, int64_t cstride, int d, const float *bg, float *render,
-                        float *alpha, cudaStream_t st);  // render_tc_wc.cu: weight-cache variant (GWBP_RENDER_WCACHE=1)
 
 // ---- device helpers ------------------------------------------------------------------------
 // One Gaussian against one pixel, gsplat rasterize_to_pixels_fwd semantics.

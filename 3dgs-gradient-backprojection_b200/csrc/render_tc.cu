@@ -5,19 +5,23 @@
 //      A = X^T  [M = 128 features x K = 16 Gaussians]   MN-major (a Gaussian's 8 consecutive features = 16 B)
 //      B = W    [K = 16 Gaussians x N = 256 pixels]     K-major  (a pixel's 8 consecutive Gaussians = 16 B)
 //      D        [128 features (TMEM lanes) x 256 pixels (TMEM columns)] fp32, double buffered in the 512 columns
-// so the weights are generated once per (tile, 128-feature chunk) -- the chunked CUDA-core kernel
-// (composite_simt.cu, and gsplat itself) regenerates them for every 32 channels -- and the epilogue writes
-// 128 contiguous bytes per pixel without a transpose (lane = feature).  Work unit = (tile, chunk): with two
-// accumulator buffers the epilogue's stores (the whole [H,W,D] output must reach DRAM: 2.2 GB at config G)
-// drain while the next unit is being contracted.  A 256-feature unit halves the weight generation but
-// serialises those stores behind the MMAs: measured 2.8 ms vs this layout at config G (profiles/r01_render_tc.txt).
+// The [128 x 256] accumulator pair fills the TMEM, so a D-channel render takes D/128 passes over a tile's
+// Gaussians.  The weights are GENERATED once per tile, in pass 0, which also records them (64 KB per 64-Gaussian
+// batch, per-CTA scratch in the dead part of the workspace, L2-resident); the passes of the other feature chunks copy
+// them back instead of recomputing them (the chunked CUDA-core kernel -- composite_simt.cu, and gsplat itself --
+// regenerates them for every 32 channels).  The epilogue writes 128 contiguous bytes per pixel without a transpose
+// (lane = feature).  With two accumulator buffers the epilogue's stores of one (tile, chunk) unit (the whole [H,W,D]
+// output must reach DRAM: 2.2 GB at config G) drain while the next unit is being contracted.  A 256-feature unit
+// halves the passes but serialises those stores behind the MMAs: measured 2.8 ms at config G
+// (profiles/r01_render_tc.txt).
 //
 // Both operands are split into bf16 hi + lo and three MMAs are issued per K-step (hi*hi + hi*lo + lo*hi),
 // as in backproject_tc.cu: ~2^-16 relative error in the contraction.
 //
 // One persistent CTA per SM, warp-specialised (544 threads):
 //   warps 0-7   ALU      : thread = pixel; walks the tile's depth-sorted list 64 Gaussians at a time and writes
-//                          W (bf16 hi/lo) straight into the UMMA layout, double buffered.
+//                          W (bf16 hi/lo) straight into the UMMA layout, double buffered (pass 0: generated and
+//                          recorded; later passes: replayed from the record).
 //   warps 8-11  loaders  : gather the batch's X rows (fp32, 512 B pieces), split to bf16 hi/lo and store them
 //                          in UMMA layout into an 8-stage ring (one 16-Gaussian K-step per stage).
 //   warps 12-15 epilogue : at the end of a (tile, chunk) unit, tcgen05.ld the accumulators and store
@@ -122,10 +126,13 @@ struct RenderArgs {
     int64_t cstride;
     const float *bg;
     float *render, *alpha;
-    int d, dp, nchunks, nunits;
+    int d, dp, nchunks, ntiles;
     int *unit_counter;
+    uint4 *wsave;  // weight cache: per CTA `cap` batches x (8 Gaussian groups x hi/lo x 256 threads) uint4 ...
+    int *gsave;    // ... and the batches' Gaussian ids (GB ints each)
+    int cap;       // batches per tile the cache holds (0 = regenerate the weights for every feature chunk)
     unsigned long long *prof;  // debug: per-role cycle accounting, [4 roles][8 categories] (gwbp_debug_set_trace)
-    int debug;  // GWBP_RENDER_DEBUG (experiments only): 1 = no X loads, 2 = no render stores
+    int debug;  // GWBP_RENDER_DEBUG (experiments only): 1 = no X loads, 2 = no render stores, 8 = no weight cache
 };
 
 __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs a) {
@@ -161,131 +168,203 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs
         };
         Prof pf;  // ALU: 0 other, 1 popc barrier, 2 wait entry slot, 3 wait w_free, 4 generate + store W
         pf.start(a.prof != nullptr && tid == 0);
-        // Work queue: the NEXT unit id is requested at the start of the current unit (tid 0 keeps the atomic's
-        // result in a register) so its round trip is hidden behind the unit's work.
+        // Work queue: TILES.  The NEXT tile id is requested at the start of the current one (tid 0 keeps the atomic's
+        // result in a register) so its round trip is hidden behind the tile's work.
+        //
+        // Weight cache.  The [128 feature x 256 pixel] accumulator pair fills the TMEM, so a D-channel render takes
+        // D/128 passes over the tile's Gaussians.  The weights do not depend on the feature chunk: pass 0 generates
+        // them (the kernel's critical path: ~26 instructions per pixel and Gaussian) and also streams every thread's
+        // 16 core-matrix rows per batch to a per-CTA scratch in the dead part of the workspace (coalesced, L2
+        // resident: 64 KB per batch); passes 1.. copy them back into the W buffers instead of recomputing them.  A
+        // tile that walks more than `cap` batches falls back to regeneration for all its passes.
+        uint4 *const wsave = a.wsave + (size_t)blockIdx.x * a.cap * (16 * 256);
+        int *const gsave = a.gsave + (size_t)blockIdx.x * a.cap * GB;
         if (tid == 0) s_unit[1] = atomicAdd(a.unit_counter, 1);
         bar_sync_alu();
-        int unit = s_unit[1];
-        for (int useq = 0; unit < a.nunits; ++useq) {
-            int next_unit = 0;
-            if (tid == 0) next_unit = atomicAdd(a.unit_counter, 1);
-            const int tile = unit / a.nchunks, chunk = unit - tile * a.nchunks;
+        int tile = s_unit[1];
+        for (int useq = 0; tile < a.ntiles; ++useq) {
+            int next_tile = 0;
+            if (tid == 0) next_tile = atomicAdd(a.unit_counter, 1);
             const int ty = tile / a.t.tw, tx = tile % a.t.tw;
             const int s = a.t.offsets[tile], eend = a.t.offsets[tile + 1];
             const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
             const bool inside = yy < a.t.H && xx < a.t.W;
             const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
-            bool done = !inside;
-            float T = 1.0f;
-            int nbatches = 0;
-            // Records are fetched two-deep: the list entry (Gaussian index) of batch b+2 and the record of batch
-            // b+1 are requested while batch b is processed, so no load waits on another load inside the loop.
-            float4 r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            int idn = -1;
-            if (tid < GB) {
-                if (s + tid < eend) {
-                    const int id = a.t.flatten[s + tid];
-                    r0 = a.t.grec[2 * (int64_t)id];
-                    r1 = a.t.grec[2 * (int64_t)id + 1];
-                }
-                if (s + GB + tid < eend) idn = a.t.flatten[s + GB + tid];
-            }
-            for (int b = s; b < eend; b += GB) {
-                pf.tick(0);
-                if (bar_red_popc_alu(!done) == 0) break;  // also: every warp is done reading gbuf of the previous batch
-                pf.tick(1);
-                const int slot = e % ERING;
-                wait_entry_slot(slot);
-                pf.tick(2);
-                if (tid < GB) {
-                    gbuf[tid] = make_float4(r0.x, r0.y, r0.z, -0.5f * kLog2e * r1.x);
-                    gbuf[GB + tid] = make_float4(-kLog2e * r1.y, -0.5f * kLog2e * r1.z, 0.f, 0.f);
-                    ent[slot].gid[tid] = __float_as_int(r0.w);
-                }
-                if (tid == 0) {
-                    ent[slot].unit = unit;
-                    ent[slot].nb = min(GB, eend - b);
-                    ent[slot].first = (nbatches == 0);
-                    ent[slot].nbatches = 0;
-                }
-                bar_sync_alu();
-                if (tid == 0) mbar_arrive(bar(Smem::ent_full + slot));
-                ++e;
-                ++nbatches;
-                r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                r1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tid < GB) {
-                    if (idn >= 0) {
-                        r0 = a.t.grec[2 * (int64_t)idn];
-                        r1 = a.t.grec[2 * (int64_t)idn + 1];
+            bool cached = a.cap > 0;
+            int nb0 = 0;       // batches pass 0 walked
+            float T_end = 1.0f;
+            for (int chunk = 0; chunk < a.nchunks; ++chunk) {
+                const int unit = tile * a.nchunks + chunk;
+                int nbatches = 0;
+                float T = 1.0f;
+                if (chunk == 0 || !cached) {
+                    // ---------------- generate (and, in pass 0, record) ----------------
+                    bool done = !inside;
+                    // Records are fetched two-deep: the list entry (Gaussian index) of batch b+2 and the record of
+                    // batch b+1 are requested while batch b is processed, so no load waits on another load in the loop.
+                    float4 r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int idn = -1;
+                    if (tid < GB) {
+                        if (s + tid < eend) {
+                            const int id = a.t.flatten[s + tid];
+                            r0 = a.t.grec[2 * (int64_t)id];
+                            r1 = a.t.grec[2 * (int64_t)id + 1];
+                        }
+                        if (s + GB + tid < eend) idn = a.t.flatten[s + GB + tid];
                     }
-                    idn = (b + 2 * GB + tid < eend) ? a.t.flatten[b + 2 * GB + tid] : -1;
-                }
-                const int buf = q & 1;
-                pf.tick(0);
-                if (q >= 2) mbar_wait(bar(Smem::w_free + buf), ((q >> 1) - 1) & 1);
-                pf.tick(3);
-                uint8_t *whi = smem + Smem::w + buf * W_BUF + pslab, *wlo = whi + W_PART;
-                if (__all_sync(0xffffffffu, done)) {
-                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                    for (int b = s; b < eend; b += GB) {
+                        pf.tick(0);
+                        if (bar_red_popc_alu(!done) == 0) break;  // also: every warp is done reading gbuf of the previous batch
+                        pf.tick(1);
+                        const int slot = e % ERING;
+                        wait_entry_slot(slot);
+                        pf.tick(2);
+                        if (chunk == 0 && nbatches >= a.cap) cached = false;  // uniform: the tile outgrew the cache
+                        const bool save = chunk == 0 && cached;
+                        if (tid < GB) {
+                            gbuf[tid] = make_float4(r0.x, r0.y, r0.z, -0.5f * kLog2e * r1.x);
+                            gbuf[GB + tid] = make_float4(-kLog2e * r1.y, -0.5f * kLog2e * r1.z, 0.f, 0.f);
+                            ent[slot].gid[tid] = __float_as_int(r0.w);
+                            if (save) gsave[nbatches * GB + tid] = __float_as_int(r0.w);
+                        }
+                        if (tid == 0) {
+                            ent[slot].unit = unit;
+                            ent[slot].nb = min(GB, eend - b);
+                            ent[slot].first = (nbatches == 0);
+                            ent[slot].nbatches = 0;
+                        }
+                        bar_sync_alu();
+                        if (tid == 0) mbar_arrive(bar(Smem::ent_full + slot));
+                        ++e;
+                        r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                        r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (tid < GB) {
+                            if (idn >= 0) {
+                                r0 = a.t.grec[2 * (int64_t)idn];
+                                r1 = a.t.grec[2 * (int64_t)idn + 1];
+                            }
+                            idn = (b + 2 * GB + tid < eend) ? a.t.flatten[b + 2 * GB + tid] : -1;
+                        }
+                        const int buf = q & 1;
+                        pf.tick(0);
+                        if (q >= 2) mbar_wait(bar(Smem::w_free + buf), ((q >> 1) - 1) & 1);
+                        pf.tick(3);
+                        uint8_t *whi = smem + Smem::w + buf * W_BUF + pslab, *wlo = whi + W_PART;
+                        uint4 *const wrow = wsave + (size_t)nbatches * (16 * 256) + tid;
+                        if (__all_sync(0xffffffffu, done)) {
+                            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                    for (int kg = 0; kg < GB / 8; ++kg) {
-                        *reinterpret_cast<uint4 *>(whi + kg * W_KSTR) = z;
-                        *reinterpret_cast<uint4 *>(wlo + kg * W_KSTR) = z;
-                    }
-                } else {
+                            for (int kg = 0; kg < GB / 8; ++kg) {
+                                *reinterpret_cast<uint4 *>(whi + kg * W_KSTR) = z;
+                                *reinterpret_cast<uint4 *>(wlo + kg * W_KSTR) = z;
+                                if (save) { wrow[(2 * kg) * 256] = z; wrow[(2 * kg + 1) * 256] = z; }
+                            }
+                        } else {
 #pragma unroll 1
-                    for (int j = 0; j < GB / 16; ++j) {
-                        float w[16];
+                            for (int j = 0; j < GB / 16; ++j) {
+                                float w[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float4 g0 = gbuf[16 * j + i], g1 = gbuf[GB + 16 * j + i];
-                            const float dx = g0.x - px, dy = g0.y - py;
-                            const float pw = dx * fmaf(g0.w, dx, g1.x * dy) + (g1.y * dy) * dy;  // -sigma*log2(e)
-                            const float alpha = fminf(kAlphaMax, g0.z * fast_ex2(pw));
-                            const float nT = fmaf(-alpha, T, T);
-                            const bool valid = !done && pw <= 0.0f && alpha >= kAlphaMin;
-                            const bool stop = valid && nT <= kTMin;
-                            const bool take = valid && !stop;
-                            w[i] = take ? alpha * T : 0.0f;
-                            T = take ? nT : T;
-                            done = done || stop;
-                        }
+                                for (int i = 0; i < 16; ++i) {
+                                    const float4 g0 = gbuf[16 * j + i], g1 = gbuf[GB + 16 * j + i];
+                                    const float dx = g0.x - px, dy = g0.y - py;
+                                    const float pw = dx * fmaf(g0.w, dx, g1.x * dy) + (g1.y * dy) * dy;  // -sigma*log2(e)
+                                    const float alpha = fminf(kAlphaMax, g0.z * fast_ex2(pw));
+                                    const float nT = fmaf(-alpha, T, T);
+                                    const bool valid = !done && pw <= 0.0f && alpha >= kAlphaMin;
+                                    const bool stop = valid && nT <= kTMin;
+                                    const bool take = valid && !stop;
+                                    w[i] = take ? alpha * T : 0.0f;
+                                    T = take ? nT : T;
+                                    done = done || stop;
+                                }
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 hi, lo;
-                            split_bf16x2(w[8 * h + 0], w[8 * h + 1], hi.x, lo.x);
-                            split_bf16x2(w[8 * h + 2], w[8 * h + 3], hi.y, lo.y);
-                            split_bf16x2(w[8 * h + 4], w[8 * h + 5], hi.z, lo.z);
-                            split_bf16x2(w[8 * h + 6], w[8 * h + 7], hi.w, lo.w);
-                            *reinterpret_cast<uint4 *>(whi + (2 * j + h) * W_KSTR) = hi;
-                            *reinterpret_cast<uint4 *>(wlo + (2 * j + h) * W_KSTR) = lo;
+                                for (int h = 0; h < 2; ++h) {
+                                    uint4 hi, lo;
+                                    split_bf16x2(w[8 * h + 0], w[8 * h + 1], hi.x, lo.x);
+                                    split_bf16x2(w[8 * h + 2], w[8 * h + 3], hi.y, lo.y);
+                                    split_bf16x2(w[8 * h + 4], w[8 * h + 5], hi.z, lo.z);
+                                    split_bf16x2(w[8 * h + 6], w[8 * h + 7], hi.w, lo.w);
+                                    *reinterpret_cast<uint4 *>(whi + (2 * j + h) * W_KSTR) = hi;
+                                    *reinterpret_cast<uint4 *>(wlo + (2 * j + h) * W_KSTR) = lo;
+                                    if (save) { wrow[(2 * (2 * j + h)) * 256] = hi; wrow[(2 * (2 * j + h) + 1) * 256] = lo; }
+                                }
+                            }
                         }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(Smem::w_full + buf));
+                        pf.tick(4);
+                        ++q;
+                        ++nbatches;
                     }
+                    if (chunk == 0) { nb0 = nbatches; T_end = T; }
+                } else {
+                    // ---------------- replay the recorded weights ----------------
+                    T = T_end;
+                    for (int bi = 0; bi < nb0; ++bi) {
+                        pf.tick(0);
+                        const int slot = e % ERING;
+                        wait_entry_slot(slot);
+                        pf.tick(2);
+                        if (tid < GB) ent[slot].gid[tid] = gsave[bi * GB + tid];
+                        if (tid == 0) {
+                            ent[slot].unit = unit;
+                            ent[slot].nb = min(GB, eend - (s + bi * GB));
+                            ent[slot].first = (bi == 0);
+                            ent[slot].nbatches = 0;
+                        }
+                        bar_sync_alu();
+                        if (tid == 0) mbar_arrive(bar(Smem::ent_full + slot));
+                        ++e;
+                        const uint4 *wrow = wsave + (size_t)bi * (16 * 256) + tid;
+                        uint4 v[8];  // two halves of 8 rows: 32 registers in flight
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = __ldcg(wrow + i * 256);
+                        const int buf = q & 1;
+                        pf.tick(0);
+                        if (q >= 2) mbar_wait(bar(Smem::w_free + buf), ((q >> 1) - 1) & 1);
+                        pf.tick(3);
+                        uint8_t *whi = smem + Smem::w + buf * W_BUF + pslab, *wlo = whi + W_PART;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int kg = 4 * half + k;
+                                *reinterpret_cast<uint4 *>(whi + kg * W_KSTR) = v[2 * k];
+                                *reinterpret_cast<uint4 *>(wlo + kg * W_KSTR) = v[2 * k + 1];
+                            }
+                            if (half == 0) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = __ldcg(wrow + (8 + i) * 256);
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(Smem::w_full + buf));
+                        pf.tick(4);
+                        ++q;
+                    }
+                    nbatches = nb0;
                 }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(Smem::w_full + buf));
-                pf.tick(4);
-                ++q;
-            }
-            // end-of-unit marker: final transmittances for the epilogue (background term), alpha straight out
-            {
-                const int slot = e % ERING;
-                wait_entry_slot(slot);
-                tfin[slot * kTilePix + tid] = T;
-                if (chunk == 0 && inside && a.alpha) a.alpha[(int64_t)yy * a.t.W + xx] = 1.0f - T;
-                if (tid == 0) {
-                    ent[slot].unit = unit;
-                    ent[slot].nb = 0;
-                    ent[slot].first = 0;
-                    ent[slot].nbatches = nbatches;
+                // end-of-unit marker: final transmittances for the epilogue (background term), alpha straight out
+                {
+                    const int slot = e % ERING;
+                    wait_entry_slot(slot);
+                    tfin[slot * kTilePix + tid] = T;
+                    if (chunk == 0 && inside && a.alpha) a.alpha[(int64_t)yy * a.t.W + xx] = 1.0f - T;
+                    if (tid == 0) {
+                        ent[slot].unit = unit;
+                        ent[slot].nb = 0;
+                        ent[slot].first = 0;
+                        ent[slot].nbatches = nbatches;
+                    }
+                    const bool last = chunk == a.nchunks - 1;
+                    if (last && tid == 0) s_unit[useq & 1] = next_tile;
+                    bar_sync_alu();
+                    if (tid == 0) mbar_arrive(bar(Smem::ent_full + slot));
+                    ++e;
+                    if (last) tile = s_unit[useq & 1];  // this slot is rewritten two tiles later, i.e. after another barrier
                 }
-                if (tid == 0) s_unit[useq & 1] = next_unit;
-                bar_sync_alu();
-                if (tid == 0) mbar_arrive(bar(Smem::ent_full + slot));
-                ++e;
-                unit = s_unit[useq & 1];  // this slot is rewritten two units later, i.e. after another barrier
             }
         }
         {
@@ -532,14 +611,21 @@ int launch_render_tc(const TileCtx &t, const float *colors, int64_t cstride, int
     a.d = d;
     a.dp = (d + MC - 1) / MC * MC;
     a.nchunks = (a.dp + MC - 1) / MC;
-    a.nunits = ntiles * a.nchunks;
+    a.ntiles = ntiles;
     a.unit_counter = (int *)t.scratch;
     static const int dbg = getenv("GWBP_RENDER_DEBUG") ? atoi(getenv("GWBP_RENDER_DEBUG")) : 0;
     a.debug = dbg;
     a.prof = (unsigned long long *)tc_trace_buffer();
     GWBP_CUDA_OK(cudaMemsetAsync(a.unit_counter, 0, sizeof(int), st));
     GWBP_CUDA_OK(cudaFuncSetAttribute(render_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    const int grid = a.nunits < kNumSMs ? a.nunits : kNumSMs;
+    const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
+    // weight cache in the dead part of the workspace: per CTA and batch 64 KB of weights + GB ids
+    constexpr size_t kBatchBytes = 16 * 256 * sizeof(uint4) + GB * sizeof(int);
+    size_t cap = (a.nchunks > 1 && t.dead && !(dbg & 8)) ? t.dead_bytes / ((size_t)grid * kBatchBytes) : 0;
+    if (cap > 64) cap = 64;
+    a.cap = (int)cap;
+    a.wsave = (uint4 *)t.dead;
+    a.gsave = (int *)((char *)t.dead + (size_t)grid * cap * 16 * 256 * sizeof(uint4));
     render_tc_kernel<<<grid, kThreads, Smem::total, st>>>(a);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
