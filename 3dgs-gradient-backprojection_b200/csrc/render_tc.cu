@@ -68,7 +68,8 @@ struct Smem {
     static constexpr int gbuf = x + XSTAGES * (int)X_STAGE;      // GB x 2 float4
     static constexpr int ent = gbuf + GB * 32;
     static constexpr int tfin = ent + ERING * (int)sizeof(Entry);  // ERING x 256 floats
-    static constexpr int misc = tfin + ERING * kTilePix * 4;     // work-queue slot
+    static constexpr int tend = tfin + ERING * kTilePix * 4;     // 256 floats: pass 0's final transmittances
+    static constexpr int misc = tend + kTilePix * 4;             // work-queue slot
     static constexpr int bars = misc + 16;
     static constexpr int ent_full = 0, ent_empty = ent_full + ERING, w_full = ent_empty + ERING, w_free = w_full + 2,
                          x_full = w_free + 2, x_empty = x_full + XSTAGES, acc_full = x_empty + XSTAGES,
@@ -135,6 +136,8 @@ struct RenderArgs {
     int debug;  // GWBP_RENDER_DEBUG (experiments only): 1 = no X loads, 2 = no render stores, 8 = no weight cache
 };
 
+// kCache = false compiles the recording / replay code away (single-chunk renders, or no scratch to cache in)
+template <bool kCache>
 __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -177,8 +180,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs
         // 16 core-matrix rows per batch to a per-CTA scratch in the dead part of the workspace (coalesced, L2
         // resident: 64 KB per batch); passes 1.. copy them back into the W buffers instead of recomputing them.  A
         // tile that walks more than `cap` batches falls back to regeneration for all its passes.
-        uint4 *const wsave = a.wsave + (size_t)blockIdx.x * a.cap * (16 * 256);
-        int *const gsave = a.gsave + (size_t)blockIdx.x * a.cap * GB;
+        // (the cache addresses and the per-pixel final transmittance of pass 0 are kept out of registers: the weight
+        // generation loop below needs all of them for its 16-wide instruction-level parallelism)
+        auto wrow_of = [&](int batch) { return a.wsave + ((size_t)blockIdx.x * a.cap + batch) * (16 * 256) + tid; };
+        auto gsave_of = [&](int batch) { return a.gsave + ((size_t)blockIdx.x * a.cap + batch) * GB; };
+        float *const tend = reinterpret_cast<float *>(smem + Smem::tend);
         if (tid == 0) s_unit[1] = atomicAdd(a.unit_counter, 1);
         bar_sync_alu();
         int tile = s_unit[1];
@@ -190,14 +196,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs
             const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
             const bool inside = yy < a.t.H && xx < a.t.W;
             const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
-            bool cached = a.cap > 0;
+            bool cached = kCache && a.cap > 0;
             int nb0 = 0;       // batches pass 0 walked
-            float T_end = 1.0f;
             for (int chunk = 0; chunk < a.nchunks; ++chunk) {
                 const int unit = tile * a.nchunks + chunk;
                 int nbatches = 0;
                 float T = 1.0f;
-                if (chunk == 0 || !cached) {
+                if (!kCache || chunk == 0 || !cached) {
                     // ---------------- generate (and, in pass 0, record) ----------------
                     bool done = !inside;
                     // Records are fetched two-deep: the list entry (Gaussian index) of batch b+2 and the record of
@@ -219,13 +224,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs
                         const int slot = e % ERING;
                         wait_entry_slot(slot);
                         pf.tick(2);
-                        if (chunk == 0 && nbatches >= a.cap) cached = false;  // uniform: the tile outgrew the cache
-                        const bool save = chunk == 0 && cached;
+                        if (kCache && chunk == 0 && nbatches >= a.cap) cached = false;  // uniform: the tile outgrew the cache
+                        const bool save = kCache && chunk == 0 && cached;
                         if (tid < GB) {
                             gbuf[tid] = make_float4(r0.x, r0.y, r0.z, -0.5f * kLog2e * r1.x);
                             gbuf[GB + tid] = make_float4(-kLog2e * r1.y, -0.5f * kLog2e * r1.z, 0.f, 0.f);
                             ent[slot].gid[tid] = __float_as_int(r0.w);
-                            if (save) gsave[nbatches * GB + tid] = __float_as_int(r0.w);
+                            if (save) gsave_of(nbatches)[tid] = __float_as_int(r0.w);
                         }
                         if (tid == 0) {
                             ent[slot].unit = unit;
@@ -250,14 +255,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs
                         if (q >= 2) mbar_wait(bar(Smem::w_free + buf), ((q >> 1) - 1) & 1);
                         pf.tick(3);
                         uint8_t *whi = smem + Smem::w + buf * W_BUF + pslab, *wlo = whi + W_PART;
-                        uint4 *const wrow = wsave + (size_t)nbatches * (16 * 256) + tid;
                         if (__all_sync(0xffffffffu, done)) {
                             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                             for (int kg = 0; kg < GB / 8; ++kg) {
                                 *reinterpret_cast<uint4 *>(whi + kg * W_KSTR) = z;
                                 *reinterpret_cast<uint4 *>(wlo + kg * W_KSTR) = z;
-                                if (save) { wrow[(2 * kg) * 256] = z; wrow[(2 * kg + 1) * 256] = z; }
+                                if (save) { uint4 *wrow = wrow_of(nbatches); wrow[(2 * kg) * 256] = z; wrow[(2 * kg + 1) * 256] = z; }
                             }
                         } else {
 #pragma unroll 1
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs
                                     split_bf16x2(w[8 * h + 6], w[8 * h + 7], hi.w, lo.w);
                                     *reinterpret_cast<uint4 *>(whi + (2 * j + h) * W_KSTR) = hi;
                                     *reinterpret_cast<uint4 *>(wlo + (2 * j + h) * W_KSTR) = lo;
-                                    if (save) { wrow[(2 * (2 * j + h)) * 256] = hi; wrow[(2 * (2 * j + h) + 1) * 256] = lo; }
+                                    if (save) { uint4 *wrow = wrow_of(nbatches); wrow[(2 * (2 * j + h)) * 256] = hi; wrow[(2 * (2 * j + h) + 1) * 256] = lo; }
                                 }
                             }
                         }
@@ -297,16 +301,16 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs
                         ++q;
                         ++nbatches;
                     }
-                    if (chunk == 0) { nb0 = nbatches; T_end = T; }
-                } else {
+                    if (kCache && chunk == 0) { nb0 = nbatches; tend[tid] = T; }
+                } else if (kCache) {
                     // ---------------- replay the recorded weights ----------------
-                    T = T_end;
+                    T = tend[tid];
                     for (int bi = 0; bi < nb0; ++bi) {
                         pf.tick(0);
                         const int slot = e % ERING;
                         wait_entry_slot(slot);
                         pf.tick(2);
-                        if (tid < GB) ent[slot].gid[tid] = gsave[bi * GB + tid];
+                        if (tid < GB) ent[slot].gid[tid] = gsave_of(bi)[tid];
                         if (tid == 0) {
                             ent[slot].unit = unit;
                             ent[slot].nb = min(GB, eend - (s + bi * GB));
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs
                         bar_sync_alu();
                         if (tid == 0) mbar_arrive(bar(Smem::ent_full + slot));
                         ++e;
-                        const uint4 *wrow = wsave + (size_t)bi * (16 * 256) + tid;
+                        const uint4 *wrow = wrow_of(bi);
                         uint4 v[8];  // two halves of 8 rows: 32 registers in flight
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = __ldcg(wrow + i * 256);
@@ -617,7 +621,8 @@ int launch_render_tc(const TileCtx &t, const float *colors, int64_t cstride, int
     a.debug = dbg;
     a.prof = (unsigned long long *)tc_trace_buffer();
     GWBP_CUDA_OK(cudaMemsetAsync(a.unit_counter, 0, sizeof(int), st));
-    GWBP_CUDA_OK(cudaFuncSetAttribute(render_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    GWBP_CUDA_OK(cudaFuncSetAttribute(render_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    GWBP_CUDA_OK(cudaFuncSetAttribute(render_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
     const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
     // weight cache in the dead part of the workspace: per CTA and batch 64 KB of weights + GB ids
     constexpr size_t kBatchBytes = 16 * 256 * sizeof(uint4) + GB * sizeof(int);
@@ -626,7 +631,10 @@ int launch_render_tc(const TileCtx &t, const float *colors, int64_t cstride, int
     a.cap = (int)cap;
     a.wsave = (uint4 *)t.dead;
     a.gsave = (int *)((char *)t.dead + (size_t)grid * cap * 16 * 256 * sizeof(uint4));
-    render_tc_kernel<<<grid, kThreads, Smem::total, st>>>(a);
+    if (a.cap > 0)
+        render_tc_kernel<true><<<grid, kThreads, Smem::total, st>>>(a);
+    else
+        render_tc_kernel<false><<<grid, kThreads, Smem::total, st>>>(a);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
