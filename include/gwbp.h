@@ -148,7 +148,9 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam_host, 
  * of `render` and `alpha` is written (no pre-zeroing needed).  kernel: GWBP_KERNEL_SIMT = fp32 CUDA cores,
  * weights regenerated per 32-channel chunk like gsplat; GWBP_KERNEL_TC = tcgen05 split-bf16 contraction, weights
  * generated once per 256 channels (needs 32 <= d, d % 4 == 0, 16-byte aligned rows); AUTO picks TC when it can
- * and d >= 64. */
+ * and d >= 64.  The TC kernel uses the workspace regions that are dead once a view is prepared (counts, scans,
+ * unpacked records, hit masks) as scratch for its weight cache: `ws` is const only as far as the prepared view
+ * (records, sorted lists, offsets) is concerned, and two renders of one workspace must not run concurrently. */
 int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam_host, const void *ws,
                      const gwbp_view_info *info_host, const float *colors, int64_t color_stride, int32_t d,
                      const float *background, float *render, float *alpha, int32_t kernel, void *stream);
