@@ -345,6 +345,43 @@ def test_edge_cases_gpu(gwbp):
                            torch.eye(4)[None], torch.eye(3)[None], 8, 8)
 
 
+def test_known_answers_gpu(gwbp):
+    """The hand-derived known-answer cases of tests/test_oracle.py::test_known_answers_from_published_semantics,
+    through the C ABI: radius 7 and a 2 x 2 tile rectangle, alpha = o at the centre pixel, front-to-back
+    compositing 1 - (1 - 0.5)(1 - 0.8), the 0.999 clamp + T <= 1e-4 stop rule, and the alpha < 1/255 skip."""
+    W = H = 32
+    K = np.array([[32, 0, 16.5], [0, 32, 16.5], [0, 0, 1]], np.float32)
+    vm = np.eye(4, dtype=np.float32)
+
+    def run(opacities, depths):
+        n = len(opacities)
+        z = np.asarray(depths, np.float32)
+        means = np.stack([np.zeros(n, np.float32), np.zeros(n, np.float32), z], 1)
+        quats = np.tile(np.array([[1, 0, 0, 0]], np.float32), (n, 1))
+        scales = (0.25 * z / 4.0)[:, None].repeat(3, 1).astype(np.float32)
+        bp = gwbp.BackProjector(_dev(means), _dev(quats), _dev(scales), _dev(np.asarray(opacities, np.float32)), 1,
+                                kernel="simt", tile_cull=False)
+        view = bp.add_view(vm, K, W, H, torch.ones(H, W, 1, device="cuda"))
+        _, alpha = view.render(torch.ones(n, 1, device="cuda"))
+        return view, alpha.cpu().numpy(), (bp.den - 1e-12).cpu().numpy()
+
+    view, a, den = run([0.5], [4.0])
+    m = view.meta()
+    assert m["radii"].cpu().tolist() == [7] and view.n_isects == 4
+    assert np.allclose(m["means2d"].cpu().numpy()[0], [16.5, 16.5], atol=1e-6)
+    assert np.allclose(m["conics"].cpu().numpy()[0], [1 / 4.3, 0.0, 1 / 4.3], atol=1e-6)
+    assert sorted((m["isect_ids"] >> 32).cpu().tolist()) == [0, 1, 2, 3]
+    assert abs(a[16, 16] - 0.5) < 1e-6 and abs(a[16, 17] - 0.5 * np.exp(-0.5 / 4.3)) < 1e-6
+    assert abs(den[0] - 0.5 * 2 * np.pi * 4.3 * (1 - 1 / 127.5)) < 0.02 * den[0]
+    _, a, _ = run([0.8, 0.5], [5.0, 4.0])
+    assert abs(a[16, 16] - 0.9) < 1e-6
+    _, a, _ = run([1.0, 1.0, 1.0], [4.0, 5.0, 6.0])
+    assert abs(a[16, 16] - 0.999) < 1e-6
+    _, a, den = run([0.00393, 0.00391], [4.0, 5.0])
+    assert abs(den[0] - 0.00393) < 1e-7 and den[1] == 0.0
+    assert abs(a[16, 16] - 0.00393) < 1e-7 and a[16, 17] == 0.0
+
+
 def test_full_size_properties_config_G_shape(gwbp):
     """Size-independent properties at the benchmark's image size (1297x840, D=512) on a lighter
     scene: sum(den_v) == sum(alpha_v), constant features -> num == den*c, adjointness."""
