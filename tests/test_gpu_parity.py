@@ -373,6 +373,14 @@ def test_known_answers_gpu(gwbp):
     assert sorted((m["isect_ids"] >> 32).cpu().tolist()) == [0, 1, 2, 3]
     assert abs(a[16, 16] - 0.5) < 1e-6 and abs(a[16, 17] - 0.5 * np.exp(-0.5 / 4.3)) < 1e-6
     assert abs(den[0] - 0.5 * 2 * np.pi * 4.3 * (1 - 1 / 127.5)) < 0.02 * den[0]
+    # off-axis beyond the frustum clamp (lim_x+ = 0.634375): radius 29, conic from the clamped Jacobian
+    bp = gwbp.BackProjector(_dev(np.array([[4.0, 0.0, 4.0]], np.float32)), _dev(np.array([[1, 0, 0, 0]], np.float32)),
+                            _dev(np.ones((1, 3), np.float32)), _dev(np.array([0.5], np.float32)), 1, kernel="simt",
+                            tile_cull=False)
+    m = bp.add_view(vm, K, W, H, torch.ones(H, W, 1, device="cuda")).meta()
+    assert m["radii"].cpu().tolist() == [29]
+    assert np.allclose(m["conics"].cpu().numpy()[0], [1 / (64.0 * (1.0 + 0.634375 ** 2) + 0.3), 0.0, 1 / 64.3],
+                       rtol=2e-6, atol=1e-9)
     _, a, _ = run([0.8, 0.5], [5.0, 4.0])
     assert abs(a[16, 16] - 0.9) < 1e-6
     _, a, _ = run([1.0, 1.0, 1.0], [4.0, 5.0, 6.0])

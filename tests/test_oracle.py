@@ -231,6 +231,17 @@ def test_known_answers_from_published_semantics(noracle, coracle):
     e = cv.export()
     assert e["radii"].tolist() == [7] and np.array_equal(np.sort(e["isect_ids"]), np.sort(isect["isect_ids"]))
 
+    # -- off-axis Gaussian beyond the frustum clamp: x/z = 1 > lim_x+ = (W - cx)/fx + 0.3 * (0.5 W/fx) = 0.634375, so the
+    #    Jacobian uses tx = 0.634375 z: cov2d_xx = s^2 (fx/z)^2 (1 + 0.634375^2) + 0.3 = 90.0556, cov2d_yy = 64.3,
+    #    radius = ceil(3 sqrt(90.0556)) = 29 (34 without the clamp); mean2d itself is not clamped: 32 * 1 + 16.5
+    m1 = np.array([[4.0, 0.0, 4.0]], np.float32)
+    p1, _ = noracle.view_geometry(m1, quats, np.ones((1, 3), np.float32), vm, K, W, H)
+    xx = 64.0 * (1.0 + 0.634375 ** 2) + 0.3
+    assert p1["radii"].tolist() == [29] and np.allclose(p1["means2d"][0], [48.5, 16.5], atol=1e-5)
+    assert np.allclose(p1["conics"][0], [1 / xx, 0.0, 1 / 64.3], rtol=2e-6, atol=1e-9)
+    c1 = coracle.View(m1, quats, np.ones((1, 3), np.float32), opac, vm, K, W, H).export()
+    assert c1["radii"].tolist() == [29]
+
     def alpha_c(opacities, depths=None):
         m, q, s, o, v, k = _kat_scene(opacities, depths)
         ones = np.ones((len(opacities), 1), np.float32)
