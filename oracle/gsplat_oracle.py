@@ -17,6 +17,12 @@ and anchors on the reference's own call sites and driver math:
   * 3-D mask ............................... segment.py:52-58
   * 2-D mask ............................... segment.py:209-224
 
+In the absence of reference-owned vectors the restatement is checked against known answers worked
+out by hand from that published arithmetic (tests/test_oracle.py::
+test_known_answers_from_published_semantics: EWA blur, radius, tile rectangle, alpha clamp, the
+1/255 skip, the 1e-4 stop rule, the frustum clamp of the Jacobian), against its C twin
+(bit-exact integer stages) and against the algebraic invariants the reference relies on.
+
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module.  The product path never does.
 

@@ -8,7 +8,7 @@
  *   rasterization(...) call sites ........ backproject.py:89-100,115-125,133-143
  *   num += grad, den += grad[:,0] ........ backproject.py:127-131,145-151
  *   forward feature render ............... segment.py:209-220
- * It is validated against gsplat_oracle.py (tests/test_oracle.py) and is the timed
+ * It is validated against hand-derived known answers and against gsplat_oracle.py (tests/test_oracle.py) and is the timed
  * "cpu_baseline" (kind "port") of bench.py.  Only tests/, __graft_entry__.smoke() and bench.py
  * may load it.
  *
