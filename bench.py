@@ -362,6 +362,11 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     import gwbp
 
+    if not os.path.exists(gwbp._lib.LIB_PATH) and int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        # harness convenience only (the library itself never builds or falls back): a checkout without built artefacts
+        import __graft_entry__
+
+        __graft_entry__.build()
     cfg = dict(gwbp.scene.CONFIGS[args.config])
     if args.d:
         cfg["d"] = args.d
