@@ -367,6 +367,10 @@ def main():
         import __graft_entry__
 
         __graft_entry__.build()
+    for _ in range(600):  # the other ranks of a torchrun launch wait for rank 0's build
+        if os.path.exists(gwbp._lib.LIB_PATH):
+            break
+        time.sleep(0.5)
     cfg = dict(gwbp.scene.CONFIGS[args.config])
     if args.d:
         cfg["d"] = args.d
