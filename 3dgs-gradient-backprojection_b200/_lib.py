@@ -63,6 +63,8 @@ SIGNATURES = {
     "gwbp_ratio_accumulate": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.c_void_p, C.POINTER(ViewInfo),
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                         C.c_float, C.c_void_p]),
+    "gwbp_sh_colors": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "gwbp_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "gwbp_mask3d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                               C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -81,8 +81,8 @@ class BackProjector:
         """feats_low: the ENCODER-resolution map [h,w,D] (any strides, e.g. `net_out[0].permute(1,2,0)`).
         Equivalent to add_view(interpolate(feats_low, (H,W), mode)) (backproject.py:110-113 / :245-249) but
         the upsample is fused into the feature re-layout pass and the [H,W,D] tensor is never built."""
-        assert feats_low.dim() == 3 and feats_low.shape[-1] == self.d and feats_low.dtype == torch.float32
         assert mode in ("bilinear", "nearest"), mode
+        self._check_map(feats_low, make_camera(viewmat, K, width, height, **cam_kw), True)
         if not fpack_bytes(int(width), int(height), self.d) or self.kernel == L.KERNEL_SIMT:
             up = torch.nn.functional.interpolate(feats_low.permute(2, 0, 1)[None], size=(int(height), int(width)),
                                                  mode=mode)[0].permute(1, 2, 0)
@@ -97,7 +97,13 @@ class BackProjector:
         copy stream into one of two device staging buffers while the PREVIOUS view is being back-projected, so the
         PCIe transfer and the kernels overlap; the view is accumulated at the next add_view_host()/flush() (every
         accessor of the accumulators flushes)."""
-        assert not feats_host.is_cuda and feats_host.dim() == 3 and feats_host.shape[0] == self.d
+        assert not feats_host.is_cuda and feats_host.dim() == 3 and feats_host.shape[0] == self.d, \
+            f"host map must be a CPU tensor [D={self.d}, h, w], got {tuple(feats_host.shape)} on {feats_host.device}"
+        assert feats_host.dtype == torch.float32, f"host map must be float32, got {feats_host.dtype}"
+        assert lowres_mode in (None, "bilinear", "nearest"), lowres_mode
+        if lowres_mode is None:
+            assert tuple(feats_host.shape[1:]) == (int(height), int(width)), \
+                f"host map must be [D, H={int(height)}, W={int(width)}], got {tuple(feats_host.shape)}"
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         if self._stage is None:
@@ -132,8 +138,27 @@ class BackProjector:
         if prev is not None:
             self._run_pending(prev)
 
+    def _check_map(self, feats: torch.Tensor, cam, lowres: bool) -> None:
+        """The packed (tcgen05) path hands raw pointers and strides to the C ABI, so everything View.backproject()
+        would have asserted is checked HERE, before any kernel sees the tensor: a half-precision (autocast) encoder
+        output, a CPU tensor or a wrong-size map must raise, not be reinterpreted as fp32 [H,W,D]."""
+        if not isinstance(feats, torch.Tensor) or not feats.is_cuda:
+            raise RuntimeError("feature map must be a CUDA tensor (CUDA is required; there is no CPU path) -- got "
+                               f"{getattr(feats, 'device', type(feats))}; use add_view_host() for host-resident maps")
+        if feats.device != self.device:
+            raise RuntimeError(f"feature map lives on {feats.device}, the accumulators on {self.device}")
+        assert feats.dtype == torch.float32, f"feature map must be float32, got {feats.dtype} (cast it: .float())"
+        assert feats.dim() == 3 and feats.shape[2] == self.d, \
+            f"feature map must be [h,w,D={self.d}], got {tuple(feats.shape)}"
+        if lowres:
+            assert feats.shape[0] >= 1 and feats.shape[1] >= 1, tuple(feats.shape)
+        else:
+            assert feats.shape[0] == cam.height and feats.shape[1] == cam.width, \
+                f"feature map must be [H={cam.height}, W={cam.width}, D], got {tuple(feats.shape)}"
+
     def _add(self, viewmat, K, width, height, feats, lowres_mode, cam_kw) -> View:
         cam = make_camera(viewmat, K, width, height, **cam_kw)
+        self._check_map(feats, cam, lowres_mode is not None)
         cur = torch.cuda.current_stream(self.device)
         fp, kernel = None, self.kernel
         if self.kernel != L.KERNEL_SIMT:

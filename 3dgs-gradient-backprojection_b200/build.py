@@ -26,6 +26,7 @@ SOURCES = {
     "binning.cu": [],
     "composite_simt.cu": [],
     "finalize.cu": [],
+    "sh.cu": [],
     "backproject_tc.cu": [],
     "render_tc.cu": [],
 }

@@ -17,6 +17,18 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int num_sms() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev] = v;
+    }
+    return cache[dev];
+}
+
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 static int tile_bits_for(int n_tiles) {
@@ -251,6 +263,15 @@ int gwbp_ratio_accumulate(const gwbp_scene *scene, const gwbp_camera *cam, const
     WsDev w = ws_view(const_cast<void *>(ws), L);
     return launch_ratio_accumulate(w.grec, info->n_vis, num_v, den_v, acc, den_acc, d, num_scale, den_scale, eps,
                                    (cudaStream_t)stream);
+}
+
+int gwbp_sh_colors(int64_t n, int32_t degree, const float *means, const float *coeffs, int64_t sN, int64_t sK, int64_t sC,
+                   const float *cam_pos_host, float *out, void *stream) {
+    GWBP_REQUIRE(n >= 0, "sh_colors: n must be >= 0");
+    GWBP_REQUIRE(degree >= 0 && degree <= 4, "sh_colors: sh_degree must be 0..4 (got %d)", degree);
+    if (n == 0) return 0;
+    GWBP_REQUIRE(means && coeffs && cam_pos_host && out, "sh_colors: NULL pointer");
+    return launch_sh_colors(n, degree, means, coeffs, sN, sK, sC, cam_pos_host, out, (cudaStream_t)stream);
 }
 
 int gwbp_finalize(const float *num, const float *den, float *out, int64_t n, int32_t d, void *stream) {

@@ -54,7 +54,6 @@ constexpr int EPI_ROWS = 16;                             // rows staged per roun
 constexpr int EPI_PITCH = EPI_COLS * 4 + 16;             // padded row pitch (144 B): conflict-free 16-byte stores
 
 constexpr int kEpiWarp0 = 8, kProducerWarp = 13, kMmaWarp = 14, kThreads = 480;
-constexpr float kLog2e = 1.4426950408889634f;
 
 struct RowInfo {
     int gid[MB];
@@ -93,11 +92,6 @@ __device__ __forceinline__ int bar_red_popc_alu(bool pred) {
         : "r"((int)pred)
         : "memory");
     return cnt;
-}
-__device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2, what __expf lowers to after the log2(e) scale
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
 }
 __device__ __forceinline__ void bar_sync_alu() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -187,6 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             const int s = a.t.offsets[tile], e = a.t.offsets[tile + 1];
             const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
             const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
+            const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
             bool done = !(yy < a.t.H && xx < a.t.W);
             float T = 1.0f;
             // prefetch the first batch's record for row `tid` (threads 0..127)
@@ -202,9 +197,12 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 const int slot = q % RING;
                 if (q >= RING) mbar_wait(bar(Smem::rows_free + slot), ((q / RING) - 1) & 1);
                 if (tid < MB) {
-                    // exponent pre-scaled for ex2: alpha = op * 2^(a dx^2 + b dx dy + c dy^2)
-                    gbuf[tid] = make_float4(r0.x, r0.y, r0.z, -0.5f * kLog2e * r1.x);
-                    gbuf[MB + tid] = make_float4(-kLog2e * r1.y, -0.5f * kLog2e * r1.z, 0.f, 0.f);
+                    // records of Gaussians 2k, 2k+1 interleaved so that the ALU loop loads packed operand pairs:
+                    // float4 (gx0,gx1,gy0,gy1), (hxx0,hxx1,cxy0,cxy1), (hyy0,hyy1,op0,op1), h** = half conic (exact)
+                    float *gp = reinterpret_cast<float *>(gbuf + 3 * (tid >> 1)) + (tid & 1);
+                    gp[0] = r0.x; gp[2] = r0.y;
+                    gp[4] = 0.5f * r1.x; gp[6] = r1.y;
+                    gp[8] = 0.5f * r1.z; gp[10] = r0.z;
                     rows[slot].gid[tid] = __float_as_int(r0.w);
                     rows[slot].den[tid] = 0.0f;
                     if (tid == 0) rows[slot].exit_flag = 0;
@@ -241,18 +239,28 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                         // only the T update is a serial chain
                         float w[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float4 g0 = gbuf[16 * j + i], g1 = gbuf[MB + 16 * j + i];
-                            const float dx = g0.x - px, dy = g0.y - py;
-                            const float pw = dx * fmaf(g0.w, dx, g1.x * dy) + (g1.y * dy) * dy;  // -sigma*log2(e)
-                            const float alpha = fminf(kAlphaMax, g0.z * fast_ex2(pw));
-                            const float nT = fmaf(-alpha, T, T);
-                            const bool valid = !done && pw <= 0.0f && alpha >= kAlphaMin;
-                            const bool stop = valid && nT <= kTMin;
-                            const bool take = valid && !stop;
-                            w[i] = take ? alpha * T : 0.0f;
-                            T = take ? nT : T;
-                            done = done || stop;
+                        for (int i2 = 0; i2 < 8; ++i2) {
+                            // sigma of two Gaussians at once on the packed fp32 pipe (FADD2/FMUL2/FFMA2): same
+                            // roundings as the scalar pair_sigma() of the CUDA-core kernels, half the instructions
+                            const float4 q0 = gbuf[3 * (8 * j + i2)], q1 = gbuf[3 * (8 * j + i2) + 1],
+                                         q2 = gbuf[3 * (8 * j + i2) + 2];
+                            const float2 dx = add2_rn(make_float2(q0.x, q0.y), npx);
+                            const float2 dy = add2_rn(make_float2(q0.z, q0.w), npy);
+                            const float2 sg = pair_sigma2(dx, dy, make_float2(q1.x, q1.y), make_float2(q1.z, q1.w),
+                                                          make_float2(q2.x, q2.y));
+                            const float2 ex = mul2_rn(sg, make_float2(-kLog2e, -kLog2e));
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const float sigma = h ? sg.y : sg.x;
+                                const float alpha = fminf(kAlphaMax, __fmul_rn(h ? q2.w : q2.z, ex2_approx(h ? ex.y : ex.x)));
+                                const float nT = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                                const bool valid = !done && sigma >= 0.0f && alpha >= kAlphaMin;
+                                const bool stop = valid && nT <= kTMin;
+                                const bool take = valid && !stop;
+                                w[2 * i2 + h] = take ? __fmul_rn(alpha, T) : 0.0f;
+                                T = take ? nT : T;
+                                done = done || stop;
+                            }
                         }
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
@@ -805,15 +813,19 @@ int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t 
     a.d = d; a.dp = dp; a.nchunks = nchunks; a.nunits = ntiles;
     a.unit_counter = (int *)t.scratch;
     a.stats = stats;
+    a.debug = 0;
+    a.band = kBand;
+#ifdef GWBP_EXPERIMENTS  // result-altering timing knobs exist only in experiment builds (never in lib/libgwbp.so)
     static const int dbg = getenv("GWBP_TC_DEBUG") ? atoi(getenv("GWBP_TC_DEBUG")) : 0;
     a.debug = dbg;
     static const int band_env = getenv("GWBP_TC_BAND") ? atoi(getenv("GWBP_TC_BAND")) : kBand;
     a.band = band_env > 0 ? band_env : kBand;
+#endif
     GWBP_CUDA_OK(cudaMemsetAsync(a.unit_counter, 0, sizeof(int), st));
     // per-device function attribute: set on every launch (microseconds) so a process that drives several
     // devices never launches with the default 48 KB limit
     GWBP_CUDA_OK(cudaFuncSetAttribute(bp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    const int grid = a.nunits < kNumSMs ? a.nunits : kNumSMs;
+    const int grid = a.nunits < num_sms() ? a.nunits : num_sms();
     bp_tc_kernel<<<grid, kThreads, Smem::total, st>>>(a);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;

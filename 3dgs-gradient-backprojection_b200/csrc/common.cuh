@@ -13,7 +13,9 @@ constexpr int kTilePix = kTile * kTile;
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kAlphaMax = 0.999f;
 constexpr float kTMin = 1e-4f;
-constexpr int kNumSMs = 148;  // B200
+// SMs of the CURRENT device (cudaDevAttrMultiProcessorCount, cached per device; 148 on a full B200): persistent
+// grids and per-CTA scratch partitions are sized with it, so MIG slices / other sm_100a SKUs are not mis-subscribed.
+int num_sms();
 
 // thread-local error string behind gwbp_last_error()
 void set_error(const char *fmt, ...);
@@ -122,6 +124,8 @@ int launch_render_pixels(const TileCtx &t, const float *colors, int64_t cstride,
                          const int *xy, int k, float *out, float *alpha, cudaStream_t st);
 int launch_ratio_accumulate(const float4 *grec, int64_t n_vis, float *num_v, float *den_v, float *acc, float *den_acc,
                             int d, float num_scale, float den_scale, float eps, cudaStream_t st);
+int launch_sh_colors(int64_t n, int degree, const float *means, const float *coeffs, int64_t sN, int64_t sK, int64_t sC,
+                     const float *cam_pos_host, float *out, cudaStream_t st);
 int launch_finalize(const float *num, const float *den, float *out, int64_t n, int d, cudaStream_t st);
 int launch_mask(const float *x, int64_t rows, int d, const float *text, int p, int npos, float thr,
                 int use_thr, uint8_t *mask, float *score, cudaStream_t st);
@@ -143,20 +147,71 @@ int launch_render_tc(const TileCtx &t, const float *colors, int64_t cstride, int
                      float *alpha, cudaStream_t st);
 
 // ---- device helpers ------------------------------------------------------------------------
-// One Gaussian against one pixel, gsplat rasterize_to_pixels_fwd semantics.
+// One (pixel, Gaussian) pair, gsplat-1.4.0 rasterize_to_pixels_{fwd,bwd} arithmetic:
+//     sigma = 0.5f * (conic.x*dx*dx + conic.z*dy*dy) + conic.y*dx*dy;   alpha = min(0.999f, opac * __expf(-sigma));
+// The roundings are spelled out (the contraction nvcc applies to that expression under its default
+// -fmad=true, and __expf(x) = ex2.approx(x * log2(e))) so that EVERY kernel of this library -- CUDA-core and
+// tcgen05, forward and backward -- evaluates a pair bit-identically and a pair sitting on a threshold
+// (alpha = 1/255, T(1-alpha) = 1e-4) falls on the same side everywhere.
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// hxx = 0.5f*conic.x, hyy = 0.5f*conic.z: halving is exact, so fma(hxx*dx, dx, (hyy*dy)*dy) == 0.5f * s bit for bit.
+// The cross term is folded into the last FMA: sigma = fma(cxy*dx, dy, 0.5f*s) (one of the two contractions a
+// compiler may pick for the expression above; ptxas picks it for packed operands whatever the PTX says, see below).
+__device__ __forceinline__ float pair_sigma(float dx, float dy, float hxx, float cxy, float hyy) {
+    const float s = __fmaf_rn(__fmul_rn(hxx, dx), dx, __fmul_rn(__fmul_rn(hyy, dy), dy));
+    return __fmaf_rn(__fmul_rn(cxy, dx), dy, s);
+}
+__device__ __forceinline__ float pair_alpha(float op, float sigma) {
+    return fminf(kAlphaMax, __fmul_rn(op, ex2_approx(__fmul_rn(sigma, -kLog2e))));
+}
+// Packed fp32 (sm_100 FADD2 / FMUL2 / FFMA2): two pairs per instruction, inline PTX with explicit .rn.
+// NB: ptxas 12.9 fuses a mul.rn.f32x2 feeding an add.rn.f32x2 into ONE FFMA2 (even under -fmad=false; the scalar
+// .rn forms are left alone), so pair_sigma() is defined with that FMA on the scalar side too and no packed
+// mul->add pair is ever written here.
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rr, ra, rb;\n\tmov.b64 {%0, %1}, rr;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rr, ra, rb;\n\tmov.b64 {%0, %1}, rr;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 fma2_rn(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rr, ra, rb, rc;\n\tmov.b64 {%0, %1}, rr;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+// pair_sigma() for two Gaussians at once: identical roundings, half the instructions
+__device__ __forceinline__ float2 pair_sigma2(float2 dx, float2 dy, float2 hxx, float2 cxy, float2 hyy) {
+    const float2 s = fma2_rn(mul2_rn(hxx, dx), dx, mul2_rn(mul2_rn(hyy, dy), dy));
+    return fma2_rn(mul2_rn(cxy, dx), dy, s);
+}
 // Returns the weight alpha*T (0 if skipped) and updates T / done.
 __device__ __forceinline__ float composite_step(float gx, float gy, float op, float cxx, float cxy,
                                                 float cyy, float px, float py, float &T, bool &done) {
     const float dx = gx - px, dy = gy - py;
-    const float sigma = 0.5f * (cxx * dx * dx + cyy * dy * dy) + cxy * dx * dy;
-    const float alpha = fminf(kAlphaMax, op * __expf(-sigma));
+    const float sigma = pair_sigma(dx, dy, 0.5f * cxx, cxy, 0.5f * cyy);
+    const float alpha = pair_alpha(op, sigma);
     float w = 0.0f;
     if (!done && sigma >= 0.0f && alpha >= kAlphaMin) {
-        const float nT = T * (1.0f - alpha);
+        const float nT = __fmul_rn(T, __fsub_rn(1.0f, alpha));
         if (nT <= kTMin) {
             done = true;
         } else {
-            w = alpha * T;
+            w = __fmul_rn(alpha, T);
             T = nT;
         }
     }

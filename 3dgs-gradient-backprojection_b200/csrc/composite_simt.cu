@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(256) render_pixels_kernel(TileCtx t, const flo
                 const int id = t.flatten[b + tid];
                 const float4 g0 = t.grec[2 * (int64_t)id], g1 = t.grec[2 * (int64_t)id + 1];
                 const float dx = g0.x - px, dy = g0.y - py;
-                const float sigma = 0.5f * (g1.x * dx * dx + g1.z * dy * dy) + g1.y * dx * dy;
-                const float a = fminf(kAlphaMax, g0.z * __expf(-sigma));
+                const float sigma = pair_sigma(dx, dy, 0.5f * g1.x, g1.y, 0.5f * g1.z);
+                const float a = pair_alpha(g0.z, sigma);
                 s_a[tid] = (sigma >= 0.0f && a >= kAlphaMin) ? a : 0.0f;
                 s_gid[tid] = __float_as_int(g0.w);
             }
@@ -249,9 +249,9 @@ __global__ void __launch_bounds__(256) render_pixels_kernel(TileCtx t, const flo
                     float w = 0.0f;
                     const float a = s_a[k];
                     if (!done && a > 0.0f) {
-                        const float nT = T * (1.0f - a);
+                        const float nT = __fmul_rn(T, __fsub_rn(1.0f, a));
                         if (nT <= kTMin) done = true;
-                        else { w = a * T; T = nT; }
+                        else { w = __fmul_rn(a, T); T = nT; }
                     }
                     s_w[k] = w;
                     if (extra && w > 0.0f) ex += w * extra[s_gid[k]];

@@ -251,7 +251,7 @@ int launch_mask(const float *x, int64_t rows, int d, const float *text, int p, i
         GWBP_CUDA_OK(cudaFuncSetAttribute(mask_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     int64_t blocks = (rows + 7) / 8;
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
     const bool vec = (d & 3) == 0 && ((uintptr_t)x & 15) == 0;
     if (vec && d <= 512)
         mask_kernel<4><<<(unsigned)blocks, 256, smem, st>>>(x, rows, d, text, p, npos, thr, use_thr, mask, score);

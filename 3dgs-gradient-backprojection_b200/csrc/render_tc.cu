@@ -52,7 +52,6 @@ constexpr uint32_t X_PART = (KST / 8) * X_KSTR;    // 4 KB per hi / lo part
 constexpr uint32_t X_STAGE = 2 * X_PART;
 
 constexpr int kLoadWarp0 = 8, kEpiWarp0 = 12, kMmaWarp = 16, kThreads = 17 * 32;
-constexpr float kLog2e = 1.4426950408889634f;
 
 struct Entry {
     int unit;      // -1 = exit
@@ -91,11 +90,6 @@ __device__ __forceinline__ int bar_red_popc_alu(bool pred) {
     return cnt;
 }
 __device__ __forceinline__ void bar_sync_alu() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ float fast_ex2(float v) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v));
-    return y;
-}
 
 // Debug cycle accounting: tick(cat) charges the time since the previous tick to category `cat`.
 struct Prof {
@@ -196,6 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs
             const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
             const bool inside = yy < a.t.H && xx < a.t.W;
             const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
+            const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
             bool cached = kCache && a.cap > 0;
             int nb0 = 0;       // batches pass 0 walked
             for (int chunk = 0; chunk < a.nchunks; ++chunk) {
@@ -227,8 +222,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs
                         if (kCache && chunk == 0 && nbatches >= a.cap) cached = false;  // uniform: the tile outgrew the cache
                         const bool save = kCache && chunk == 0 && cached;
                         if (tid < GB) {
-                            gbuf[tid] = make_float4(r0.x, r0.y, r0.z, -0.5f * kLog2e * r1.x);
-                            gbuf[GB + tid] = make_float4(-kLog2e * r1.y, -0.5f * kLog2e * r1.z, 0.f, 0.f);
+                            // pair-interleaved records (see bp_tc_kernel): (gx0,gx1,gy0,gy1), (hxx0,hxx1,cxy0,cxy1), (hyy0,hyy1,op0,op1)
+                            float *gp = reinterpret_cast<float *>(gbuf + 3 * (tid >> 1)) + (tid & 1);
+                            gp[0] = r0.x; gp[2] = r0.y;
+                            gp[4] = 0.5f * r1.x; gp[6] = r1.y;
+                            gp[8] = 0.5f * r1.z; gp[10] = r0.z;
                             ent[slot].gid[tid] = __float_as_int(r0.w);
                             if (save) gsave_of(nbatches)[tid] = __float_as_int(r0.w);
                         }
@@ -268,18 +266,27 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_kernel(const RenderArgs
                             for (int j = 0; j < GB / 16; ++j) {
                                 float w[16];
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) {
-                                    const float4 g0 = gbuf[16 * j + i], g1 = gbuf[GB + 16 * j + i];
-                                    const float dx = g0.x - px, dy = g0.y - py;
-                                    const float pw = dx * fmaf(g0.w, dx, g1.x * dy) + (g1.y * dy) * dy;  // -sigma*log2(e)
-                                    const float alpha = fminf(kAlphaMax, g0.z * fast_ex2(pw));
-                                    const float nT = fmaf(-alpha, T, T);
-                                    const bool valid = !done && pw <= 0.0f && alpha >= kAlphaMin;
-                                    const bool stop = valid && nT <= kTMin;
-                                    const bool take = valid && !stop;
-                                    w[i] = take ? alpha * T : 0.0f;
-                                    T = take ? nT : T;
-                                    done = done || stop;
+                                for (int i2 = 0; i2 < 8; ++i2) {
+                                    // same pair arithmetic as every other kernel (common.cuh), two Gaussians per packed op
+                                    const float4 q0 = gbuf[3 * (8 * j + i2)], q1 = gbuf[3 * (8 * j + i2) + 1],
+                                                 q2 = gbuf[3 * (8 * j + i2) + 2];
+                                    const float2 dx = add2_rn(make_float2(q0.x, q0.y), npx);
+                                    const float2 dy = add2_rn(make_float2(q0.z, q0.w), npy);
+                                    const float2 sg = pair_sigma2(dx, dy, make_float2(q1.x, q1.y), make_float2(q1.z, q1.w),
+                                                                  make_float2(q2.x, q2.y));
+                                    const float2 ex = mul2_rn(sg, make_float2(-kLog2e, -kLog2e));
+#pragma unroll
+                                    for (int h = 0; h < 2; ++h) {
+                                        const float sigma = h ? sg.y : sg.x;
+                                        const float alpha = fminf(kAlphaMax, __fmul_rn(h ? q2.w : q2.z, ex2_approx(h ? ex.y : ex.x)));
+                                        const float nT = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                                        const bool valid = !done && sigma >= 0.0f && alpha >= kAlphaMin;
+                                        const bool stop = valid && nT <= kTMin;
+                                        const bool take = valid && !stop;
+                                        w[2 * i2 + h] = take ? __fmul_rn(alpha, T) : 0.0f;
+                                        T = take ? nT : T;
+                                        done = done || stop;
+                                    }
                                 }
 #pragma unroll
                                 for (int h = 0; h < 2; ++h) {
@@ -617,13 +624,17 @@ int launch_render_tc(const TileCtx &t, const float *colors, int64_t cstride, int
     a.nchunks = (a.dp + MC - 1) / MC;
     a.ntiles = ntiles;
     a.unit_counter = (int *)t.scratch;
-    static const int dbg = getenv("GWBP_RENDER_DEBUG") ? atoi(getenv("GWBP_RENDER_DEBUG")) : 0;
+    int dbg = 0;
+#ifdef GWBP_EXPERIMENTS  // result-altering timing knobs exist only in experiment builds (never in lib/libgwbp.so)
+    static const int dbg_env = getenv("GWBP_RENDER_DEBUG") ? atoi(getenv("GWBP_RENDER_DEBUG")) : 0;
+    dbg = dbg_env;
+#endif
     a.debug = dbg;
     a.prof = (unsigned long long *)tc_trace_buffer();
     GWBP_CUDA_OK(cudaMemsetAsync(a.unit_counter, 0, sizeof(int), st));
     GWBP_CUDA_OK(cudaFuncSetAttribute(render_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
     GWBP_CUDA_OK(cudaFuncSetAttribute(render_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    const int grid = ntiles < kNumSMs ? ntiles : kNumSMs;
+    const int grid = ntiles < num_sms() ? ntiles : num_sms();
     // weight cache in the dead part of the workspace: per CTA and batch 64 KB of weights + GB ids
     constexpr size_t kBatchBytes = 16 * 256 * sizeof(uint4) + GB * sizeof(int);
     size_t cap = (a.nchunks > 1 && t.dead && !(dbg & 8)) ? t.dead_bytes / ((size_t)grid * kBatchBytes) : 0;

@@ -22,9 +22,44 @@ import torch
 
 from . import _lib as L
 from .engine import PackedScene, View, fpack_bytes, make_camera
-from .sh import eval_sh_colors
+from .sh import sh_colors
 
 _FPACK_CACHE = {}  # device -> scratch for the tcgen05 path's feature re-layout (reused across calls)
+
+# The reference calls `rasterization` three times per view with the SAME geometry and camera (RGB render for the
+# encoder, 512-channel pass, 3-channel pass: backproject.py:89,115,133), and gsplat projects + sorts three times.
+# Here the packed scene and the prepared view of the last call are kept and reused when nothing changed: tensors are
+# identified by (storage pointer, shape, in-place version counter), the camera by its bytes.
+_SCENE_CACHE = {"key": None, "scene": None}
+_VIEW_CACHE = {"key": None, "view": None}
+
+
+def cache_clear() -> None:
+    """Drop the cached scene / view (e.g. after modifying a geometry tensor through `.data`, which does not bump
+    the version counter)."""
+    _SCENE_CACHE.update(key=None, scene=None)
+    _VIEW_CACHE.update(key=None, view=None)
+
+
+def _tensor_key(t: torch.Tensor):
+    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype, t._version, t.device)
+
+
+def _cached_scene(means, quats, scales, opacities) -> PackedScene:
+    key = tuple(_tensor_key(t) for t in (means, quats, scales, opacities))
+    if _SCENE_CACHE["key"] != key:
+        cache_clear()
+        _SCENE_CACHE.update(key=key, scene=PackedScene(means, quats, scales, opacities))
+    return _SCENE_CACHE["scene"]
+
+
+def _cached_view(scene: PackedScene, cam) -> View:
+    key = (id(scene), bytes(cam))
+    if _VIEW_CACHE["key"] != key:
+        # a fresh workspace per camera: an autograd graph may still hold the previous view for its backward pass
+        _VIEW_CACHE.update(key=None, view=None)
+        _VIEW_CACHE.update(key=key, view=View(scene, cam))
+    return _VIEW_CACHE["view"]
 
 
 def _fpack_buffer(device, nbytes: int) -> torch.Tensor:
@@ -110,20 +145,20 @@ def rasterization(
                                   "are used only by the out-of-scope f3dgs trainer")
     width, height = int(width), int(height)
 
-    scene = PackedScene(means, quats, scales, opacities)
+    scene = _cached_scene(means, quats, scales, opacities)
     vm_host = viewmats.detach().to("cpu", torch.float32)
     k_host = Ks.detach().to("cpu", torch.float32)
 
     renders, alphas, metas = [], [], []
     for ci in range(c):
         cam = make_camera(vm_host[ci], k_host[ci], width, height, near_plane, far_plane, radius_clip, eps2d)
-        view = View(scene, cam)
+        view = _cached_view(scene, cam)
         if sh_degree is not None:
             # colors: [N,K,3] or [C,N,K,3] SH coefficients -> view-dependent RGB (backproject.py:88-100)
             coeffs = colors[ci] if colors.dim() == 4 else colors
             assert coeffs.dim() == 3 and coeffs.shape[0] == n and coeffs.shape[2] == 3, coeffs.shape
             assert (sh_degree + 1) ** 2 <= coeffs.shape[1], (sh_degree, coeffs.shape)
-            cols = eval_sh_colors(sh_degree, means, coeffs, vm_host[ci].to(means.device))
+            cols = sh_colors(sh_degree, means, coeffs, vm_host[ci])
         else:
             cols = colors[ci] if colors.dim() == 3 else colors
             assert cols.dim() == 2 and cols.shape[0] == n, f"colors must be [N,D] or [C,N,D], got {tuple(colors.shape)}"

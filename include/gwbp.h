@@ -27,6 +27,7 @@
  *                            of which only ONE pixel is read (click_and_segment.py:241-262)
  *   gwbp_ratio_accumulate .. `gaussian_features += grad / (grad0[:,0:1] + 1e-12)` per view
  *                            (affordance_transfer/demo_affordance_transfer.py:768-796)
+ *   gwbp_sh_colors ......... the SH -> RGB stage of `rasterization(sh_degree=3)` (backproject.py:88-100)
  *   gwbp_finalize .......... backproject.py:166-169
  *   gwbp_mask3d ............ segment.py:52-58
  *   gwbp_mask2d ............ segment.py:221-224
@@ -173,6 +174,14 @@ int gwbp_render_pixels(const gwbp_scene *scene, const gwbp_camera *cam_host, con
 int gwbp_ratio_accumulate(const gwbp_scene *scene, const gwbp_camera *cam_host, const void *ws,
                           const gwbp_view_info *info_host, float *num_v, float *den_v, float *acc, float *den_acc,
                           int32_t d, float num_scale, float den_scale, float eps, void *stream);
+
+/* colours[g, c] = max(sum_k Y_k(normalise(mean_g - cam_pos)) * coeffs[g, k, c] + 0.5, 0), k < (degree+1)^2, degree <= 4:
+ * the `rasterization(..., sh_degree=3)` colour stage (backproject.py:88-100, segment.py:197-208; gsplat-1.4.0
+ * spherical_harmonics + clamp_min(. + 0.5, 0)).  means [n,3] contiguous; coeffs [n,K,3] with ELEMENT strides
+ * (sN, sK, sC) so `torch.cat((features_dc, features_rest), 1)` or separate views need no copy; cam_pos_host: 3 floats
+ * on the HOST (camera centre in world space); out [n,3] contiguous. */
+int gwbp_sh_colors(int64_t n, int32_t degree, const float *means, const float *coeffs, int64_t sN, int64_t sK, int64_t sC,
+                   const float *cam_pos_host, float *out, void *stream);
 
 /* out[g,:] = normalise(num[g,:]/den[g]); NaN -> 0   (backproject.py:166-169); out may alias num */
 int gwbp_finalize(const float *num, const float *den, float *out, int64_t n, int32_t d, void *stream);

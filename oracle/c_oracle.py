@@ -35,6 +35,7 @@ def lib():
                                            C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_view_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_covar.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_view_margins.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -96,6 +97,14 @@ class View:
         lib().orc_view_backproject(self._h, _p(feats), sH, sW, sD, feats.shape[2], _p(num), _p(den), _p(stats))
         return dict(rows_nonzero=int(stats[0]), pairs=int(stats[1]), entries_walked=int(stats[2]),
                     n_vis=self.n_vis, n_isects=self.n_isects)
+
+    def margins(self, den_total, margin, frac=1e-3):
+        """min-update margin [N] fp32 (caller initialises to +inf) with every row's smallest relative distance to a
+        compositing threshold (alpha = 1/255, T(1-alpha) = 1e-4) in this view; see oracle.c::orc_view_margins."""
+        assert margin.dtype == np.float32 and margin.shape == (self.n,) and margin.flags.c_contiguous
+        den_total = np.ascontiguousarray(den_total, dtype=np.float64)
+        assert den_total.shape == (self.n,)
+        lib().orc_view_margins(self._h, _p(den_total), float(frac), _p(margin))
 
     def render(self, colors):
         colors = _f32(colors)

@@ -448,3 +448,80 @@ def mask2d(render, text, n_pos):
     r = _normalize(render.astype(np.float64), -1)
     score = r @ _normalize(text.astype(np.float64), 1).T
     return score[..., :n_pos].max(axis=2) > score[..., n_pos:].max(axis=2), score
+
+
+# --------------------------------------------------------------------------------------
+# 6. encoder-resolution feature maps  (backproject.py:110-112 bilinear, :245-249 nearest)
+# --------------------------------------------------------------------------------------
+def upsample(feats_low, height, width, mode="bilinear"):
+    """torch.nn.functional.interpolate(x[1,D,h,w], size=(H,W), mode=mode) restated in fp32 numpy (align_corners=False:
+    src = scale*(dst+0.5)-0.5 clamped at 0, scale = in/out; nearest: floor(dst*scale)).  feats_low: [h,w,D] -> [H,W,D].
+    Checked against torch's own CPU kernel in tests/test_oracle.py."""
+    f = feats_low.astype(F32, copy=False)
+    h, w = f.shape[:2]
+
+    def src(n_out, n_in):
+        scale = F32(n_in) / F32(n_out)
+        o = np.arange(n_out, dtype=F32)
+        if mode == "nearest":
+            i0 = np.minimum(np.floor(o * scale).astype(np.int64), n_in - 1)
+            return i0, i0, np.zeros(n_out, F32)
+        s = np.maximum(scale * (o + F32(0.5)) - F32(0.5), F32(0.0))
+        i0 = np.minimum(s.astype(np.int64), n_in - 1)
+        i1 = i0 + (i0 < n_in - 1)
+        return i0, i1, (s - i0.astype(F32)).astype(F32)
+
+    assert mode in ("bilinear", "nearest"), mode
+    y0, y1, ly = src(height, h)
+    x0, x1, lx = src(width, w)
+    if mode == "nearest":
+        return f[y0][:, x0]
+    lx = lx[None, :, None]
+    ly = ly[:, None, None]
+    top = (F32(1.0) - lx) * f[y0][:, x0] + lx * f[y0][:, x1]
+    bot = (F32(1.0) - lx) * f[y1][:, x0] + lx * f[y1][:, x1]
+    return ((F32(1.0) - ly) * top + ly * bot).astype(F32)
+
+
+# --------------------------------------------------------------------------------------
+# 7. spherical-harmonics colours  (rasterization(sh_degree=3): backproject.py:88-100; SURVEY.md §9.2)
+# --------------------------------------------------------------------------------------
+def sh_basis(degree, dirs):
+    """Real spherical harmonics up to `degree` from FIRST PRINCIPLES (associated Legendre functions with the
+    Condon-Shortley phase, scipy.special.lpmv) -- deliberately not the hard-coded polynomial tables the CUDA kernel
+    uses, so the two are independent.  3DGS / gsplat order: index l*l + l + m, sign convention
+    Y_1 = (-C1 y, C1 z, -C1 x).  dirs [N,3] (normalised here).  Returns [N, (degree+1)^2] fp64."""
+    from math import factorial, pi, sqrt
+
+    from scipy.special import lpmv
+
+    d = dirs.astype(np.float64)
+    d = d / np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-30)
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    phi = np.arctan2(y, x)
+    ct = np.clip(z, -1.0, 1.0)
+    out = np.zeros((d.shape[0], (degree + 1) ** 2))
+    for l in range(degree + 1):
+        for m in range(-l, l + 1):
+            am = abs(m)
+            k = sqrt((2 * l + 1) / (4 * pi) * factorial(l - am) / factorial(l + am))
+            p = lpmv(am, l, ct)
+            if m == 0:
+                v = k * p
+            elif m > 0:
+                v = sqrt(2.0) * k * np.cos(am * phi) * p
+            else:
+                v = sqrt(2.0) * k * np.sin(am * phi) * p
+            out[:, l * l + l + m] = v
+    return out
+
+
+def sh_colors(degree, means, coeffs, viewmat):
+    """colour[g] = max(sum_k Y_k(dir_g) * coeffs[g,k,:] + 0.5, 0), dir_g = mean_g - camera position
+    (gsplat-1.4.0 rendering.py: `dirs = means - camtoworlds[:, :3, 3]`, `clamp_min(colors + 0.5, 0)`).  fp64."""
+    vm = viewmat.astype(np.float64)
+    cam_pos = -(vm[:3, :3].T @ vm[:3, 3])
+    basis = sh_basis(degree, means.astype(np.float64) - cam_pos[None])
+    k = (degree + 1) ** 2
+    col = np.einsum("nk,nkc->nc", basis, coeffs[:, :k].astype(np.float64))
+    return np.maximum(col + 0.5, 0.0)

@@ -426,6 +426,71 @@ void orc_view_render(const OrcView *v, const float *colors, int D, double *out, 
     }
 }
 
+/* ---- threshold-margin analysis (tests only) ---------------------------------------------------------
+ * The compositing loop has two hard cut-offs: alpha < 1/255 -> skip, and T(1-alpha) <= 1e-4 -> stop.  A
+ * GPU that evaluates exp() a few ulp differently can land a (pixel, Gaussian) pair on the other side of
+ * one; parity tests must be able to tell such a flip from a real error.  For every Gaussian row this
+ * walk records the SMALLEST relative distance to a threshold among the tests that can change the row:
+ *   - the row's own tests, |alpha - 1/255| / (1/255) (when sigma >= 0) and |T' - 1e-4| / 1e-4
+ *     (a flip changes w(g,p) itself);
+ *   - every alpha test met EARLIER on the same pixel's walk (a flip there scales the transmittance of
+ *     all later Gaussians by 1 - 1/255), counted only at pixels that carry at least `frac` of the
+ *     row's total weight den_total[g], since a 0.4 % change of a smaller share cannot move the row.
+ * A T-stop flip touches only the Gaussian it happens at: in either outcome the very next valid
+ * Gaussian stops the pixel (T <~ 1e-4 already).
+ * margin[] must be initialised by the caller (e.g. to +inf) and is min-updated, so views accumulate. */
+void orc_view_margins(const OrcView *v, const double *den_total, double frac, float *margin) {
+    const int ntiles = v->tw * v->th;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int ty = tile / v->tw, tx = tile % v->tw;
+        const int64_t s = v->offsets[tile];
+        const int64_t e = (tile + 1 < ntiles) ? v->offsets[tile + 1] : v->n_isects;
+        unsigned char done[NPIX];
+        float px[NPIX], py[NPIX], T[NPIX], pm[NPIX];
+        int live = 0;
+        for (int p = 0; p < NPIX; ++p) {
+            const int yy = ty * TILE + p / TILE, xx = tx * TILE + p % TILE;
+            px[p] = (float)xx + 0.5f; py[p] = (float)yy + 0.5f;
+            done[p] = !(yy < v->H && xx < v->W);
+            live += !done[p];
+            T[p] = 1.0f; pm[p] = INFINITY;
+        }
+        for (int64_t k = s; k < e && live > 0; ++k) {
+            const int g = v->gaussian_ids[v->flatten_ids[k]];
+            const float gx = v->means2d[2 * (size_t)g], gy = v->means2d[2 * (size_t)g + 1];
+            const float cxx = v->conics[3 * (size_t)g], cxy = v->conics[3 * (size_t)g + 1], cyy = v->conics[3 * (size_t)g + 2];
+            const float op = v->opac[g];
+            float best = INFINITY;
+            for (int p = 0; p < NPIX; ++p) {
+                if (done[p]) continue;
+                const float dx = gx - px[p], dy = gy - py[p];
+                const float sigma = 0.5f * ((cxx * dx) * dx + (cyy * dy) * dy) + (cxy * dx) * dy;
+                const float alpha = fminf(0.999f, op * expf(-sigma));
+                float own = INFINITY;
+                if (sigma >= 0.0f) own = fabsf(alpha - 1.0f / 255.0f) * 255.0f;
+                const float upstream = pm[p];
+                if (own < pm[p]) pm[p] = own; /* later Gaussians of this pixel see this alpha test */
+                if (sigma < 0.0f || alpha < 1.0f / 255.0f) { if (own < best) best = own; continue; }
+                const float nT = T[p] * (1.0f - alpha);
+                const float mt = fabsf(nT - 1e-4f) * 1e4f;
+                if (mt < own) own = mt;
+                if (own < best) best = own;
+                if (nT <= 1e-4f) { done[p] = 1; --live; continue; }
+                const float w = alpha * T[p];
+                T[p] = nT;
+                if ((double)w >= frac * den_total[g] && upstream < best) best = upstream;
+            }
+            if (best < INFINITY) { /* atomic min: non-negative floats order like their bit patterns */
+                uint32_t nb, *slot = (uint32_t *)(margin + g);
+                memcpy(&nb, &best, 4);
+                uint32_t cur = __atomic_load_n(slot, __ATOMIC_RELAXED);
+                while (nb < cur && !__atomic_compare_exchange_n(slot, &cur, nb, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+            }
+        }
+    }
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -33,3 +33,14 @@ def row_cosine(a, b):
     na, nb = np.linalg.norm(a, axis=1), np.linalg.norm(b, axis=1)
     ok = (na > 0) & (nb > 0)
     return (a[ok] * b[ok]).sum(1) / (na[ok] * nb[ok]), ok
+
+
+def oracle_margins(coracle, sc, vm, K, width, height, den_total, views=None, frac=1e-3):
+    """Per-Gaussian smallest relative distance to a compositing threshold (alpha = 1/255, T(1-alpha) = 1e-4)
+    over the given views (oracle.c::orc_view_margins); +inf for rows no test ever touched."""
+    margin = np.full(sc.n, np.inf, np.float32)
+    for v in (range(vm.shape[0]) if views is None else views):
+        view = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, width, height)
+        view.margins(den_total, margin, frac)
+        view.close()
+    return margin

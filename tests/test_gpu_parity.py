@@ -4,18 +4,22 @@ inputs.  Bars (BASELINE.json north_star / BASELINE.md §3):
   * integer stages (radii, isect_ids, flatten_ids, isect_offsets, gaussian_ids): BIT-EXACT
   * per-Gaussian normalised features: row rel-err <= 1e-4, cosine >= 0.9999 (rows with den > 1e-6)
   * identical den>0 (prune) mask; identical segmentation masks (ties aside)
-Threshold discontinuities (alpha ~ 1/255, T ~ 1e-4) can flip a (pixel, Gaussian) pair between
-`__expf` on the GPU and expf on the CPU; such flips are counted and bounded separately."""
+Threshold discontinuities: `alpha < 1/255 -> skip` and `T(1-alpha) <= 1e-4 -> stop` are hard cut-offs, and the GPU's
+ex2.approx differs from libm's expf in the last bits, so a (pixel, Gaussian) pair sitting ON a threshold can fall on
+the other side.  There is NO blanket outlier allowance: every row above the bar must be PROVEN to be such a flip --
+the oracle reports, per row, the smallest relative distance to a threshold among the tests that can change it
+(oracle.c::orc_view_margins) and that distance must be < FLIP_MARGIN; the count is printed beside the base rate."""
 import numpy as np
 import pytest
 import torch
 
-from helpers import oracle_job, row_cosine, row_rel_err, small_case
+from helpers import oracle_job, oracle_margins, row_cosine, row_rel_err, small_case
 
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-4      # north_star: rel-err <= 1e-4 (fp32 accumulate)
 COS_TOL = 0.9999    # north_star: cosine >= 0.9999
+FLIP_MARGIN = 1e-5  # a row may exceed the bars only if one of its threshold tests is closer than this (relative)
 
 
 def _dev(a):
@@ -38,22 +42,42 @@ def _gpu_job(gwbp, sc, vm, K, W, H, feats, d, kernel="simt", contiguous=False):
     return bp
 
 
-def _check_features(bp, num_o, den_o, noracle):
+def _check_features(bp, num_o, den_o, noracle, margin=None, tag=""):
+    """Bars of BASELINE.json on every row with den > 1e-6: rel-err <= 1e-4, cosine >= 0.9999, den rel-err <= 1e-4,
+    identical prune mask.  `margin` (helpers.oracle_margins): rows above a bar must be proven threshold flips."""
     num = bp.num.double().cpu().numpy()
     den = (bp.den.double().cpu().numpy() - 1e-12)
-    assert np.array_equal(den > 5e-13, den_o > 0), "prune mask differs"
-    f_gpu = bp.finalize().double().cpu().numpy()
-    f_ref = noracle.finalize(num_o, den_o + 1e-12)
+    return _check_arrays(num, den, bp.finalize().double().cpu().numpy(), num_o, den_o, noracle, margin, tag)
+
+
+def _check_arrays(num, den, f_gpu, num_o, den_o, noracle, margin, tag=""):
+    mask_diff = (den > 5e-13) != (den_o > 0)
     sel = den_o > 1e-6
-    rel, _ = row_rel_err(f_gpu[sel], f_ref[sel])
-    cos, _ = row_cosine(f_gpu[sel], f_ref[sel])
-    # a threshold flip changes one pair's weight; rows hit by one are reported, not hidden
-    outliers = int((rel > REL_TOL).sum())
-    assert outliers <= max(2, int(2e-4 * sel.sum())), f"{outliers} rows above {REL_TOL}: max {rel.max():.3e}"
-    assert np.percentile(rel, 99.9) <= REL_TOL, np.percentile(rel, 99.9)
-    assert np.percentile(cos, 0.1) >= COS_TOL
-    den_rel = np.abs(den[sel] - den_o[sel]) / den_o[sel]
-    assert np.percentile(den_rel, 99.9) <= REL_TOL
+    f_ref = noracle.finalize(num_o[sel], den_o[sel] + 1e-12)
+    return _check_rows(f_gpu[sel], den[sel], f_ref, den_o[sel], None if margin is None else margin[sel], mask_diff,
+                       None if margin is None else margin[mask_diff], tag)
+
+
+def _check_rows(f_gpu, den, f_ref, den_o, m, mask_diff, m_mask_diff, tag=""):
+    """Rows already restricted to den_o > 1e-6; `m` = their threshold margins; mask_diff / m_mask_diff = the rows whose
+    den > 0 decision differs and their margins."""
+    rel, _ = row_rel_err(f_gpu, f_ref)
+    cos, _ = row_cosine(f_gpu, f_ref)
+    den_rel = np.abs(den - den_o) / den_o
+    bad = (rel > REL_TOL) | (cos < COS_TOL) | (den_rel > REL_TOL)
+    if m is None:
+        assert not bad.any(), f"{int(bad.sum())} rows above the bars (max rel {rel.max():.3e}) and no margins supplied"
+        assert not mask_diff.any(), "prune mask differs"
+    else:
+        unexplained = bad & ~(m < FLIP_MARGIN)
+        assert not unexplained.any(), (f"{int(unexplained.sum())} rows above the bars are NOT threshold flips: "
+                                       f"max rel {rel[unexplained].max():.3e}, margins {m[unexplained][:5]}")
+        # a den > 0 <-> den == 0 disagreement is the same thing: the row's only pair sits on a threshold
+        assert not (m_mask_diff >= FLIP_MARGIN).any(), "prune mask differs away from thresholds"
+        base = float((m < FLIP_MARGIN).mean())
+        print(f"[parity{tag}] rows {rel.size}: {int(bad.sum())} above the bars, all with a threshold test closer than "
+              f"{FLIP_MARGIN:g} (such rows are {100 * base:.2f} % of all rows); prune-mask flips {int(mask_diff.sum())}; "
+              f"other rows: rel max {rel[~bad].max():.2e}, cos min {cos[~bad].min():.7f}, den rel max {den_rel[~bad].max():.2e}")
     return rel, cos
 
 
@@ -113,8 +137,9 @@ def test_integer_stages_bit_exact_config_S_and_odd_sizes(gwbp, coracle):
 def test_backprojection_small(gwbp, coracle, noracle, case, kernel):
     sc, vm, K, feats = case
     num_o, den_o, st = oracle_job(coracle, sc, vm, K, 96, 64, feats, 8)
+    margin = oracle_margins(coracle, sc, vm, K, 96, 64, den_o)
     bp = _gpu_job(gwbp, sc, vm, K, 96, 64, feats, 8, kernel)
-    _check_features(bp, num_o, den_o, noracle)
+    _check_features(bp, num_o, den_o, noracle, margin, f" small/{kernel}")
     s = bp.stats()
     assert abs(s["rows_nonzero"] - sum(x["rows_nonzero"] for x in st)) <= 4  # threshold flips only
 
@@ -128,20 +153,68 @@ def test_backprojection_config_S(gwbp, coracle, noracle, kernel):
     vm, K = S.make_cameras(c["views"], c["width"], c["height"], 0)
     feats = [S.make_feature_map_np(v, c["d"], c["height"], c["width"], 0) for v in range(c["views"])]
     num_o, den_o, _ = oracle_job(coracle, sc, vm, K, c["width"], c["height"], feats, c["d"])
+    margin = oracle_margins(coracle, sc, vm, K, c["width"], c["height"], den_o)
     bp = _gpu_job(gwbp, sc, vm, K, c["width"], c["height"], feats, c["d"], kernel)
-    rel, cos = _check_features(bp, num_o, den_o, noracle)
-    print(f"[config S/{kernel}] rel-err max {rel.max():.2e} p99.9 {np.percentile(rel, 99.9):.2e}; cos min {cos.min():.6f}")
+    _check_features(bp, num_o, den_o, noracle, margin, f" config S/{kernel}")
 
 
-@pytest.mark.parametrize("d", [1, 3, 16, 100, 512, 768])
+def test_tensor_core_and_cuda_core_kernels_flip_identically(gwbp):
+    """Both kernels evaluate a (pixel, Gaussian) pair with the SAME roundings (common.cuh pair_sigma / pair_alpha /
+    composite_step), so their weights are bit-identical: same den up to the summation order, same non-zero rows --
+    the tcgen05 path adds no threshold flips of its own (config S)."""
+    S = gwbp.scene
+    c = S.CONFIGS["S"]
+    sc = S.make_scene(c["n"], 0)
+    vm, K = S.make_cameras(c["views"], c["width"], c["height"], 0)
+    feats = [S.make_feature_map_np(v, c["d"], c["height"], c["width"], 0) for v in range(c["views"])]
+    a = _gpu_job(gwbp, sc, vm, K, c["width"], c["height"], feats, c["d"], "simt")
+    b = _gpu_job(gwbp, sc, vm, K, c["width"], c["height"], feats, c["d"], "tc")
+    assert a.stats() == b.stats()
+    assert torch.equal(a.den > 1e-12, b.den > 1e-12)
+    assert torch.allclose(a.den, b.den, rtol=2e-6, atol=1e-12)  # fp32 sums of identical terms in a different order
+    seen = a.den > 1e-6
+    err = (a.num[seen] - b.num[seen]).norm(dim=1) / a.num[seen].norm(dim=1).clamp_min(1e-9)
+    assert float(err.max()) < 2e-5, float(err.max())  # split-bf16 contraction vs fp32 FMA, no outliers at all
+
+
+@pytest.mark.parametrize("d", [1, 3, 16, 100, 512, 768, 1024])
 def test_backprojection_feature_dims(gwbp, coracle, noracle, d):
     S = gwbp.scene
     sc, vm, K, _ = small_case(S, n=1500, views=1, width=64, height=48, d=8, seed=7)
     feats = [S.make_feature_map_np(0, d, 48, 64, 7, enc_res=10)]
     num_o, den_o, _ = oracle_job(coracle, sc, vm, K, 64, 48, feats, d)
+    margin = oracle_margins(coracle, sc, vm, K, 64, 48, den_o)
     for kernel in ("simt", "auto"):
         bp = _gpu_job(gwbp, sc, vm, K, 64, 48, feats, d, kernel)
-        _check_features(bp, num_o, den_o, noracle)
+        _check_features(bp, num_o, den_o, noracle, margin, f" D={d}/{kernel}")
+
+
+@pytest.mark.parametrize("mode,d,enc", [("nearest", 1024, 64), ("bilinear", 512, 60), ("nearest", 48, 9), ("bilinear", 16, 7)])
+def test_encoder_resolution_maps_against_the_oracle(gwbp, coracle, noracle, mode, d, enc):
+    """The DINOv2 variant (backproject.py:206-211,236-249: [N,1024] accumulators, 64x64 tokens upsampled with
+    mode="nearest") and the LSeg one (:108-112, bilinear), fed with the ENCODER-resolution map: the oracle
+    upsamples with its own restatement of F.interpolate (oracle/gsplat_oracle.py::upsample) and back-projects
+    the full-resolution map; the GPU path fuses the upsample (add_view_lowres) and is also given the materialised map."""
+    S = gwbp.scene
+    W, H = 211, 137
+    sc = S.make_scene(6000, 21)
+    vm, K = S.make_cameras(2, W, H, 21)
+    rng = np.random.default_rng(d + enc)
+    lows = []
+    for _ in range(2):
+        low = rng.standard_normal((enc, enc, d)).astype(np.float32)
+        lows.append(low / np.linalg.norm(low, axis=2, keepdims=True))
+    feats = [noracle.upsample(low, H, W, mode) for low in lows]
+    num_o, den_o, _ = oracle_job(coracle, sc, vm, K, W, H, feats, d)
+    margin = oracle_margins(coracle, sc, vm, K, W, H, den_o)
+    args = (_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities), d)
+    fused, full = gwbp.BackProjector(*args, kernel="tc"), gwbp.BackProjector(*args, kernel="tc")
+    for v in range(2):
+        planar_low = _dev(np.ascontiguousarray(np.transpose(lows[v], (2, 0, 1))))  # encoder output [D,h,w]
+        fused.add_view_lowres(vm[v], K, W, H, planar_low.permute(1, 2, 0), mode=mode)
+        full.add_view(vm[v], K, W, H, _feat_dev(feats[v]))
+    _check_features(fused, num_o, den_o, noracle, margin, f" lowres {mode} D={d} fused")
+    _check_features(full, num_o, den_o, noracle, margin, f" lowres {mode} D={d} materialised")
 
 
 def test_tile_culling_does_not_change_the_accumulators(gwbp, case):
@@ -158,6 +231,33 @@ def test_tile_culling_does_not_change_the_accumulators(gwbp, case):
     assert torch.allclose(n0, n1, rtol=1e-5, atol=1e-6) and torch.allclose(d0, d1, rtol=1e-5, atol=1e-7)
     assert s0["rows_nonzero"] == s1["rows_nonzero"] and s1["entries_walked"] < s0["entries_walked"]
     assert torch.equal(d0 > 1e-12, d1 > 1e-12)
+
+
+def test_tile_culling_config_S_identical_results(gwbp):
+    """Tile culling is ON by default in BackProjector and is not part of gsplat: at config S (50k Gaussians, 8 views
+    of 256x256) the culled and the gsplat-exact intersection lists must give the same non-zero rows, the same prune
+    mask and the same accumulators (only the order of the fp32 atomic adds may differ)."""
+    S = gwbp.scene
+    c = S.CONFIGS["S"]
+    sc = S.make_scene(c["n"], 0)
+    vm, K = S.make_cameras(c["views"], c["width"], c["height"], 0)
+    feats = [_feat_dev(S.make_feature_map_np(v, c["d"], c["height"], c["width"], 0)) for v in range(c["views"])]
+    for kernel in ("simt", "tc"):
+        out = []
+        for cull in (False, True):
+            bp = gwbp.BackProjector(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities), c["d"],
+                                    kernel=kernel, collect_stats=True, tile_cull=cull)
+            isects = 0
+            for v in range(c["views"]):
+                isects += bp.add_view(vm[v], K, c["width"], c["height"], feats[v]).n_isects
+            out.append((bp.num.clone(), bp.den.clone(), bp.stats(), isects))
+        (n0, d0, s0, i0), (n1, d1, s1, i1) = out
+        assert s0["rows_nonzero"] == s1["rows_nonzero"] and i1 < 0.8 * i0 and s1["entries_walked"] < s0["entries_walked"]
+        assert torch.equal(d0 > 1e-12, d1 > 1e-12)
+        assert torch.allclose(d0, d1, rtol=2e-6, atol=1e-12)
+        seen = d0 > 1e-6
+        err = (n0[seen] - n1[seen]).norm(dim=1) / n0[seen].norm(dim=1).clamp_min(1e-9)
+        assert float(err.max()) < 2e-5, (kernel, float(err.max()))
 
 
 @pytest.mark.parametrize("mode", ["bilinear", "nearest"])
@@ -222,8 +322,7 @@ def test_tcgen05_feature_layouts_agree(gwbp, d):
         if first is None:  # tensor cores vs CUDA cores: split-bf16 contraction, threshold flips aside
             first = bp
             err = (bp.num[seen] - ref.num[seen]).norm(dim=1) / ref.num[seen].norm(dim=1).clamp_min(1e-6)
-            assert float(torch.quantile(err, 0.999)) < REL_TOL, float(torch.quantile(err, 0.999))
-            assert int((err > REL_TOL).sum()) <= max(2, int(2e-4 * int(seen.sum())))
+            assert float(err.max()) < 2e-5, float(err.max())  # identical weights (common.cuh): no flips, no outliers
         else:  # same packed operand whatever the input layout: only the order of the atomic adds differs
             assert torch.allclose(bp.den, first.den, rtol=1e-5, atol=1e-9), name
             assert torch.allclose(bp.num, first.num, rtol=1e-4, atol=1e-5), name
@@ -471,6 +570,43 @@ def test_full_size_config_G_properties(gwbp):
     assert abs(lhs - rhs) <= 1e-5 * scale, (lhs, rhs, scale)
 
 
+@pytest.mark.parametrize("config,view", [("G", 7), ("M", 500)])
+def test_full_size_view_against_the_oracle(gwbp, coracle, noracle, config, view):
+    """ONE view of BASELINE config[1] (5.8 M Gaussians, 1297x840, D = 512) and of config[4] (6 M, 1920x1080, D = 768)
+    at FULL size, tcgen05 path with the default tile culling, against the C oracle on the same inputs: bit-exact
+    intersection counts (gsplat-exact list), identical prune mask, and the rel-err / cosine / den bars on every row
+    with den > 1e-6 (rows above a bar must be proven threshold flips)."""
+    S = gwbp.scene
+    cfg = S.CONFIGS[config]
+    W, H, d = cfg["width"], cfg["height"], cfg["d"]
+    sc = S.make_scene(cfg["n"], 0)
+    vm, K = S.make_cameras(cfg["views"], W, H, 0)
+    F = S.make_feature_map_torch(view, d, H, W, "cuda", 0, enc_res=240)  # permuted view of a planar [D,H,W] buffer
+    bp = gwbp.BackProjector(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities), d, kernel="tc",
+                            collect_stats=True)
+    v_gpu = bp.add_view(vm[view], K, W, H, F)
+    F_host = F.permute(2, 0, 1).contiguous().cpu().numpy().transpose(1, 2, 0)
+    del F
+    cv = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[view], K, W, H)
+    cvc = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[view], K, W, H, cull=True)
+    assert (v_gpu.n_vis, v_gpu.n_isects) == (cvc.n_vis, cvc.n_isects)  # the culled list, bit-exact counts
+    cvc.close()
+    num_o = np.zeros((sc.n, d), np.float64)  # calloc: only touched rows are committed
+    den_o = np.zeros(sc.n, np.float64)
+    st = cv.backproject(F_host, num_o, den_o)
+    margin = np.full(sc.n, np.inf, np.float32)
+    cv.margins(den_o, margin)
+    cv.close()
+    assert abs(bp.stats()["rows_nonzero"] - st["rows_nonzero"]) <= max(4, 1e-4 * st["rows_nonzero"])
+    den = bp.den.double().cpu().numpy() - 1e-12
+    mask_diff = (den > 5e-13) != (den_o > 0)
+    idx = np.nonzero(den_o > 1e-6)[0]
+    f_ref = noracle.finalize(num_o[idx], den_o[idx] + 1e-12)
+    del num_o
+    f_gpu = bp.finalize()[torch.from_numpy(idx).cuda()].double().cpu().numpy()
+    _check_rows(f_gpu, den[idx], f_ref, den_o[idx], margin[idx], mask_diff, margin[mask_diff], f" config {config} full size")
+
+
 def test_full_size_config_M_properties(gwbp):
     """BASELINE config[4] at FULL size on one GPU (6 M Gaussians, 1920x1080, D = 768: three column chunks on the
     tcgen05 path), through size-independent properties: sum(den_v) == sum(alpha_v); constant features =>
@@ -533,13 +669,21 @@ def test_rasterization_backgrounds_depth_modes_and_sh(gwbp, coracle, case, tmp_p
     want_ed = rz_o[..., 0] / np.maximum(a_o, 1e-10)
     cover = a_o > 0.05
     assert np.abs(out_ed[0, ..., 3].double().cpu().numpy() - want_ed)[cover].max() < 1e-2
-    # SH degree 3 with only the DC term set == constant colour 0.5 + C0 * dc
-    sh = torch.zeros(sc.n, 16, 3, device="cuda")
-    sh[:, 0, :] = _dev(cols)
-    out_sh, _, _ = gwbp.rasterization(means, quats, scales, opac, sh, _dev(vm[0])[None], _dev(K)[None], 96, 64,
-                                      sh_degree=3)
-    r_dc, _ = cv.render((0.5 + 0.28209479177387814 * cols).astype(np.float32))
-    assert np.abs(out_sh[0].double().cpu().numpy() - r_dc).max() < 2e-4
+    # SH colours, degree 0..4 (the reference uses 3: backproject.py:99), against the oracle's independent basis
+    # (associated Legendre functions, oracle/gsplat_oracle.py::sh_basis) composited by the C oracle
+    sh_np = (rng.standard_normal((sc.n, 25, 3)) * 0.4).astype(np.float32)
+    sh_np[:, 0, :] += 0.8
+    for degree in (0, 1, 2, 3, 4):
+        kk = (degree + 1) ** 2
+        coeffs = _dev(sh_np)[:, :max(kk, 16)] if degree < 4 else _dev(sh_np)
+        out_sh, _, _ = gwbp.rasterization(means, quats, scales, opac, coeffs, _dev(vm[0])[None], _dev(K)[None], 96, 64,
+                                          sh_degree=degree)
+        cols_o = noracle.sh_colors(degree, sc.means, sh_np, vm[0])
+        assert (cols_o == 0).any() and (cols_o > 0).any()  # the clamp at 0 is exercised
+        cols_gpu = gwbp.sh_colors(degree, means, coeffs, _dev(vm[0])).double().cpu().numpy()
+        assert np.abs(cols_gpu - cols_o).max() < 5e-6 * max(1.0, np.abs(cols_o).max()), degree
+        r_sh, _ = cv.render(cols_o.astype(np.float32))
+        assert np.abs(out_sh[0].double().cpu().numpy() - r_sh).max() < 2e-4, degree
     # feature-field file in the reference's format
     bp = gwbp.BackProjector(means, quats, scales, opac, 8)
     for v in range(vm.shape[0]):

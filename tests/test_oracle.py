@@ -314,3 +314,94 @@ def test_golden_fixture(gwbp, coracle, noracle):
     t = gwbp.scene.make_text_queries(3, d, 0)
     m, _ = noracle.mask3d(f, t, 1)
     assert (m != g["mask3d"]).sum() <= 1
+
+
+def test_sh_basis_from_first_principles_matches_the_3dgs_tables(noracle):
+    """oracle/gsplat_oracle.py::sh_basis (associated Legendre functions) against the real-SH polynomial tables of the
+    3DGS code base that csrc/sh.cu hard-codes: degree 0..3 constants and signs, parity of the bands, and the colour
+    rule max(SH + 0.5, 0) with dirs = mean - camera centre (backproject.py:88-100)."""
+    rng = np.random.default_rng(0)
+    d = rng.standard_normal((500, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    x, y, z = d.T
+    B = noracle.sh_basis(4, d)
+    C1, C2 = 0.4886025119029199, 1.0925484305920792
+    want = {0: 0.28209479177387814 + 0 * x, 1: -C1 * y, 2: C1 * z, 3: -C1 * x, 4: C2 * x * y, 5: -C2 * y * z,
+            6: 0.31539156525252005 * (2 * z * z - x * x - y * y), 7: -C2 * x * z, 8: 0.5462742152960396 * (x * x - y * y),
+            9: -0.5900435899266435 * y * (3 * x * x - y * y), 10: 2.890611442640554 * x * y * z,
+            15: -0.5900435899266435 * x * (x * x - 3 * y * y), 20: 0.10578554691520431 * (z * z * (35 * z * z - 30) + 3)}
+    for k, v in want.items():
+        assert np.abs(B[:, k] - v).max() < 1e-12, k
+    Bm = noracle.sh_basis(4, -d)  # band l has parity (-1)^l
+    for l in range(5):
+        assert np.abs(Bm[:, l * l:(l + 1) ** 2] - (-1) ** l * B[:, l * l:(l + 1) ** 2]).max() < 1e-12
+    # orthonormality on the sphere (Monte-Carlo, 4 pi / n weights)
+    dd = rng.standard_normal((200_000, 3))
+    G = noracle.sh_basis(3, dd)
+    gram = 4 * np.pi * (G.T @ G) / dd.shape[0]
+    assert np.abs(gram - np.eye(16)).max() < 0.03
+    means = rng.standard_normal((50, 3)).astype(np.float32)
+    coeffs = (rng.standard_normal((50, 16, 3)) * 0.3).astype(np.float32)
+    vm = np.eye(4, dtype=np.float32)
+    vm[:3, 3] = [0.1, -0.2, 4.0]
+    c0 = noracle.sh_colors(0, means, coeffs, vm)
+    assert np.allclose(c0, np.maximum(0.28209479177387814 * coeffs[:, 0] + 0.5, 0), atol=1e-7)
+    c3 = noracle.sh_colors(3, means, coeffs, vm)
+    assert c3.shape == (50, 3) and (c3 >= 0).all() and (c3 == 0).any()
+
+
+def test_upsample_restates_torch_interpolate(noracle):
+    """oracle/gsplat_oracle.py::upsample == torch.nn.functional.interpolate (CPU kernel), the call the reference makes
+    on the encoder output (backproject.py:110-112 bilinear, :245-249 nearest)."""
+    import torch
+
+    rng = np.random.default_rng(1)
+    for (h, w, H, W) in [(24, 31, 137, 211), (64, 64, 137, 211), (12, 12, 64, 96), (30, 40, 17, 15)]:
+        low = rng.standard_normal((h, w, 5)).astype(np.float32)
+        for mode in ("bilinear", "nearest"):
+            ref = torch.nn.functional.interpolate(torch.from_numpy(low).permute(2, 0, 1)[None], size=(H, W), mode=mode)
+            ref = ref[0].permute(1, 2, 0).numpy()
+            up = noracle.upsample(low, H, W, mode)
+            assert up.shape == (H, W, 5) and up.dtype == np.float32
+            assert np.abs(up - ref).max() < (1e-5 if mode == "bilinear" else 0.0) + 1e-12, (h, w, H, W, mode)
+
+
+def test_threshold_margins(coracle):
+    """oracle.c::orc_view_margins: a Gaussian whose centre-pixel alpha sits exactly on 1/255 gets margin ~0, one far
+    from every threshold gets a large margin, and a row behind a near-threshold alpha test inherits the small margin
+    on the pixel that carries its weight."""
+    W = H = 32
+    K = np.array([[32, 0, 16.5], [0, 32, 16.5], [0, 0, 1]], np.float32)
+    vm = np.eye(4, dtype=np.float32)
+
+    def run(opacities, depths, scale=0.25):
+        n = len(opacities)
+        z = np.asarray(depths, np.float32)
+        means = np.stack([np.zeros(n, np.float32), np.zeros(n, np.float32), z], 1)
+        quats = np.tile(np.array([[1, 0, 0, 0]], np.float32), (n, 1))
+        scales = (scale * z / 4.0)[:, None].repeat(3, 1).astype(np.float32)
+        v = coracle.View(means, quats, scales, np.asarray(opacities, np.float32), vm, K, W, H)
+        num, den = np.zeros((n, 1)), np.zeros(n)
+        v.backproject(np.ones((H, W, 1), np.float32), num, den)
+        m = np.full(n, np.inf, np.float32)
+        v.margins(den, m)
+        return m, den
+
+    m, den = run([0.5], [4.0])
+    assert den[0] > 1 and 1e-4 < m[0] < 1.0       # ordinary Gaussian: some ring pixel is within 1e-4..1 of alpha = 1/255
+    on = np.float32(1.0 / 255.0)
+    m, den = run([on], [4.0])
+    assert m[0] < 1e-6                            # centre pixel: alpha == opacity == 1/255 exactly
+    # a Gaussian exactly on the alpha threshold in front of an ordinary one: the back row inherits that margin through
+    # the centre pixel, which carries ~3.7 % of its weight (a flip there would move it by 0.4 % x 3.7 % > 1e-4) ...
+    m, den = run([on, 0.5], [4.0, 5.0])
+    assert m[0] < 1e-6 and m[1] < 1e-6
+    # ... but not when only pixels carrying at least half of the row's weight are allowed to pass a margin on
+    z = np.array([4.0, 5.0], np.float32)
+    means = np.stack([np.zeros(2, np.float32), np.zeros(2, np.float32), z], 1)
+    quats = np.tile(np.array([[1, 0, 0, 0]], np.float32), (2, 1))
+    scales = (0.25 * z / 4.0)[:, None].repeat(3, 1).astype(np.float32)
+    v = coracle.View(means, quats, scales, np.array([on, 0.5], np.float32), vm, K, W, H)
+    mm = np.full(2, np.inf, np.float32)
+    v.margins(den, mm, frac=0.5)
+    assert mm[0] < 1e-6 and 1e-4 < mm[1] < 1.0
