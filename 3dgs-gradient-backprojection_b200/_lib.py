@@ -12,9 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgwbp.so")
 
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC = 0, 1, 2
-ABI_VERSION = 9
+ABI_VERSION = 10
 KERNEL_FPACK_READY = 0x100
-PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL = 0, 1
+PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL, PREPARE_SORTED_KEYS = 0, 1, 2
 
 
 class Scene(C.Structure):
@@ -29,7 +29,8 @@ class Camera(C.Structure):
 class WsLayout(C.Structure):
     _fields_ = [(k, C.c_size_t) for k in ("total", "cnt", "scan", "rec", "mask", "grec", "erec", "radii",
                                           "tiles_per_gauss", "dkeys0", "dkeys1", "dvals0", "dvals1", "cnt2", "base2",
-                                          "tkeys0", "tkeys1", "tvals0", "tvals1", "offsets", "stats", "cub_tmp",
+                                          "tkeys0", "tkeys1", "tvals0", "tvals1", "offsets", "stats", "bin_counts", "bin_seg",
+                                          "bin_tot", "cub_tmp",
                                           "cub_tmp_bytes")]
 
 
@@ -41,6 +42,7 @@ class ViewInfo(C.Structure):
 # name -> (restype, argtypes); kept in one table so tests can check it against include/gwbp.h
 SIGNATURES = {
     "gwbp_abi_version": (C.c_int, []),
+    "gwbp_launch_count": (C.c_ulonglong, []),
     "gwbp_last_error": (C.c_char_p, []),
     "gwbp_workspace_layout": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.POINTER(WsLayout)]),
     "gwbp_pack_scene": (C.c_int, [C.c_int64] + [C.c_void_p] * 6),

@@ -29,6 +29,9 @@ int num_sms() {
     return cache[dev];
 }
 
+static unsigned long long g_launches = 0;  // kernels launched by this library (all threads; relaxed counter)
+void count_launches(int k) { __atomic_fetch_add(&g_launches, (unsigned long long)k, __ATOMIC_RELAXED); }
+
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 static int tile_bits_for(int n_tiles) {
@@ -98,6 +101,14 @@ int gwbp_workspace_layout(int64_t n, int32_t width, int32_t height, int64_t cap,
     L->tvals1 = o; o = align_up(o + sizeof(int) * c1);
     L->offsets = o; o = align_up(o + sizeof(int) * (tiles + 1));
     L->stats = o; o = align_up(o + sizeof(long long) * 16);
+    {   // sort-free tile binning tables (only used when the image has <= kBinMaxTiles tiles)
+        int chunks_pad = 0, tiles_pad = 0, nseg = 0;
+        const bool fast = bin_fast_supported((int)tiles);
+        if (fast) bin_table_bytes((int)tiles, &chunks_pad, &tiles_pad, &nseg, nullptr, nullptr);
+        L->bin_counts = o; o = align_up(o + sizeof(unsigned) * (size_t)chunks_pad * tiles_pad + 16);
+        L->bin_seg = o; o = align_up(o + sizeof(unsigned) * (size_t)nseg * tiles_pad + 16);
+        L->bin_tot = o; o = align_up(o + sizeof(unsigned) * (size_t)tiles_pad + 16);
+    }
     L->cub_tmp_bytes = binning_tmp_bytes(n, c1);
     L->cub_tmp = o; o = align_up(o + L->cub_tmp_bytes);
     L->total = o;
@@ -135,8 +146,8 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     unsigned long long totals = 0;
     GWBP_CUDA_OK(cudaMemcpyAsync(&totals, w.scan + n, sizeof(totals), cudaMemcpyDeviceToHost, st));
     GWBP_CUDA_OK(cudaStreamSynchronize(st));
-    info->n_vis = (int64_t)(totals >> 32);
-    info->n_isects = (int64_t)(totals & 0xffffffffull);
+    info->n_vis = (int64_t)(totals >> kVisShift);
+    info->n_isects = (int64_t)(totals & kTileCountMask);
     if (info->n_isects > cap) {
         set_error("intersection capacity exceeded: need %lld, workspace sized for %lld",
                   (long long)info->n_isects, (long long)cap);
@@ -146,16 +157,28 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     int dsel = 0;
     if (int rc = launch_depth_sort(info->n_vis, w, &dsel, st)) return rc;
     const unsigned *order = w.dvals[dsel];
+    const int n_tiles = cd.tw * cd.th;
+    if (bin_fast_supported(n_tiles) && !(flags & GWBP_PREPARE_SORTED_KEYS)) {
+        // hand-written stable counting sort fused with the emission: no (tile, index) intermediate, no radix sort
+        info->tile_key_bytes = 0;
+        info->sorted_buf = 0;
+        return launch_bin(n, cd, order, w, cap, st);
+    }
+    // fallback for very large images (> kBinMaxTiles tiles) or when the caller asks for materialised tile keys:
+    // emit (tile, index) pairs in depth order, stable CUB radix sort on the tile id, range finding
     if (int rc = launch_gather_counts(info->n_vis, order, w, st)) return rc;
     if (int rc = launch_scan_counts(info->n_vis, w, st)) return rc;
-    const bool key16 = cd.tw * cd.th <= 65536;
+    const bool key16 = n_tiles <= 65536;
     info->tile_key_bytes = key16 ? 2 : 4;
     if (int rc = launch_emit(info->n_vis, cd, order, w, cap, key16, st)) return rc;
     int sorted = 0;
-    if (int rc = launch_tile_sort(info->n_isects, tile_bits_for(cd.tw * cd.th), w, key16, &sorted, st)) return rc;
+    const int tb = tile_bits_for(n_tiles);
+    if (int rc = launch_tile_sort(info->n_isects, key16 && tb > 16 ? 16 : tb, w, key16, &sorted, st)) return rc;
     info->sorted_buf = sorted;
-    return launch_offsets(info->n_isects, cd.tw * cd.th, w.tkeys[sorted], key16, w.offsets, st);
+    return launch_offsets(info->n_isects, n_tiles, w.tkeys[sorted], key16, w.offsets, st);
 }
+
+unsigned long long gwbp_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int gwbp_debug_set_trace(void *buf, size_t bytes) {
     tc_set_trace(buf, bytes);

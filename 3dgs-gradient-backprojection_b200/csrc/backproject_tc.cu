@@ -760,8 +760,10 @@ int launch_fpack(int W, int H, const float *F, int64_t sH, int64_t sW, int64_t s
         constexpr int kPix = 256, kCols = 64;
         dim3 grid((tw * kTile + kPix - 1) / kPix, H, (dp + kCols - 1) / kCols);
         fpack_planar_kernel<kPix, kCols><<<grid, kPix, 0, st>>>(F, sH, sD, W, H, tw, d, dp, (uint8_t *)fpack);
+        count_launches(1);
     } else {
         fpack_kernel<<<ntiles * nchunks, 256, 0, st>>>(F, sH, sW, sD, W, H, tw, d, dp, nchunks, (uint8_t *)fpack);
+        count_launches(1);
     }
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
@@ -782,6 +784,7 @@ int launch_fpack_lowres(int W, int H, const float *S, int sh, int sw, int64_t ss
         dim3 grid((W + kLowSpan - 1) / kLowSpan, th, (dp + kLowCh - 1) / kLowCh);
         fpack_lowres_tile_kernel<<<grid, 256, smem, st>>>(S, sh, sw, ssh, ssw, ssd, nearest, W, H, tw, d, dp,
                                                           (uint8_t *)fpack);
+        count_launches(1);
         GWBP_CUDA_OK(cudaGetLastError());
         return 0;
     }
@@ -791,6 +794,7 @@ int launch_fpack_lowres(int W, int H, const float *S, int sh, int sw, int64_t ss
                                      (size_t)tw * kTilePix * dp * 4, st));
     dim3 grid((W + 31) / 32, H, nchunks);
     fpack_lowres_kernel<<<grid, 256, 0, st>>>(S, sh, sw, ssh, ssw, ssd, nearest, W, H, tw, d, dp, nchunks, (uint8_t *)fpack);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -827,6 +831,7 @@ int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t 
     GWBP_CUDA_OK(cudaFuncSetAttribute(bp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
     const int grid = a.nunits < num_sms() ? a.nunits : num_sms();
     bp_tc_kernel<<<grid, kThreads, Smem::total, st>>>(a);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }

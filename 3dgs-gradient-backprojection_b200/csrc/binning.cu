@@ -27,6 +27,7 @@ int launch_scan(int64_t n, WsDev ws, cudaStream_t st) {
     GWBP_REQUIRE(need <= ws.cub_tmp_bytes, "scan scratch too small: %zu > %zu", need, ws.cub_tmp_bytes);
     size_t b = ws.cub_tmp_bytes;
     GWBP_CUDA_OK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp, b, ws.cnt, ws.scan, (long long)(n + 1), st));
+    count_launches(2);  // DeviceScanInitKernel + DeviceScanKernel
     return 0;
 }
 
@@ -41,6 +42,7 @@ static int sort_pairs(K *k0, K *k1, V *v0, V *v1, int64_t n, int bits, WsDev ws,
     GWBP_REQUIRE(need <= ws.cub_tmp_bytes, "sort scratch too small: %zu > %zu", need, ws.cub_tmp_bytes);
     size_t b = ws.cub_tmp_bytes;
     GWBP_CUDA_OK(cub::DeviceRadixSort::SortPairs(ws.cub_tmp, b, k, v, (long long)n, 0, bits, st));
+    count_launches(2 + (bits + 7) / 8);  // histogram + exclusive-sum + one onesweep pass per 8-bit digit
     *sorted_buf = k.selector;
     if (v.selector != k.selector) {
         set_error("radix sort returned mismatched key/value buffers");
@@ -61,6 +63,7 @@ int launch_scan_counts(int64_t n_vis, WsDev ws, cudaStream_t st) {
     GWBP_REQUIRE(need <= ws.cub_tmp_bytes, "scan scratch too small: %zu > %zu", need, ws.cub_tmp_bytes);
     size_t b = ws.cub_tmp_bytes;
     GWBP_CUDA_OK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp, b, ws.cnt2, ws.base2, (long long)(n_vis + 1), st));
+    count_launches(2);
     return 0;
 }
 
@@ -115,6 +118,7 @@ int launch_offsets(int64_t n_isects, int n_tiles, const void *keys, bool key16, 
         offsets_kernel<<<blocks, 256, 0, st>>>(n_isects, n_tiles, (const unsigned short *)keys, offsets);
     else
         offsets_kernel<<<blocks, 256, 0, st>>>(n_isects, n_tiles, (const unsigned *)keys, offsets);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }

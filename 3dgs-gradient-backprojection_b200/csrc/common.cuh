@@ -13,6 +13,12 @@ constexpr int kTilePix = kTile * kTile;
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kAlphaMax = 0.999f;
 constexpr float kTMin = 1e-4f;
+// per-Gaussian (visible, tile hits) counters travel through ONE 64-bit scan: tile hits in the low 33 bits, the
+// visible flag above them, so a view can hold up to 8.5e9 intersections before the sum spills into the visible count
+// (any total above the workspace capacity, which is < 2^31, is reported as "capacity exceeded")
+constexpr int kVisShift = 33;
+constexpr unsigned long long kTileCountMask = (1ull << kVisShift) - 1ull;
+constexpr int kBinMaxTiles = 12288;  // sort-free tile binning up to this many tiles (48 KB table per warp); CUB sort above
 // SMs of the CURRENT device (cudaDevAttrMultiProcessorCount, cached per device; 148 on a full B200): persistent
 // grids and per-CTA scratch partitions are sized with it, so MIG slices / other sm_100a SKUs are not mis-subscribed.
 int num_sms();
@@ -61,6 +67,7 @@ struct WsDev {
     int *tvals[2];                  // packed Gaussian index per intersection (flatten_ids)
     int *offsets;
     long long *stats;
+    unsigned *bin_counts, *bin_seg, *bin_tot;  // sort-free tile binning tables (project.cu)
     void *cub_tmp;
     size_t cub_tmp_bytes;
 };
@@ -84,6 +91,9 @@ inline WsDev ws_view(void *base, const gwbp_ws_layout &L) {
     w.tvals[0] = (int *)(b + L.tvals0); w.tvals[1] = (int *)(b + L.tvals1);
     w.offsets = (int *)(b + L.offsets);
     w.stats = (long long *)(b + L.stats);
+    w.bin_counts = (unsigned *)(b + L.bin_counts);
+    w.bin_seg = (unsigned *)(b + L.bin_seg);
+    w.bin_tot = (unsigned *)(b + L.bin_tot);
     w.cub_tmp = (void *)(b + L.cub_tmp);
     w.cub_tmp_bytes = L.cub_tmp_bytes;
     return w;
@@ -105,6 +115,12 @@ int launch_scan_counts(int64_t n_vis, WsDev ws, cudaStream_t st);
 // key16: tile ids are stored as uint16 in the tkeys buffers (tiles <= 65536): 25 % less sort traffic
 int launch_tile_sort(int64_t n_isects, int tile_bits, WsDev ws, bool key16, int *sorted_buf, cudaStream_t st);
 int launch_offsets(int64_t n_isects, int n_tiles, const void *tkeys, bool key16, int *offsets, cudaStream_t st);
+// sort-free stable tile binning (project.cu): counting pass, three scans, ordered scatter -> offsets + flatten (tvals[0])
+bool bin_fast_supported(int n_tiles);
+size_t bin_table_bytes(int n_tiles, int *chunks_pad, int *tiles_pad, int *nseg, int *chunks, int *wpc);
+int launch_bin(int64_t n, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, cudaStream_t st);
+// kernels launched by this library so far (process-wide; bench.py reports the difference over its timed region)
+void count_launches(int k);
 
 struct TileCtx {
     const float4 *grec;

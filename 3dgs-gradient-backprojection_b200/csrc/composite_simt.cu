@@ -123,6 +123,7 @@ int launch_backproject_simt(const TileCtx &t, const float *F, int64_t sH, int64_
         case 4: bp_simt_kernel<4, 16><<<tiles, 256, 0, st>>>(t, F, sH, sW, sD, d, num, den, stats); break;
         default: set_error("SIMT back-projection supports D <= 1024 (got %d)", d); return -1;
     }
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -197,6 +198,7 @@ int launch_render_simt(const TileCtx &t, const float *colors, int64_t cstride, i
         render_simt_kernel<4><<<tiles, 256, 0, st>>>(t, colors, cstride, d, bg, render, alpha);
     else
         render_simt_kernel<32><<<tiles, 256, 0, st>>>(t, colors, cstride, d, bg, render, alpha);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -289,6 +291,7 @@ int launch_render_pixels(const TileCtx &t, const float *colors, int64_t cstride,
     if (k == 0) return 0;
     GWBP_REQUIRE(d <= 256 * kProbeRegs, "render_pixels supports D <= %d (got %d)", 256 * kProbeRegs, d);
     render_pixels_kernel<<<k, 256, 0, st>>>(t, colors, cstride, d, extra, xy, out, alpha);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }

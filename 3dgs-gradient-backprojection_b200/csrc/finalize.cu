@@ -106,6 +106,7 @@ int launch_finalize(const float *num, const float *den, float *out, int64_t n, i
         finalize_kernel<8><<<blocks, 256, 0, st>>>(num, den, out, n, d);
     else
         finalize_kernel<0><<<blocks, 256, 0, st>>>(num, den, out, n, d);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -141,6 +142,7 @@ int launch_ratio_accumulate(const float4 *grec, int64_t n_vis, float *num_v, flo
     if (n_vis == 0) return 0;
     ratio_accumulate_kernel<<<(unsigned)((n_vis + 7) / 8), 256, 0, st>>>(grec, n_vis, num_v, den_v, acc, den_acc,
                                                                          d, num_scale, den_scale, eps);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -259,6 +261,7 @@ int launch_mask(const float *x, int64_t rows, int d, const float *text, int p, i
         mask_kernel<8><<<(unsigned)blocks, 256, smem, st>>>(x, rows, d, text, p, npos, thr, use_thr, mask, score);
     else
         mask_kernel<0><<<(unsigned)blocks, 256, smem, st>>>(x, rows, d, text, p, npos, thr, use_thr, mask, score);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -11,9 +11,11 @@
 // first, intersections are emitted in that order, and a stable 13-bit sort on the tile id finishes;
 // the result is identical to gsplat's 45-bit (tile|depth) sort of all intersections at ~1/5 the traffic.
 //
-// B200 notes: all kernels here are HBM-bound streaming kernels.  The scene is repacked ONCE
-// into SoA float4/float4/float2 (40 B/Gaussian, 16-byte coalesced loads); projection reads those
-// 40 B, writes an 8-byte count for every Gaussian and a 32-byte record for visible ones only.
+// B200 notes: the scene is repacked ONCE into SoA float4/float4/float2 (40 B/Gaussian, 16-byte coalesced loads);
+// projection reads those 40 B, writes an 8-byte count for every Gaussian and a 32-byte record for visible ones only.
+// pack_scene / compact are HBM-bound streaming kernels; project_kernel is NOT: with every a*b+c split into two
+// roundings (bit-exactness against the FMA-free oracle) and the exact tile test on ~7 candidate tiles per visible
+// Gaussian it is instruction-issue-bound (ncu: issue slots 84 % busy, DRAM 20 %), see DESIGN.md.
 #include "common.cuh"
 
 namespace gwbp {
@@ -78,6 +80,7 @@ int launch_pack_scene(int64_t n, const float *means, const float *quats, const f
     float4 *g1 = g0 + n;
     float2 *g2 = (float2 *)(g1 + n);
     pack_scene_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, means, quats, scales, opac, g0, g1, g2);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(256) project_kernel(int64_t n, const float4 *_
             if (lane == src) tiles = hits;
         }
     }
-    if (in_range) cnt[i] = ok ? ((1ull << 32) | (unsigned long long)tiles) : 0ull;
+    if (in_range) cnt[i] = ok ? ((1ull << kVisShift) | (unsigned long long)tiles) : 0ull;
 }
 
 int launch_project(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cudaStream_t st) {
@@ -288,6 +291,7 @@ int launch_project(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cuda
     const float4 *g1 = g0 + n;
     const float2 *g2 = (const float2 *)(g1 + n);
     project_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(n, g0, g1, g2, cam, ws.cnt, ws.rec, ws.mask);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -310,14 +314,14 @@ __global__ void __launch_bounds__(256) compact_kernel(int64_t n, CamDev cam, con
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long c = cnt[i];
-    if (!(c >> 32)) return;
-    const int pos = (int)(scan[i] >> 32);
+    if (!(c >> kVisShift)) return;
+    const int pos = (int)(scan[i] >> kVisShift);
     const float4 r0 = rec[2 * i], r1 = rec[2 * i + 1];
     grec[2 * (int64_t)pos] = make_float4(r0.x, r0.y, r0.z, __int_as_float((int)i));
     grec[2 * (int64_t)pos + 1] = make_float4(r1.x, r1.y, r1.z, r0.w);
     const int radius = __float_as_int(r1.w);
     radii[pos] = radius;
-    tpg[pos] = (int)(c & 0xffffffffull);
+    tpg[pos] = (int)(c & kTileCountMask);
     int x0, x1, y0, y1;
     tile_rect(r0.x, r0.y, radius, cam.tw, cam.th, x0, x1, y0, y1);
     const int bw = x1 - x0, ntiles = (y1 - y0) * bw;
@@ -336,6 +340,7 @@ int launch_compact(int64_t n, const CamDev &cam, WsDev ws, cudaStream_t st) {
     compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, cam, ws.cnt, ws.scan, ws.rec, ws.mask, ws.grec,
                                                               ws.radii, ws.tiles_per_gauss, ws.erec, ws.dkeys[0],
                                                               ws.dvals[0]);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -349,6 +354,7 @@ __global__ void __launch_bounds__(256) gather_counts_kernel(int64_t n_vis, const
 
 int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, cudaStream_t st) {
     gather_counts_kernel<<<(unsigned)((n_vis + 1 + 255) / 256), 256, 0, st>>>(n_vis, order, ws.tiles_per_gauss, ws.cnt2);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -435,6 +441,321 @@ int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev w
     else
         emit_kernel<unsigned><<<blocks, 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.erec,
                                                       ws.tkeys[0], ws.tvals[0], cap);
+    count_launches(1);
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tile binning without a sort (the default path; tiles <= kBinMaxTiles).
+//
+// After the depth sort, "sort the intersections by tile id, stably" is a COUNTING sort whose input never has
+// to exist: the depth-ordered Gaussians are cut into `chunks` contiguous pieces, ONE WARP PER CHUNK, and
+//   pass A  bin_count_kernel   : per-chunk histogram of tile hits (private shared-memory table, one counter/tile)
+//   scans   bin_scan*_kernel   : exclusive prefix over chunks for every tile + exclusive prefix over tiles
+//                                 (= isect_offsets) -- three small kernels over the [chunks x tiles] table
+//   pass B  bin_scatter_kernel : every warp re-walks its chunk IN DEPTH ORDER, 32 intersections per step, and
+//                                 writes each packed index straight to its final slot of flatten_ids
+// replace gather_counts + scan + emit + 2-pass radix sort + offsets (5 stages, 0.45 ms of a 2.8 ms view at config
+// G) and their (tile, index) intermediate (2 x 100 MB).  The result is bit-identical to the stable radix sort:
+// within a tile, entries keep emission order = (depth, packed index) order.
+//
+// Order inside a step: lane j holds the j-th intersection of the step (Gaussians in depth order, a Gaussian's tiles
+// row-major), `match.any` on the tile id finds the lanes that hit the same tile, the rank among them is the lane
+// order, and the private running table (absolute positions, u32 per tile) is bumped once per tile by the last of
+// them.  No atomics in pass B, so the output is deterministic.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int select_bit64(unsigned lo, unsigned hi, int k) {  // position of the k-th (0-based) set bit
+    int pos = 0;
+    unsigned m = lo;
+    int c = __popc(lo);
+    if (k >= c) { k -= c; pos = 32; m = hi; }
+    c = __popc(m & 0xffffu); if (k >= c) { k -= c; pos += 16; m >>= 16; }
+    c = __popc(m & 0xffu);   if (k >= c) { k -= c; pos += 8;  m >>= 8; }
+    c = __popc(m & 0xfu);    if (k >= c) { k -= c; pos += 4;  m >>= 4; }
+    c = __popc(m & 0x3u);    if (k >= c) { k -= c; pos += 2;  m >>= 2; }
+    c = (int)(m & 1u);       if (k >= c) { pos += 1; }
+    return pos;
+}
+
+struct BinArgs {
+    CamDev cam;
+    const unsigned *order;   // depth order -> packed index
+    const uint4 *erec;
+    const float4 *grec;
+    const int *radii;
+    const unsigned long long *scan;  // scan[n] holds the totals: visible count in the high bits
+    long long n;
+    unsigned *counts;        // [chunks_pad][tiles_pad]
+    unsigned *segsum;        // [nseg][tiles_pad]
+    unsigned *totals;        // [tiles_pad]
+    int *offsets;            // [tiles + 1]
+    int *flatten;            // [cap]
+    long long cap;
+    int chunks, tiles, tiles_pad, nseg;
+    int wpc;                 // warps (= chunks) per CTA: as many private tables as fit in shared memory, <= kBinWarps
+};
+
+__device__ __forceinline__ void bin_chunk_range(const BinArgs &a, int chunk, long long &lo, long long &hi) {
+    const long long n_vis = (long long)(a.scan[a.n] >> kVisShift);
+    long long per = (n_vis + a.chunks - 1) / a.chunks;
+    per = (per + 31) & ~31ll;
+    lo = (long long)chunk * per;
+    hi = lo + per;
+    if (lo > n_vis) lo = n_vis;
+    if (hi > n_vis) hi = n_vis;
+}
+
+// Walks one chunk in emission order and calls f(tile, packed_index, active) with the whole warp converged, 32
+// consecutive intersections at a time.  Shared by the counting and the scattering pass so that they cannot disagree.
+template <typename F>
+__device__ __forceinline__ void bin_walk_chunk(const BinArgs &a, long long lo, long long hi, F f) {
+    const int lane = threadIdx.x & 31;
+    // the (order -> erec) gather of group g+1 is issued before group g is processed: two dependent DRAM round trips
+    // per 32 Gaussians would otherwise sit on the warp's serial path
+    int pos_n = 0;
+    uint4 er_n = make_uint4(0u, 0u, 0u, 0u);
+    if (lo + lane < hi) {
+        pos_n = (int)a.order[lo + lane];
+        er_n = a.erec[pos_n];
+    }
+    for (long long g0 = lo; g0 < hi; g0 += 32) {
+        const bool vis = g0 + lane < hi;
+        const int pos = pos_n;
+        const uint4 er = er_n;
+        pos_n = 0;
+        er_n = make_uint4(0u, 0u, 0u, 0u);
+        if (g0 + 32 + lane < hi) {
+            pos_n = (int)a.order[g0 + 32 + lane];
+            er_n = a.erec[pos_n];
+        }
+        const bool big = vis && (er.z & kErecBig);
+        const int cnt = (vis && !big) ? __popc(er.x) + __popc(er.y) : 0;
+        unsigned bigmask = __ballot_sync(0xffffffffu, big);
+        int first = 0;  // lanes [first, stop) form a run of small rectangles, lane `stop` (if < 32) is a big one
+        while (first < 32) {
+            const int stop = bigmask ? (__ffs(bigmask) - 1) : 32;
+            // ---- run of small rectangles: inclusive prefix of their hit counts over the run's lanes
+            int incl = (lane >= first && lane < stop) ? cnt : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                const bool act = t < total;
+                int l = 0, h = 31;  // owner = first lane whose inclusive count exceeds t
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const int mid = (l + h) >> 1;
+                    const int v = __shfl_sync(0xffffffffu, incl, mid);
+                    if (v > t) h = mid; else l = mid + 1;
+                }
+                const int own = act ? l : 0;
+                const int oincl = __shfl_sync(0xffffffffu, incl, own), ocnt = __shfl_sync(0xffffffffu, cnt, own);
+                const unsigned mlo = __shfl_sync(0xffffffffu, er.x, own), mhi = __shfl_sync(0xffffffffu, er.y, own);
+                const unsigned code = __shfl_sync(0xffffffffu, er.z, own);
+                const int opos = __shfl_sync(0xffffffffu, pos, own);
+                int tile = 0;
+                if (act) {
+                    const int k = t - (oincl - ocnt);
+                    const int b = select_bit64(mlo, mhi, k);
+                    const int bw = (int)((code >> 24) & 0x3fu) + 1;
+                    const int row = (int)(((float)b + 0.5f) / (float)bw);  // b / bw for small non-negative ints
+                    tile = ((int)((code >> 12) & 0xfffu) + row) * a.cam.tw + (int)(code & 0xfffu) + (b - row * bw);
+                }
+                f(tile, opos, act);
+            }
+            if (stop >= 32) break;
+            // ---- one big rectangle (> 64 tiles), re-tested and emitted by the whole warp, 32 tiles per step
+            {
+                const int src = stop;
+                int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+                CullGauss cg = {};
+                if (lane == src) {
+                    const float4 r0 = a.grec[2 * (long long)pos], r1 = a.grec[2 * (long long)pos + 1];
+                    tile_rect(r0.x, r0.y, a.radii[pos], a.cam.tw, a.cam.th, x0, x1, y0, y1);
+                    if (a.cam.cull) cg = cull_setup(r0.x, r0.y, r1.x, r1.y, r1.z, r0.z);
+                }
+                const CullGauss sg = shfl_cull(cg, src);
+                const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
+                const int sbw = __shfl_sync(0xffffffffu, x1 - x0, src);
+                const int snt = __shfl_sync(0xffffffffu, (y1 - y0) * (x1 - x0), src);
+                const int spos = __shfl_sync(0xffffffffu, pos, src);
+                for (int k0 = 0; k0 < snt; k0 += 32) {
+                    const int k = k0 + lane;
+                    const int ty = sy0 + k / sbw, tx = sx0 + k % sbw;
+                    const bool hit = (k < snt) && (!a.cam.cull || tile_hit(sg, tx, ty, a.cam.W, a.cam.H));
+                    f(ty * a.cam.tw + tx, spos, hit);
+                }
+            }
+            bigmask &= bigmask - 1;
+            first = stop + 1;
+        }
+    }
+}
+
+constexpr int kBinWarps = 8;  // warps (= chunks) per CTA, fewer when the per-warp tile table is large
+
+__global__ void __launch_bounds__(32 * kBinWarps) bin_count_kernel(const BinArgs a) {
+    extern __shared__ unsigned bin_tab[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x * a.wpc + warp;
+    unsigned *tab = bin_tab + (size_t)warp * a.tiles_pad;
+    for (int t = lane; t < a.tiles_pad; t += 32) tab[t] = 0u;
+    __syncwarp();
+    if (chunk < a.chunks) {
+        long long lo, hi;
+        bin_chunk_range(a, chunk, lo, hi);
+        bin_walk_chunk(a, lo, hi, [&](int tile, int, bool act) {
+            if (act) atomicAdd(&tab[tile], 1u);  // several lanes of a step may hit the same tile
+        });
+    }
+    __syncwarp();
+    unsigned *dst = a.counts + (size_t)chunk * a.tiles_pad;  // rows chunks..chunks_pad-1 are written as zeros
+    for (int t = lane; t < a.tiles_pad; t += 32) dst[t] = tab[t];
+}
+
+constexpr int kBinSeg = 32;  // chunks per scan segment
+
+// counts[c][t] -> exclusive prefix over the 32 chunks of its segment (in place); segsum[s][t] = segment total
+__global__ void __launch_bounds__(256) bin_scan1_kernel(const BinArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+    if (t >= a.tiles_pad) return;
+    unsigned *col = a.counts + (size_t)s * kBinSeg * a.tiles_pad + t;
+    unsigned v[kBinSeg];
+#pragma unroll
+    for (int j = 0; j < kBinSeg; ++j) v[j] = col[(size_t)j * a.tiles_pad];
+    unsigned acc = 0;
+#pragma unroll
+    for (int j = 0; j < kBinSeg; ++j) {
+        col[(size_t)j * a.tiles_pad] = acc;
+        acc += v[j];
+    }
+    a.segsum[(size_t)s * a.tiles_pad + t] = acc;
+}
+
+// segsum[s][t] -> exclusive prefix over segments (in place); totals[t] = intersections of tile t
+__global__ void __launch_bounds__(256) bin_scan2_kernel(const BinArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.tiles_pad) return;
+    unsigned acc = 0;
+    for (int s = 0; s < a.nseg; ++s) {
+        const unsigned v = a.segsum[(size_t)s * a.tiles_pad + t];
+        a.segsum[(size_t)s * a.tiles_pad + t] = acc;
+        acc += v;
+    }
+    a.totals[t] = acc;
+}
+
+// offsets[t] = exclusive prefix of totals over tiles (= gsplat isect_offsets), offsets[tiles] = n_isects.  One CTA.
+__global__ void __launch_bounds__(1024) bin_scan3_kernel(const BinArgs a) {
+    __shared__ unsigned warp_sums[32];
+    __shared__ unsigned carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0u;
+    __syncthreads();
+    for (int t0 = 0; t0 < a.tiles; t0 += 1024) {
+        const int t = t0 + tid;
+        const unsigned v = t < a.tiles ? a.totals[t] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned w = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_sums[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned base = carry + (warp ? warp_sums[warp - 1] : 0u);
+        if (t < a.tiles) a.offsets[t] = (int)(base + incl - v);
+        __syncthreads();
+        if (tid == 1023) carry = base + incl;
+        __syncthreads();
+    }
+    if (tid == 0) a.offsets[a.tiles] = (int)carry;
+}
+
+__global__ void __launch_bounds__(32 * kBinWarps) bin_scatter_kernel(const BinArgs a) {
+    extern __shared__ unsigned bin_tab[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x * a.wpc + warp;
+    if (chunk >= a.chunks) return;
+    long long lo, hi;
+    bin_chunk_range(a, chunk, lo, hi);
+    if (lo >= hi) return;
+    unsigned *tab = bin_tab + (size_t)warp * a.tiles_pad;
+    const unsigned *cbase = a.counts + (size_t)chunk * a.tiles_pad;
+    const unsigned *sbase = a.segsum + (size_t)(chunk / kBinSeg) * a.tiles_pad;
+    for (int t = lane; t < a.tiles; t += 32) tab[t] = (unsigned)a.offsets[t] + sbase[t] + cbase[t];  // absolute slots
+    __syncwarp();
+    bin_walk_chunk(a, lo, hi, [&](int tile, int pos, bool act) {
+        const unsigned key = act ? (unsigned)tile : (0x80000000u | (unsigned)lane);  // inactive lanes match nobody
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int rank = __popc(peers & ((1u << lane) - 1u)), npeers = __popc(peers);
+        unsigned slot = 0;
+        if (act) slot = tab[tile];
+        __syncwarp();
+        if (act && rank == npeers - 1) tab[tile] = slot + (unsigned)npeers;
+        __syncwarp();
+        if (act && (long long)(slot + rank) < a.cap) a.flatten[slot + rank] = pos;
+    });
+}
+
+// geometry of the binning tables for an image of n_tiles tiles (host only; also sizes the workspace)
+size_t bin_table_bytes(int n_tiles, int *chunks_pad, int *tiles_pad, int *nseg, int *chunks, int *wpc) {
+    const int tp = (n_tiles + 31) & ~31;
+    const size_t tab = (size_t)tp * sizeof(unsigned);
+    int w = (int)((size_t)(200 * 1024) / tab);
+    if (w > kBinWarps) w = kBinWarps;
+    if (w < 1) w = 1;
+    const int ch = num_sms() * w;  // one CTA per SM
+    const int ns = (ch + kBinSeg - 1) / kBinSeg;
+    if (chunks) *chunks = ch;
+    if (chunks_pad) *chunks_pad = (ns * kBinSeg + w - 1) / w * w;  // whole CTAs; rows beyond `chunks` hold zeros
+    if (tiles_pad) *tiles_pad = tp;
+    if (nseg) *nseg = ns;
+    if (wpc) *wpc = w;
+    return tab;
+}
+
+bool bin_fast_supported(int n_tiles) { return n_tiles >= 1 && n_tiles <= kBinMaxTiles; }
+
+int launch_bin(int64_t n, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, cudaStream_t st) {
+    BinArgs a;
+    a.cam = cam;
+    a.order = order; a.erec = ws.erec; a.grec = ws.grec; a.radii = ws.radii; a.scan = ws.scan;
+    a.n = n;
+    a.counts = ws.bin_counts; a.segsum = ws.bin_seg; a.totals = ws.bin_tot;
+    a.offsets = ws.offsets; a.flatten = ws.tvals[0]; a.cap = cap;
+    a.tiles = cam.tw * cam.th;
+    int chunks_pad = 0;
+    const size_t tab = bin_table_bytes(a.tiles, &chunks_pad, &a.tiles_pad, &a.nseg, &a.chunks, &a.wpc);
+    const size_t smem = tab * a.wpc;
+    GWBP_CUDA_OK(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GWBP_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned ctas = (unsigned)(chunks_pad / a.wpc);
+    bin_count_kernel<<<ctas, 32 * a.wpc, smem, st>>>(a);
+    count_launches(1);
+    bin_scan1_kernel<<<dim3((unsigned)((a.tiles_pad + 255) / 256), (unsigned)a.nseg), 256, 0, st>>>(a);
+    count_launches(1);
+    bin_scan2_kernel<<<(unsigned)((a.tiles_pad + 255) / 256), 256, 0, st>>>(a);
+    count_launches(1);
+    bin_scan3_kernel<<<1, 1024, 0, st>>>(a);
+    count_launches(1);
+    bin_scatter_kernel<<<ctas, 32 * a.wpc, smem, st>>>(a);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -646,6 +646,7 @@ int launch_render_tc(const TileCtx &t, const float *colors, int64_t cstride, int
         render_tc_kernel<true><<<grid, kThreads, Smem::total, st>>>(a);
     else
         render_tc_kernel<false><<<grid, kThreads, Smem::total, st>>>(a);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -59,6 +59,7 @@ int launch_sh_colors(int64_t n, int degree, const float *means, const float *coe
     const int64_t work = 3 * n;
     sh_colors_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(n, degree, means, coeffs, sN, sK, sC, cam_pos_host[0],
                                                                    cam_pos_host[1], cam_pos_host[2], out);
+    count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
 }

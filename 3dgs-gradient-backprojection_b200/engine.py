@@ -86,10 +86,12 @@ class View:
     (= everything one `rasterization()` call computes before compositing)."""
 
     def __init__(self, scene: PackedScene, cam: L.Camera, cap_isects: Optional[int] = None,
-                 workspace: Optional[torch.Tensor] = None, tile_cull: bool = False):
+                 workspace: Optional[torch.Tensor] = None, tile_cull: bool = False, sorted_keys: bool = False):
         """tile_cull=False: the intersection list is gsplat-1.4.0's (bit-exact `meta`).
         tile_cull=True : pairs that cannot reach alpha >= 1/255 on the tile are dropped before the sort
-        (identical accumulators, less work) -- the BackProjector default."""
+        (identical accumulators, less work) -- the BackProjector default.
+        sorted_keys=True forces the emit + radix-sort binning (the fallback used for images of more than 12 288
+        tiles) instead of the sort-free counting path; both give the same flatten_ids / isect_offsets."""
         self.scene, self.cam = scene, cam
         n = scene.n
         cap = int(cap_isects) if cap_isects else max(1 << 16, 8 * n)
@@ -100,7 +102,8 @@ class View:
             info = L.ViewInfo()
             with torch.cuda.device(scene.device):
                 rc = L.lib().gwbp_view_prepare(C.byref(scene.c), C.byref(cam), workspace.data_ptr(), workspace.numel(),
-                                               cap, L.PREPARE_TILE_CULL if tile_cull else L.PREPARE_GSPLAT_EXACT,
+                                               cap, (L.PREPARE_TILE_CULL if tile_cull else L.PREPARE_GSPLAT_EXACT)
+                                               | (L.PREPARE_SORTED_KEYS if sorted_keys else 0),
                                                _stream_ptr(scene.device), C.byref(info))
             if rc == -2:  # capacity: the library told us the exact need; grow once and redo
                 cap = int(info.n_isects * 1.25) + 1024
@@ -132,12 +135,17 @@ class View:
         g = self.grec()
         nv, ni = self.n_vis, self.n_isects
         sb = self.info.sorted_buf
-        if self.info.tile_key_bytes == 2:  # uint16 tile ids
+        th, tw = self.info.tile_h, self.info.tile_w
+        if self.info.tile_key_bytes == 0:
+            # sort-free binning: sorted tile ids are never materialised; position p belongs to the tile whose
+            # [offsets[t], offsets[t+1]) range holds it
+            off = self._win(self.layout.offsets, th * tw + 1, torch.int32).to(torch.int64)
+            tiles = torch.repeat_interleave(torch.arange(th * tw, device=self.ws.device), off[1:] - off[:-1])
+        elif self.info.tile_key_bytes == 2:  # uint16 tile ids
             tiles = self._win(self.layout.tkeys1 if sb else self.layout.tkeys0, ni, torch.int16).to(torch.int64) & 0xFFFF
         else:
             tiles = self._win(self.layout.tkeys1 if sb else self.layout.tkeys0, ni, torch.int32)
         vals = self._win(self.layout.tvals1 if sb else self.layout.tvals0, ni, torch.int32)
-        th, tw = self.info.tile_h, self.info.tile_w
         # gsplat's int64 keys (tile << 32 | depth bits), rebuilt from the two-stage sort's outputs
         depth_bits = g[:, 7].contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
         keys = (tiles.to(torch.int64) << 32) | depth_bits[vals.to(torch.int64)]

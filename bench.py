@@ -164,8 +164,8 @@ def run_ours(args, cfg):
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     if world > 1:
-        # rank 0 must print ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
-        os.environ["NCCL_DEBUG"] = os.environ.get("GWBP_NCCL_DEBUG", "WARN")
+        # the caller's NCCL_DEBUG is honoured: fd 1 already points at stderr, so NCCL's INFO lines cannot reach the
+        # JSON line on the saved stdout descriptor
         dist.init_process_group("nccl", device_id=dev)
     S = gwbp.scene
     W, H, d, V = cfg["width"], cfg["height"], cfg["d"], cfg["views"]
@@ -213,10 +213,12 @@ def run_ours(args, cfg):
     bp.kernel_events = []
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     barrier()
+    launches0 = int(gwbp._lib.lib().gwbp_launch_count())
     e0.record()
     for i in range(args.steps):
         step(args.warmup + i)
     e1.record()
+    launches = int(gwbp._lib.lib().gwbp_launch_count()) - launches0  # kernels libgwbp.so launched in the timed loop
     if world > 1:
         if args.collective == "allreduce":
             gwbp.dist.allreduce_accumulators(bp.num, bp.den)
@@ -332,7 +334,7 @@ def run_ours(args, cfg):
                            "l2": f"{pool_n} feature maps of {fmap_bytes / 1e9:.2f} GB cycled: every view's input "
                                  "is far larger than the 126 MB L2",
                            "parallelism": f"views sharded over {world} GPU(s), one {args.collective} of (num, den) at the end"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (7 if args.kernel != "simt" else 6),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "ms_views": ms_views, "allreduce_ms": ms_total - ms_views, "roofline": roofline,
                 "cpu_baseline": cpu}
         real_stdout.write(json.dumps(line) + "\n")

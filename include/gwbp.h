@@ -43,7 +43,7 @@ extern "C" {
 #endif
 
 #define GWBP_TILE 16
-#define GWBP_ABI_VERSION 9
+#define GWBP_ABI_VERSION 10
 
 /* kernel selection for gwbp_backproject_view and gwbp_render_view */
 #define GWBP_KERNEL_AUTO 0
@@ -55,6 +55,9 @@ extern "C" {
 #define GWBP_PREPARE_GSPLAT_EXACT 0 /* intersection list == gsplat-1.4.0 isect_tiles (bounding-square test) */
 #define GWBP_PREPARE_TILE_CULL 1    /* additionally drop (Gaussian, tile) pairs whose alpha stays < 1/255 on the
                                        whole tile: same accumulators, ~40 % shorter list to sort and walk */
+#define GWBP_PREPARE_SORTED_KEYS 2  /* force the emit + radix-sort binning (materialises the sorted tile ids in tkeys);
+                                       default is the sort-free counting path, which yields the same flatten_ids /
+                                       isect_offsets without them (tile_key_bytes == 0) */
 
 typedef struct gwbp_scene {
     int64_t n;        /* Gaussians */
@@ -88,6 +91,9 @@ typedef struct gwbp_ws_layout {
     size_t tvals0, tvals1;  /* int32  [cap] flatten_ids: packed index per intersection */
     size_t offsets;   /* int32  [tiles+1] isect_offsets (+ terminator = n_isects) */
     size_t stats;     /* int64  [16]    device counters */
+    size_t bin_counts; /* uint32 [chunks][tiles] per-chunk tile histograms -> exclusive prefixes (sort-free binning) */
+    size_t bin_seg;    /* uint32 [segments][tiles] */
+    size_t bin_tot;    /* uint32 [tiles]  intersections per tile */
     size_t cub_tmp;   /* scratch for scan / sort */
     size_t cub_tmp_bytes;
 } gwbp_ws_layout;
@@ -97,13 +103,16 @@ typedef struct gwbp_view_info {
     int64_t cap_isects; /* the capacity the workspace layout was computed with */
     int32_t tile_w, tile_h;
     int32_t sorted_buf; /* which of tkeys0/tkeys1, tvals0/tvals1 holds the sorted result */
-    int32_t tile_key_bytes; /* 2 or 4: element size of the tkeys buffers (16-bit keys when tiles <= 65536) */
+    int32_t tile_key_bytes; /* 0: sort-free binning, no tile keys materialised (flatten_ids in tvals0); 2 or 4: element
+                               size of the sorted tkeys buffer of the radix-sort path (16-bit keys when tiles <= 65536) */
 } gwbp_view_info;
 
 /* counters filled by gwbp_backproject_view when `stats` != NULL (device int64[4]):
  * [0] rows with non-zero weight  [1] (tile,Gaussian) entries walked  [2],[3] reserved */
 
 int gwbp_abi_version(void);
+/* kernels this library has launched so far in this process (bench.py reports the difference over its timed region) */
+unsigned long long gwbp_launch_count(void);
 const char *gwbp_last_error(void);
 
 int gwbp_workspace_layout(int64_t n, int32_t width, int32_t height, int64_t cap_isects, gwbp_ws_layout *out_host);
@@ -112,7 +121,7 @@ int gwbp_workspace_layout(int64_t n, int32_t width, int32_t height, int64_t cap_
 int gwbp_pack_scene(int64_t n, const float *means, const float *quats, const float *scales,
                     const float *opacities, void *geo, void *stream);
 
-/* project + bin + sort one camera into `ws`.  Synchronises `stream` once (intersection count). */
+/* project + depth-sort + tile-bin one camera into `ws`.  Synchronises `stream` once (intersection count). */
 int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam_host, void *ws, size_t ws_bytes,
                       int64_t cap_isects, int32_t flags, void *stream, gwbp_view_info *info_host);
 

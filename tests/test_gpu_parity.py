@@ -95,12 +95,15 @@ def test_native_library_is_loaded(gwbp):
 
 
 @pytest.mark.parametrize("cull", [False, True])
-def test_integer_stages_bit_exact(gwbp, coracle, case, cull):
-    """cull=False: gsplat-1.4.0 isect_tiles semantics; cull=True: the exact tile-culling extension."""
+@pytest.mark.parametrize("sorted_keys", [False, True])
+def test_integer_stages_bit_exact(gwbp, coracle, case, cull, sorted_keys):
+    """cull=False: gsplat-1.4.0 isect_tiles semantics; cull=True: the exact tile-culling extension.
+    sorted_keys=False: the hand-written sort-free tile binning (default); True: emit + radix sort (large-image fallback)."""
     sc, vm, K, _ = case
     scene = gwbp.PackedScene(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities))
     for v in range(vm.shape[0]):
-        view = gwbp.View(scene, gwbp.make_camera(vm[v], K, 96, 64), tile_cull=cull)
+        view = gwbp.View(scene, gwbp.make_camera(vm[v], K, 96, 64), tile_cull=cull, sorted_keys=sorted_keys)
+        assert view.info.tile_key_bytes == (2 if sorted_keys else 0)
         e = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, 96, 64, cull=cull).export()
         m = view.meta()
         gids = m["gaussian_ids"].cpu().numpy()
@@ -117,20 +120,25 @@ def test_integer_stages_bit_exact(gwbp, coracle, case, cull):
 
 def test_integer_stages_bit_exact_config_S_and_odd_sizes(gwbp, coracle):
     S = gwbp.scene
-    # the last case has 257 x 257 = 66 049 tiles: tile ids no longer fit the 16-bit sort keys (32-bit key path)
+    # (3000, 4112, 4100): 257 x 257 = 66 049 tiles -- beyond the sort-free path (radix-sort fallback) AND beyond
+    # 16-bit tile keys (32-bit key path); (40_000, 1920, 1080): config M's 8 160 tiles (6 binning warps per CTA);
+    # the 2 000-Gaussian scenes at large images hold rectangles of more than 64 tiles (warp-cooperative emission)
     for (n, W, H, seed) in [(50_000, 256, 256, 0), (20_000, 333, 211, 3), (5_000, 17, 15, 4), (2_000, 1297, 840, 5),
-                            (3_000, 4112, 4100, 6)]:
+                            (40_000, 1920, 1080, 8), (700, 2200, 1400, 9), (3_000, 4112, 4100, 6)]:
         sc = S.make_scene(n, seed)
         vm, K = S.make_cameras(2, W, H, seed)
         scene = gwbp.PackedScene(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities))
         for cull in (False, True):
-            view = gwbp.View(scene, gwbp.make_camera(vm[1], K, W, H), tile_cull=cull)
             e = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[1], K, W, H, cull=cull).export()
-            m = view.meta()
-            assert view.info.tile_key_bytes == (2 if view.info.tile_w * view.info.tile_h <= 65536 else 4)
-            assert np.array_equal(m["isect_ids"].cpu().numpy(), e["isect_ids"]), (n, W, H, cull)
-            assert np.array_equal(m["flatten_ids"].cpu().numpy(), e["flatten_ids"]), (n, W, H, cull)
-            assert np.array_equal(m["isect_offsets"].cpu().numpy()[0], e["isect_offsets"]), (n, W, H, cull)
+            for sorted_keys in (False, True):
+                view = gwbp.View(scene, gwbp.make_camera(vm[1], K, W, H), tile_cull=cull, sorted_keys=sorted_keys)
+                tiles = view.info.tile_w * view.info.tile_h
+                want = (2 if tiles <= 65536 else 4) if (sorted_keys or tiles > 12288) else 0
+                assert view.info.tile_key_bytes == want, (n, W, H, view.info.tile_key_bytes)
+                m = view.meta()
+                assert np.array_equal(m["isect_ids"].cpu().numpy(), e["isect_ids"]), (n, W, H, cull, sorted_keys)
+                assert np.array_equal(m["flatten_ids"].cpu().numpy(), e["flatten_ids"]), (n, W, H, cull, sorted_keys)
+                assert np.array_equal(m["isect_offsets"].cpu().numpy()[0], e["isect_offsets"]), (n, W, H, cull, sorted_keys)
 
 
 @pytest.mark.parametrize("kernel", ["simt", "auto"])
