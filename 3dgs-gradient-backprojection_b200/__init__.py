@@ -12,7 +12,7 @@ from . import splats  # noqa: F401  (torch-only data-contract helpers)
 from ._lib import LIB_PATH, KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC  # noqa: F401
 from .backproject import BackProjector, create_feature_field, DEN_EPS  # noqa: F401
 from .engine import PackedScene, View, cosine_mask, finalize, make_camera, fpack_bytes  # noqa: F401
-from .rasterization import rasterization  # noqa: F401
+from .rasterization import rasterization, cache_clear as rasterization_cache_clear  # noqa: F401
 from .sh import sh_colors  # noqa: F401
 from .segment import (click_mask3d, click_prompt, gaussian_scores, get_mask3d, render_features,  # noqa: F401
                       render_mask_2d)

@@ -48,6 +48,8 @@ SIGNATURES = {
     "gwbp_pack_scene": (C.c_int, [C.c_int64] + [C.c_void_p] * 6),
     "gwbp_view_prepare": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.c_void_p, C.c_size_t, C.c_int64,
                                     C.c_int32, C.c_void_p, C.POINTER(ViewInfo)]),
+    "gwbp_profile_enable": (C.c_int, [C.c_int]),
+    "gwbp_profile_read": (C.c_int, [C.POINTER(C.c_float), C.c_int]),
     "gwbp_debug_set_trace": (C.c_int, [C.c_void_p, C.c_size_t]),
     "gwbp_fpack_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "gwbp_pack_features": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
@@ -73,6 +75,9 @@ SIGNATURES = {
     "gwbp_mask2d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                               C.c_void_p]),
 }
+
+PROFILE_STAGES = ("project", "count_scan_and_readback", "compact", "depth_sort", "tile_binning", "feature_relayout",
+                  "backproject")
 
 _lib = None
 

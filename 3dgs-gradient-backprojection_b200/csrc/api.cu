@@ -32,6 +32,21 @@ int num_sms() {
 static unsigned long long g_launches = 0;  // kernels launched by this library (all threads; relaxed counter)
 void count_launches(int k) { __atomic_fetch_add(&g_launches, (unsigned long long)k, __ATOMIC_RELAXED); }
 
+// ---- optional per-stage timing (gwbp_profile_*): CUDA events recorded on the caller's stream at stage boundaries ----
+enum { kEvProject0 = 0, kEvProject1, kEvCounts, kEvCompact, kEvDepthSort, kEvBin, kEvPack0, kEvPack1, kEvBp0, kEvBp1, kNumEv };
+static bool g_prof_on = false;
+static cudaEvent_t g_ev[kNumEv];
+static bool g_ev_ready = false, g_ev_set[kNumEv] = {false};
+static void prof_mark(int i, cudaStream_t st) {
+    if (!g_prof_on) return;
+    if (!g_ev_ready) {
+        for (int k = 0; k < kNumEv; ++k) cudaEventCreate(&g_ev[k]);
+        g_ev_ready = true;
+    }
+    cudaEventRecord(g_ev[i], st);
+    g_ev_set[i] = true;
+}
+
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 static int tile_bits_for(int n_tiles) {
@@ -141,11 +156,14 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     info->tile_w = cd.tw; info->tile_h = cd.th;
     info->cap_isects = cap;
 
+    prof_mark(kEvProject0, st);
     if (int rc = launch_project(n, scene->geo, cd, w, st)) return rc;
+    prof_mark(kEvProject1, st);
     if (int rc = launch_scan(n, w, st)) return rc;
     unsigned long long totals = 0;
     GWBP_CUDA_OK(cudaMemcpyAsync(&totals, w.scan + n, sizeof(totals), cudaMemcpyDeviceToHost, st));
     GWBP_CUDA_OK(cudaStreamSynchronize(st));
+    prof_mark(kEvCounts, st);
     info->n_vis = (int64_t)(totals >> kVisShift);
     info->n_isects = (int64_t)(totals & kTileCountMask);
     if (info->n_isects > cap) {
@@ -154,15 +172,22 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
         return -2;
     }
     if (int rc = launch_compact(n, cd, w, st)) return rc;
+    prof_mark(kEvCompact, st);
     int dsel = 0;
     if (int rc = launch_depth_sort(info->n_vis, w, &dsel, st)) return rc;
+    prof_mark(kEvDepthSort, st);
     const unsigned *order = w.dvals[dsel];
     const int n_tiles = cd.tw * cd.th;
     if (bin_fast_supported(n_tiles) && !(flags & GWBP_PREPARE_SORTED_KEYS)) {
-        // hand-written stable counting sort fused with the emission: no (tile, index) intermediate, no radix sort
+        // hand-written stable counting sort fused with the emission: no (tile, index) intermediate, no radix sort;
+        // the depth-ordered prefix of the per-Gaussian hit counts cuts the list into chunks of equal work
+        if (int rc = launch_gather_counts(info->n_vis, order, w, st)) return rc;
+        if (int rc = launch_scan_counts(info->n_vis, w, st)) return rc;
         info->tile_key_bytes = 0;
         info->sorted_buf = 0;
-        return launch_bin(n, cd, order, w, cap, st);
+        const int rc = launch_bin(n, cd, order, w, cap, st);
+        prof_mark(kEvBin, st);
+        return rc;
     }
     // fallback for very large images (> kBinMaxTiles tiles) or when the caller asks for materialised tile keys:
     // emit (tile, index) pairs in depth order, stable CUB radix sort on the tile id, range finding
@@ -175,7 +200,32 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     const int tb = tile_bits_for(n_tiles);
     if (int rc = launch_tile_sort(info->n_isects, key16 && tb > 16 ? 16 : tb, w, key16, &sorted, st)) return rc;
     info->sorted_buf = sorted;
-    return launch_offsets(info->n_isects, n_tiles, w.tkeys[sorted], key16, w.offsets, st);
+    const int rc = launch_offsets(info->n_isects, n_tiles, w.tkeys[sorted], key16, w.offsets, st);
+    prof_mark(kEvBin, st);
+    return rc;
+}
+
+int gwbp_profile_enable(int on) {
+    g_prof_on = on != 0;
+    for (int k = 0; k < kNumEv; ++k) g_ev_set[k] = false;
+    return 0;
+}
+
+int gwbp_profile_read(float *ms_host, int n) {
+    static const int pairs[GWBP_PROFILE_STAGES][2] = {{kEvProject0, kEvProject1}, {kEvProject1, kEvCounts},
+                                                      {kEvCounts, kEvCompact},   {kEvCompact, kEvDepthSort},
+                                                      {kEvDepthSort, kEvBin},    {kEvPack0, kEvPack1},
+                                                      {kEvBp0, kEvBp1}};
+    GWBP_REQUIRE(ms_host && n >= GWBP_PROFILE_STAGES, "profile_read: need room for %d floats", GWBP_PROFILE_STAGES);
+    for (int i = 0; i < GWBP_PROFILE_STAGES; ++i) {
+        ms_host[i] = -1.0f;
+        const int a = pairs[i][0], b = pairs[i][1];
+        if (!g_ev_ready || !g_ev_set[a] || !g_ev_set[b]) continue;
+        GWBP_CUDA_OK(cudaEventSynchronize(g_ev[b]));
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, g_ev[a], g_ev[b]) == cudaSuccess) ms_host[i] = ms;
+    }
+    return 0;
 }
 
 unsigned long long gwbp_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
@@ -195,7 +245,10 @@ int gwbp_pack_features(int32_t width, int32_t height, const float *F, int64_t sH
     GWBP_REQUIRE(width > 0 && height > 0, "pack_features: bad image size");
     GWBP_REQUIRE(tc_supported(d), "pack_features: tcgen05 path does not support D=%d", d);
     GWBP_REQUIRE(F && fpack, "pack_features: NULL pointer");
-    return launch_fpack(width, height, F, sH, sW, sD, d, fpack, (cudaStream_t)stream);
+    prof_mark(kEvPack0, (cudaStream_t)stream);
+    const int rc = launch_fpack(width, height, F, sH, sW, sD, d, fpack, (cudaStream_t)stream);
+    prof_mark(kEvPack1, (cudaStream_t)stream);
+    return rc;
 }
 
 int gwbp_pack_features_lowres(int32_t width, int32_t height, const float *S, int32_t src_h, int32_t src_w, int64_t sH,
@@ -203,7 +256,10 @@ int gwbp_pack_features_lowres(int32_t width, int32_t height, const float *S, int
     GWBP_REQUIRE(width > 0 && height > 0, "pack_features_lowres: bad image size");
     GWBP_REQUIRE(tc_supported(d), "pack_features_lowres: tcgen05 path does not support D=%d", d);
     GWBP_REQUIRE(S && fpack, "pack_features_lowres: NULL pointer");
-    return launch_fpack_lowres(width, height, S, src_h, src_w, sH, sW, sD, nearest, d, fpack, (cudaStream_t)stream);
+    prof_mark(kEvPack0, (cudaStream_t)stream);
+    const int rc = launch_fpack_lowres(width, height, S, src_h, src_w, sH, sW, sD, nearest, d, fpack, (cudaStream_t)stream);
+    prof_mark(kEvPack1, (cudaStream_t)stream);
+    return rc;
 }
 
 int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws,
@@ -224,11 +280,17 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam, const
     if (k == GWBP_KERNEL_TC) {
         GWBP_REQUIRE(tc_supported(d), "tcgen05 back-projection does not support D=%d", d);
         GWBP_REQUIRE(fpack != nullptr, "tcgen05 back-projection needs the fpack buffer (gwbp_fpack_bytes)");
-        return launch_backproject_tc(t, F, sH, sW, sD, d, num, den, fpack, (kernel & GWBP_KERNEL_FPACK_READY) != 0,
-                                     (long long *)stats, st);
+        prof_mark(kEvBp0, st);
+        const int rc = launch_backproject_tc(t, F, sH, sW, sD, d, num, den, fpack, (kernel & GWBP_KERNEL_FPACK_READY) != 0,
+                                             (long long *)stats, st);
+        prof_mark(kEvBp1, st);
+        return rc;
     }
     GWBP_REQUIRE(k == GWBP_KERNEL_SIMT, "unknown kernel id %d", kernel);
-    return launch_backproject_simt(t, F, sH, sW, sD, d, num, den, (long long *)stats, st);
+    prof_mark(kEvBp0, st);
+    const int rc = launch_backproject_simt(t, F, sH, sW, sD, d, num, den, (long long *)stats, st);
+    prof_mark(kEvBp1, st);
+    return rc;
 }
 
 int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws, const gwbp_view_info *info,

@@ -450,37 +450,28 @@ int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev w
 // Tile binning without a sort (the default path; tiles <= kBinMaxTiles).
 //
 // After the depth sort, "sort the intersections by tile id, stably" is a COUNTING sort whose input never has
-// to exist: the depth-ordered Gaussians are cut into `chunks` contiguous pieces, ONE WARP PER CHUNK, and
+// to exist: the depth-ordered Gaussians are cut into `chunks` contiguous pieces of (nearly) equal intersection
+// count, ONE WARP PER CHUNK, and
 //   pass A  bin_count_kernel   : per-chunk histogram of tile hits (private shared-memory table, one counter/tile)
 //   scans   bin_scan*_kernel   : exclusive prefix over chunks for every tile + exclusive prefix over tiles
 //                                 (= isect_offsets) -- three small kernels over the [chunks x tiles] table
 //   pass B  bin_scatter_kernel : every warp re-walks its chunk IN DEPTH ORDER, 32 intersections per step, and
 //                                 writes each packed index straight to its final slot of flatten_ids
-// replace gather_counts + scan + emit + 2-pass radix sort + offsets (5 stages, 0.45 ms of a 2.8 ms view at config
-// G) and their (tile, index) intermediate (2 x 100 MB).  The result is bit-identical to the stable radix sort:
-// within a tile, entries keep emission order = (depth, packed index) order.
+// replace emit + 2-pass radix sort + offsets (0.40 ms of a 2.8 ms view at config G) and their (tile, index)
+// intermediate (2 x 100 MB).  The result is bit-identical to the stable radix sort: within a tile, entries keep
+// emission order = (depth, packed index) order.
 //
-// Order inside a step: lane j holds the j-th intersection of the step (Gaussians in depth order, a Gaussian's tiles
-// row-major), `match.any` on the tile id finds the lanes that hit the same tile, the rank among them is the lane
-// order, and the private running table (absolute positions, u32 per tile) is bumped once per tile by the last of
+// Pass A needs no order: lane = Gaussian, every lane walks the set bits of its own hit mask and bumps the warp's
+// table with shared-memory atomics.  Pass B needs emission order: the lanes first expand their Gaussians' hits into a
+// small per-warp staging list (lane g writes its tiles at its exclusive offset), which is then consumed 32 entries
+// per step; `match.any` on the tile id finds the lanes of a step that hit the same tile, the rank among them is the
+// lane order, and the private running table (absolute positions, u32 per tile) is bumped once per tile by the last of
 // them.  No atomics in pass B, so the output is deterministic.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int select_bit64(unsigned lo, unsigned hi, int k) {  // position of the k-th (0-based) set bit
-    int pos = 0;
-    unsigned m = lo;
-    int c = __popc(lo);
-    if (k >= c) { k -= c; pos = 32; m = hi; }
-    c = __popc(m & 0xffffu); if (k >= c) { k -= c; pos += 16; m >>= 16; }
-    c = __popc(m & 0xffu);   if (k >= c) { k -= c; pos += 8;  m >>= 8; }
-    c = __popc(m & 0xfu);    if (k >= c) { k -= c; pos += 4;  m >>= 4; }
-    c = __popc(m & 0x3u);    if (k >= c) { k -= c; pos += 2;  m >>= 2; }
-    c = (int)(m & 1u);       if (k >= c) { pos += 1; }
-    return pos;
-}
-
 struct BinArgs {
     CamDev cam;
     const unsigned *order;   // depth order -> packed index
+    const unsigned *base2;   // [n_vis + 1] exclusive prefix of the per-Gaussian hit counts in depth order
     const uint4 *erec;
     const float4 *grec;
     const int *radii;
@@ -496,20 +487,81 @@ struct BinArgs {
     int wpc;                 // warps (= chunks) per CTA: as many private tables as fit in shared memory, <= kBinWarps
 };
 
-__device__ __forceinline__ void bin_chunk_range(const BinArgs &a, int chunk, long long &lo, long long &hi) {
-    const long long n_vis = (long long)(a.scan[a.n] >> kVisShift);
-    long long per = (n_vis + a.chunks - 1) / a.chunks;
-    per = (per + 31) & ~31ll;
-    lo = (long long)chunk * per;
-    hi = lo + per;
-    if (lo > n_vis) lo = n_vis;
-    if (hi > n_vis) hi = n_vis;
+constexpr int kBinWarps = 8;     // warps (= chunks) per CTA, fewer when the per-warp tile table is large
+constexpr int kBinSeg = 32;      // chunks per scan segment
+constexpr int kBinStage = 1024;  // staging entries per warp in pass B (a group of 32 small rectangles has <= 2048 hits)
+
+// first depth-ordered Gaussian whose first intersection index is >= target (32-ary search by the whole warp)
+__device__ __forceinline__ long long bin_lower_bound(const unsigned *base2, long long n_vis, unsigned long long target) {
+    const int lane = threadIdx.x & 31;
+    long long lo = 0, hi = n_vis;  // answer in [lo, hi]; base2[n_vis] = total
+    while (hi - lo > 0) {
+        const long long span = hi - lo;
+        const long long step = (span + 31) / 32;
+        const long long probe = lo + (long long)lane * step;  // ascending in the lane index
+        const bool ge = probe >= hi || (unsigned long long)base2[probe] >= target;
+        const unsigned m = __ballot_sync(0xffffffffu, ge);   // monotone: 0..0 1..1
+        const int firstge = m ? (__ffs(m) - 1) : 32;
+        const long long nhi = firstge < 32 ? min(hi, lo + (long long)firstge * step) : hi;
+        const long long nlo = firstge > 0 ? lo + (long long)(firstge - 1) * step + 1 : lo;
+        if (firstge == 0) return lo;
+        lo = min(nlo, nhi);
+        hi = nhi;
+    }
+    return lo;
 }
 
-// Walks one chunk in emission order and calls f(tile, packed_index, active) with the whole warp converged, 32
-// consecutive intersections at a time.  Shared by the counting and the scattering pass so that they cannot disagree.
+// chunk c owns the Gaussians whose FIRST intersection index lies in [c*q, (c+1)*q), q = ceil(I / chunks)
+__device__ __forceinline__ void bin_chunk_range(const BinArgs &a, int chunk, long long &lo, long long &hi) {
+    const long long n_vis = (long long)(a.scan[a.n] >> kVisShift);
+    const unsigned long long total = a.base2[n_vis];
+    const unsigned long long q = (total + a.chunks - 1) / a.chunks;
+    if (q == 0) {  // no intersections at all
+        lo = hi = 0;
+        return;
+    }
+    lo = chunk == 0 ? 0 : bin_lower_bound(a.base2, n_vis, (unsigned long long)chunk * q);
+    hi = chunk == a.chunks - 1 ? n_vis : bin_lower_bound(a.base2, n_vis, (unsigned long long)(chunk + 1) * q);
+}
+
+// tile id of bit b of a small rectangle's hit mask; code = x0 | y0 << 12 | (bw - 1) << 24
+__device__ __forceinline__ int bin_tile_of_bit(unsigned code, int b, int tw) {
+    const int bw = (int)((code >> 24) & 0x3fu) + 1;
+    const int row = (b * ((65536 + bw - 1) / bw)) >> 16;  // == b / bw for b < 64, bw <= 64
+    return ((int)((code >> 12) & 0xfffu) + row) * tw + (int)(code & 0xfffu) + (b - row * bw);
+}
+
+// one rectangle of more than 64 tiles, re-tested and emitted by the whole warp, 32 tiles per step in row-major order
 template <typename F>
-__device__ __forceinline__ void bin_walk_chunk(const BinArgs &a, long long lo, long long hi, F f) {
+__device__ __forceinline__ void bin_walk_big(const BinArgs &a, int src, int pos, F f) {
+    const int lane = threadIdx.x & 31;
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    CullGauss cg = {};
+    if (lane == src) {
+        const float4 r0 = a.grec[2 * (long long)pos], r1 = a.grec[2 * (long long)pos + 1];
+        tile_rect(r0.x, r0.y, a.radii[pos], a.cam.tw, a.cam.th, x0, x1, y0, y1);
+        if (a.cam.cull) cg = cull_setup(r0.x, r0.y, r1.x, r1.y, r1.z, r0.z);
+    }
+    const CullGauss sg = shfl_cull(cg, src);
+    const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
+    const int sbw = __shfl_sync(0xffffffffu, x1 - x0, src);
+    const int snt = __shfl_sync(0xffffffffu, (y1 - y0) * (x1 - x0), src);
+    const int spos = __shfl_sync(0xffffffffu, pos, src);
+    for (int k0 = 0; k0 < snt; k0 += 32) {
+        const int k = k0 + lane;
+        const int ty = sy0 + k / sbw, tx = sx0 + k % sbw;
+        const bool hit = (k < snt) && (!a.cam.cull || tile_hit(sg, tx, ty, a.cam.W, a.cam.H));
+        f(ty * a.cam.tw + tx, spos, hit);
+    }
+}
+
+// Walks one chunk and calls f(tile, packed_index, active) for every intersection.
+//   kOrdered = false (pass A): any order, f is called divergently (lane = Gaussian);
+//   kOrdered = true  (pass B): emission order, f is called with the whole warp converged, 32 consecutive
+//                              intersections per call; `stage` = kBinStage words of shared memory of this warp.
+// Shared by the counting and the scattering pass so that they cannot disagree about which hits exist.
+template <bool kOrdered, typename F>
+__device__ __forceinline__ void bin_walk_chunk(const BinArgs &a, long long lo, long long hi, unsigned *stage, F f) {
     const int lane = threadIdx.x & 31;
     // the (order -> erec) gather of group g+1 is issued before group g is processed: two dependent DRAM round trips
     // per 32 Gaussians would otherwise sit on the warp's serial path
@@ -530,74 +582,66 @@ __device__ __forceinline__ void bin_walk_chunk(const BinArgs &a, long long lo, l
             er_n = a.erec[pos_n];
         }
         const bool big = vis && (er.z & kErecBig);
-        const int cnt = (vis && !big) ? __popc(er.x) + __popc(er.y) : 0;
         unsigned bigmask = __ballot_sync(0xffffffffu, big);
+        if (!kOrdered) {
+            if (vis && !big) {
+                unsigned long long mk = ((unsigned long long)er.y << 32) | er.x;
+                while (mk) {
+                    const int b = __ffsll((long long)mk) - 1;
+                    mk &= mk - 1;
+                    f(bin_tile_of_bit(er.z, b, a.cam.tw), pos, true);
+                }
+            }
+            __syncwarp();  // reconverge before the warp-cooperative part
+            while (bigmask) {
+                const int src = __ffs(bigmask) - 1;
+                bigmask &= bigmask - 1;
+                bin_walk_big(a, src, pos, f);
+            }
+            continue;
+        }
+        const int cnt = (vis && !big) ? __popc(er.x) + __popc(er.y) : 0;
         int first = 0;  // lanes [first, stop) form a run of small rectangles, lane `stop` (if < 32) is a big one
         while (first < 32) {
             const int stop = bigmask ? (__ffs(bigmask) - 1) : 32;
             // ---- run of small rectangles: inclusive prefix of their hit counts over the run's lanes
-            int incl = (lane >= first && lane < stop) ? cnt : 0;
+            const bool in_run = lane >= first && lane < stop;
+            int incl = in_run ? cnt : 0;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
-            for (int t0 = 0; t0 < total; t0 += 32) {
-                const int t = t0 + lane;
-                const bool act = t < total;
-                int l = 0, h = 31;  // owner = first lane whose inclusive count exceeds t
-#pragma unroll
-                for (int it = 0; it < 5; ++it) {
-                    const int mid = (l + h) >> 1;
-                    const int v = __shfl_sync(0xffffffffu, incl, mid);
-                    if (v > t) h = mid; else l = mid + 1;
+            const int excl = incl - (in_run ? cnt : 0);
+            for (int w0 = 0; w0 < total; w0 += kBinStage) {  // one window unless the group has > kBinStage hits
+                if (in_run && cnt) {
+                    unsigned long long mk = ((unsigned long long)er.y << 32) | er.x;
+                    int e = excl - w0;
+                    while (mk && e < kBinStage) {
+                        const int b = __ffsll((long long)mk) - 1;
+                        mk &= mk - 1;
+                        if (e >= 0) stage[e] = (unsigned)bin_tile_of_bit(er.z, b, a.cam.tw) | ((unsigned)lane << 16);
+                        ++e;
+                    }
                 }
-                const int own = act ? l : 0;
-                const int oincl = __shfl_sync(0xffffffffu, incl, own), ocnt = __shfl_sync(0xffffffffu, cnt, own);
-                const unsigned mlo = __shfl_sync(0xffffffffu, er.x, own), mhi = __shfl_sync(0xffffffffu, er.y, own);
-                const unsigned code = __shfl_sync(0xffffffffu, er.z, own);
-                const int opos = __shfl_sync(0xffffffffu, pos, own);
-                int tile = 0;
-                if (act) {
-                    const int k = t - (oincl - ocnt);
-                    const int b = select_bit64(mlo, mhi, k);
-                    const int bw = (int)((code >> 24) & 0x3fu) + 1;
-                    const int row = (int)(((float)b + 0.5f) / (float)bw);  // b / bw for small non-negative ints
-                    tile = ((int)((code >> 12) & 0xfffu) + row) * a.cam.tw + (int)(code & 0xfffu) + (b - row * bw);
+                __syncwarp();
+                const int lim = min(total - w0, kBinStage);
+                for (int t0 = 0; t0 < lim; t0 += 32) {
+                    const bool act = t0 + lane < lim;
+                    const unsigned v = act ? stage[t0 + lane] : 0u;
+                    const int opos = __shfl_sync(0xffffffffu, pos, (int)(v >> 16));
+                    f((int)(v & 0xffffu), opos, act);
                 }
-                f(tile, opos, act);
+                __syncwarp();
             }
             if (stop >= 32) break;
-            // ---- one big rectangle (> 64 tiles), re-tested and emitted by the whole warp, 32 tiles per step
-            {
-                const int src = stop;
-                int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-                CullGauss cg = {};
-                if (lane == src) {
-                    const float4 r0 = a.grec[2 * (long long)pos], r1 = a.grec[2 * (long long)pos + 1];
-                    tile_rect(r0.x, r0.y, a.radii[pos], a.cam.tw, a.cam.th, x0, x1, y0, y1);
-                    if (a.cam.cull) cg = cull_setup(r0.x, r0.y, r1.x, r1.y, r1.z, r0.z);
-                }
-                const CullGauss sg = shfl_cull(cg, src);
-                const int sx0 = __shfl_sync(0xffffffffu, x0, src), sy0 = __shfl_sync(0xffffffffu, y0, src);
-                const int sbw = __shfl_sync(0xffffffffu, x1 - x0, src);
-                const int snt = __shfl_sync(0xffffffffu, (y1 - y0) * (x1 - x0), src);
-                const int spos = __shfl_sync(0xffffffffu, pos, src);
-                for (int k0 = 0; k0 < snt; k0 += 32) {
-                    const int k = k0 + lane;
-                    const int ty = sy0 + k / sbw, tx = sx0 + k % sbw;
-                    const bool hit = (k < snt) && (!a.cam.cull || tile_hit(sg, tx, ty, a.cam.W, a.cam.H));
-                    f(ty * a.cam.tw + tx, spos, hit);
-                }
-            }
+            bin_walk_big(a, stop, pos, f);
             bigmask &= bigmask - 1;
             first = stop + 1;
         }
     }
 }
-
-constexpr int kBinWarps = 8;  // warps (= chunks) per CTA, fewer when the per-warp tile table is large
 
 __global__ void __launch_bounds__(32 * kBinWarps) bin_count_kernel(const BinArgs a) {
     extern __shared__ unsigned bin_tab[];
@@ -609,16 +653,14 @@ __global__ void __launch_bounds__(32 * kBinWarps) bin_count_kernel(const BinArgs
     if (chunk < a.chunks) {
         long long lo, hi;
         bin_chunk_range(a, chunk, lo, hi);
-        bin_walk_chunk(a, lo, hi, [&](int tile, int, bool act) {
-            if (act) atomicAdd(&tab[tile], 1u);  // several lanes of a step may hit the same tile
+        bin_walk_chunk<false>(a, lo, hi, nullptr, [&](int tile, int, bool act) {
+            if (act) atomicAdd(&tab[tile], 1u);  // lanes may hit the same tile at the same time
         });
     }
     __syncwarp();
     unsigned *dst = a.counts + (size_t)chunk * a.tiles_pad;  // rows chunks..chunks_pad-1 are written as zeros
     for (int t = lane; t < a.tiles_pad; t += 32) dst[t] = tab[t];
 }
-
-constexpr int kBinSeg = 32;  // chunks per scan segment
 
 // counts[c][t] -> exclusive prefix over the 32 chunks of its segment (in place); segsum[s][t] = segment total
 __global__ void __launch_bounds__(256) bin_scan1_kernel(const BinArgs a) {
@@ -696,11 +738,12 @@ __global__ void __launch_bounds__(32 * kBinWarps) bin_scatter_kernel(const BinAr
     bin_chunk_range(a, chunk, lo, hi);
     if (lo >= hi) return;
     unsigned *tab = bin_tab + (size_t)warp * a.tiles_pad;
+    unsigned *stage = bin_tab + (size_t)a.wpc * a.tiles_pad + (size_t)warp * kBinStage;
     const unsigned *cbase = a.counts + (size_t)chunk * a.tiles_pad;
     const unsigned *sbase = a.segsum + (size_t)(chunk / kBinSeg) * a.tiles_pad;
     for (int t = lane; t < a.tiles; t += 32) tab[t] = (unsigned)a.offsets[t] + sbase[t] + cbase[t];  // absolute slots
     __syncwarp();
-    bin_walk_chunk(a, lo, hi, [&](int tile, int pos, bool act) {
+    bin_walk_chunk<true>(a, lo, hi, stage, [&](int tile, int pos, bool act) {
         const unsigned key = act ? (unsigned)tile : (0x80000000u | (unsigned)lane);  // inactive lanes match nobody
         const unsigned peers = __match_any_sync(0xffffffffu, key);
         const int rank = __popc(peers & ((1u << lane) - 1u)), npeers = __popc(peers);
@@ -717,7 +760,7 @@ __global__ void __launch_bounds__(32 * kBinWarps) bin_scatter_kernel(const BinAr
 size_t bin_table_bytes(int n_tiles, int *chunks_pad, int *tiles_pad, int *nseg, int *chunks, int *wpc) {
     const int tp = (n_tiles + 31) & ~31;
     const size_t tab = (size_t)tp * sizeof(unsigned);
-    int w = (int)((size_t)(200 * 1024) / tab);
+    int w = (int)((size_t)(200 * 1024) / (tab + kBinStage * sizeof(unsigned)));
     if (w > kBinWarps) w = kBinWarps;
     if (w < 1) w = 1;
     const int ch = num_sms() * w;  // one CTA per SM
@@ -735,18 +778,18 @@ bool bin_fast_supported(int n_tiles) { return n_tiles >= 1 && n_tiles <= kBinMax
 int launch_bin(int64_t n, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, cudaStream_t st) {
     BinArgs a;
     a.cam = cam;
-    a.order = order; a.erec = ws.erec; a.grec = ws.grec; a.radii = ws.radii; a.scan = ws.scan;
+    a.order = order; a.base2 = ws.base2; a.erec = ws.erec; a.grec = ws.grec; a.radii = ws.radii; a.scan = ws.scan;
     a.n = n;
     a.counts = ws.bin_counts; a.segsum = ws.bin_seg; a.totals = ws.bin_tot;
     a.offsets = ws.offsets; a.flatten = ws.tvals[0]; a.cap = cap;
     a.tiles = cam.tw * cam.th;
     int chunks_pad = 0;
     const size_t tab = bin_table_bytes(a.tiles, &chunks_pad, &a.tiles_pad, &a.nseg, &a.chunks, &a.wpc);
-    const size_t smem = tab * a.wpc;
-    GWBP_CUDA_OK(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GWBP_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem_a = tab * a.wpc, smem_b = (tab + kBinStage * sizeof(unsigned)) * a.wpc;
+    GWBP_CUDA_OK(cudaFuncSetAttribute(bin_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    GWBP_CUDA_OK(cudaFuncSetAttribute(bin_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
     const unsigned ctas = (unsigned)(chunks_pad / a.wpc);
-    bin_count_kernel<<<ctas, 32 * a.wpc, smem, st>>>(a);
+    bin_count_kernel<<<ctas, 32 * a.wpc, smem_a, st>>>(a);
     count_launches(1);
     bin_scan1_kernel<<<dim3((unsigned)((a.tiles_pad + 255) / 256), (unsigned)a.nseg), 256, 0, st>>>(a);
     count_launches(1);
@@ -754,7 +797,7 @@ int launch_bin(int64_t n, const CamDev &cam, const unsigned *order, WsDev ws, in
     count_launches(1);
     bin_scan3_kernel<<<1, 1024, 0, st>>>(a);
     count_launches(1);
-    bin_scatter_kernel<<<ctas, 32 * a.wpc, smem, st>>>(a);
+    bin_scatter_kernel<<<ctas, 32 * a.wpc, smem_b, st>>>(a);
     count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;

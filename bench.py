@@ -11,9 +11,12 @@ rank back-projects its own K views (weak scaling, views r, r+N, ...) into its ow
 accumulators and ONE all-reduce of (num, den) closes the timed region.
 
 Prints ONE JSON line (rank 0).  Keys follow the driver contract; `roofline` describes the fused
-kernel (HBM-bound: algorithmic bytes / CUDA-event time), `cpu_baseline` the oracle port on host
-cores, `e2e` the same metric through the public API with HOST feature maps (H2D copy + D2H result
-read inside the timed region).
+kernel (HBM-bound: algorithmic bytes / CUDA-event time) and carries `stages` (every stage of a view:
+ms by CUDA events, algorithmic bytes, fraction of the measured HBM peak) and `view` (the whole view
+against SURVEY.md §8d's byte count); `cpu_baseline` the oracle port on host cores, `e2e` the same
+metric through the public API with HOST feature maps (H2D copy + D2H result read inside the timed
+region); `shim` the cost of the reference's own loop (3 x rasterization + 2 x backward per view)
+on the drop-in operator.
 """
 from __future__ import annotations
 
@@ -39,6 +42,20 @@ def _peaks():
         return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 0))), "measured"
     except Exception:
         return 6650.0, 1400.0, "fallback"
+
+
+def _source_sha() -> str:
+    """Identity of the CUDA sources: profiles/*_traffic.json is only trusted for the code it was captured from
+    (the GPU box has no .git, so the commit hash is not available there)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "3dgs-gradient-backprojection_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -100,6 +117,7 @@ def _cpu_views(cfg, n_views_max: float, budget_s: float, seed=0):
     from oracle import c_oracle
 
     c_oracle.build()
+    c_oracle.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: ask for every host core
     S = gwbp.scene
     sc = S.make_scene(cfg["n"], seed)
     vm, K = S.make_cameras(cfg["views"], cfg["width"], cfg["height"], seed)
@@ -117,6 +135,49 @@ def _cpu_views(cfg, n_views_max: float, budget_s: float, seed=0):
         if time.perf_counter() - t0 > budget_s:
             break
     return done, time.perf_counter() - t0, c_oracle.num_threads()
+
+
+def _time_shim(gwbp, torch, dev, sc, vm, K, W, H, d, pool, n_views):
+    """The reference's loop body, unmodified in shape (backproject.py:115-151): rasterization(colors_feats[N,D]) ->
+    (out*feats).sum().backward() -> clone/zero_ -> rasterization(colors_feats_0[N,3]) -> out.sum().backward() ->
+    accumulate.  INTEGRATION.md §1's zero-edit path: what it costs per view on this engine."""
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    means, quats, scales, opac = t(sc.means), t(sc.quats), t(sc.scales), t(sc.opacities)
+    Kt = t(K)[None]
+    n = sc.n
+    gaussian_features = torch.zeros(n, d, device=dev)
+    gaussian_denoms = torch.ones(n, device=dev) * 1e-12
+    colors_feats = torch.zeros(n, d, device=dev, requires_grad=True)
+    colors_feats_0 = torch.zeros(n, 3, device=dev, requires_grad=True)
+
+    def one(v):
+        nonlocal gaussian_features, gaussian_denoms
+        viewmat = t(vm[v])[None]
+        feats = pool[v % len(pool)]
+        out, _, _ = gwbp.rasterization(means, quats, scales, opac, colors_feats, viewmat, Kt, width=W, height=H)
+        (out[0] * feats).sum().backward()
+        copy = colors_feats.grad.clone()
+        colors_feats.grad.zero_()
+        out0, _, _ = gwbp.rasterization(means, quats, scales, opac, colors_feats_0, viewmat, Kt, width=W, height=H)
+        out0[0].sum().backward()
+        gaussian_features += copy
+        gaussian_denoms += colors_feats_0.grad[:, 0]
+        colors_feats_0.grad.zero_()
+        del out, out0, copy
+
+    one(0)  # warm-up (allocations, lazy module loads)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for v in range(1, 1 + n_views):
+        one(v)
+    torch.cuda.synchronize(dev)
+    secs = (time.perf_counter() - t0) / n_views
+    gwbp.rasterization_cache_clear()
+    return {"ms_per_view": 1e3 * secs, "views_per_s": 1.0 / secs, "views": n_views,
+            "what": "2 x rasterization(colors=[N,D] / [N,3] zeros, requires_grad) + 2 x backward + clone/zero_/+= per view "
+                    "(backproject.py:115-151 verbatim) on the drop-in operator; projection + binning shared between the "
+                    "two calls of a view (scene/view cache); the RGB render that feeds the encoder is excluded as in every "
+                    "BASELINE config"}
 
 
 def run_reference(args, cfg):
@@ -178,6 +239,7 @@ def run_ours(args, cfg):
     pool_n = max(1, min(V, args.pool))
     pool = [S.make_feature_map_torch(v, d, H, W, dev, 0, enc_res=enc) for v in range(pool_n)]
     fmap_bytes = H * W * d * 4
+    fpack_dev_bytes = gwbp.fpack_bytes(W, H, d)
     my_view = lambda i: (rank + i * world) % V  # noqa: E731
 
     low_pool = None
@@ -301,6 +363,32 @@ def run_ours(args, cfg):
         except Exception as ex:  # never let the extra measurement break the contract line
             e2e["lowres_variant"] = {"error": str(ex)[:200]}
 
+    # ---- per-stage timing (separate, untimed loop: CUDA events at the stage boundaries inside the library) --------
+    stage_ms = None
+    if rank == 0 and args.stage_views > 0:
+        import ctypes as C
+
+        lib = gwbp._lib.lib()
+        nst = len(gwbp._lib.PROFILE_STAGES)
+        acc = [0.0] * nst
+        buf = (C.c_float * nst)()
+        lib.gwbp_profile_enable(1)
+        for i in range(args.stage_views):
+            step(args.warmup + i)
+            gwbp._lib.check(lib.gwbp_profile_read(buf, nst), "gwbp_profile_read")  # waits for this view
+            for j in range(nst):
+                acc[j] += max(0.0, float(buf[j]))
+        lib.gwbp_profile_enable(0)
+        stage_ms = [a / args.stage_views for a in acc]
+
+    # ---- zero-edit shim: the reference's own loop body (backproject.py:115-151) on the drop-in `rasterization` ----
+    shim = None
+    if rank == 0 and args.shim_views > 0:
+        try:
+            shim = _time_shim(gwbp, torch, dev, sc, vm, K, W, H, d, pool, args.shim_views)
+        except Exception as ex:  # the extra measurement never breaks the contract line
+            shim = {"error": str(ex)[:200]}
+
     if rank == 0:
         hbm, tf, src = _peaks()
         k = max(1, args.steps)
@@ -309,18 +397,52 @@ def run_ours(args, cfg):
         # + the feature map once + one (D+1)-float accumulator update per non-zero row
         algo_bytes = walked * 36.0 + fmap_bytes + rows * (d + 1) * 4.0
         achieved = algo_bytes / (ms_kernel * 1e-3) / 1e9 if ms_kernel > 0 else 0.0
-        traffic = None
-        try:  # dram__bytes_read+write of the same kernel from the committed ncu --set full capture
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                traffic = json.load(f).get(f"{args.config}:{'simt' if args.kernel == 'simt' else 'tc'}")
+        # DRAM traffic / tensor-pipe share of the dominant kernel come from an `ncu --set full` capture and are only
+        # reported when that capture was taken from THESE sources (profiles/r02_traffic.json records their hash)
+        traffic = tensor_pct = None
+        traffic_note = "no capture of these sources"
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+                cap = json.load(f)
+            ent = cap.get(f"{args.config}:{args.features}:{'simt' if args.kernel == 'simt' else 'tc'}")
+            if ent and cap.get("source_sha") == _source_sha():
+                traffic, tensor_pct = ent.get("traffic"), ent.get("tensor_pipe_pct")
+                traffic_note = f"ncu --set full capture of source {cap['source_sha']} ({ent.get('file', '')})"
+            elif ent:
+                traffic_note = f"capture is of source {cap.get('source_sha')}, this is {_source_sha()}: not reported"
         except Exception:
             pass
+        n_g, n_vis, n_is = cfg["n"], last.n_vis, last.n_isects
+        tiles = ((W + 15) // 16) * ((H + 15) // 16)
+        # B_view = 44 N + 40 n_vis + 68 I + HWD s_F + 4 R (D+1)   (I = the list this engine builds)
+        view_bytes = 44.0 * n_g + 40.0 * n_vis + 68.0 * n_is + fmap_bytes + 4.0 * rows * (d + 1)
+        ms_view = ms_views / args.steps
+        view = {"algorithmic_bytes": view_bytes, "ms": ms_view, "achieved": view_bytes / (ms_view * 1e-3) / 1e9,
+                "formula": "SURVEY 8d: 44N + 40n_vis + 68I + 4HWD + 4R(D+1), measured n_vis, I, R"}
+        view["frac"] = view["achieved"] / hbm
+        stages = None
+        if stage_ms is not None:
+            low_bytes = (enc * enc * d * 4.0) if args.features == "lowres" else float(fmap_bytes)
+            sb = {"project": 44.0 * n_g + 40.0 * n_vis,                  # SURVEY 8d "Project"
+                  "count_scan_and_readback": 16.0 * n_g,                 # 8-byte counters read + prefix written
+                  "compact": 16.0 * n_g + 96.0 * n_vis,                  # counters + records in, packed records + sort input out
+                  "depth_sort": 16.0 * n_vis,                            # one logical pass over (key, value) pairs
+                  "tile_binning": 24.0 * n_is + 4.0 * tiles,             # SURVEY 8d "Bin+sort": 12 I written + 12 I read
+                  "feature_relayout": low_bytes + float(fpack_dev_bytes),  # map read + packed operand written
+                  "backproject": algo_bytes}
+            stages = []
+            for name, ms in zip(gwbp._lib.PROFILE_STAGES, stage_ms):
+                ach = sb[name] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+                stages.append({"stage": name, "ms": ms, "algorithmic_bytes": sb[name], "achieved_gbs": ach,
+                               "frac": ach / hbm})
+            stages.append({"stage": "sum", "ms": sum(stage_ms), "note": f"{args.stage_views} views, CUDA events at the stage "
+                           "boundaries inside the library (one sync per view to read them)"})
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                    "traffic": traffic, "peak_source": src,
+                    "traffic": traffic, "tensor_pipe_pct": tensor_pct, "traffic_source": traffic_note, "peak_source": src,
                     "kernel": "bp_simt_kernel" if args.kernel == "simt" else "bp_tc_kernel (fused composite + tcgen05 contraction + accumulate)",
                     "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": algo_bytes,
                     "rows_nonzero_per_view": rows, "entries_walked_per_view": walked,
-                    "n_vis": last.n_vis, "n_isects": last.n_isects}
+                    "n_vis": last.n_vis, "n_isects": last.n_isects, "stages": stages, "view": view}
         cpu = None
         if world == 1 and args.cpu_budget > 0:
             done, secs, threads = _cpu_views(cfg, 1e9, args.cpu_budget)
@@ -330,13 +452,15 @@ def run_ours(args, cfg):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"config {args.config}", **cfg, "kernel": args.kernel, "features": args.features,
+                "config": {"workload": f"config {args.config}" + (" --features lowres (encoder-resolution maps, fused upsample)"
+                                                                  if args.features == "lowres" else ""),
+                           **cfg, "kernel": args.kernel, "features": args.features,
                            "l2": f"{pool_n} feature maps of {fmap_bytes / 1e9:.2f} GB cycled: every view's input "
                                  "is far larger than the 126 MB L2",
                            "parallelism": f"views sharded over {world} GPU(s), one {args.collective} of (num, den) at the end"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "ms_views": ms_views, "allreduce_ms": ms_total - ms_views, "roofline": roofline,
-                "cpu_baseline": cpu}
+                "ms_views": ms_views, "exchange_ms": ms_total - ms_views, "exchange": args.collective if world > 1 else None,
+                "roofline": roofline, "cpu_baseline": cpu, "shim": shim}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     if world > 1:
@@ -355,8 +479,13 @@ def main():
     ap.add_argument("--features", default="full", choices=["full", "lowres"],
                     help="full: [H,W,D] map resident in HBM (the BASELINE metric); lowres: encoder-resolution map, "
                          "bilinear upsample fused into the feature re-layout (not the headline)")
-    ap.add_argument("--collective", default="allreduce", choices=["allreduce", "reduce_scatter"],
-                    help="closing exchange of (num, den) for N > 1")
+    ap.add_argument("--collective", default="reduce_scatter", choices=["allreduce", "reduce_scatter"],
+                    help="closing exchange of (num, den) for N > 1: reduce_scatter (default; every rank ends with the "
+                         "global sums of ITS rows, finalises and saves them -- half the NVLink volume) or allreduce "
+                         "(every rank ends with the full field)")
+    ap.add_argument("--stage-views", type=int, default=6, help="views of the per-stage profiling loop (0 = skip)")
+    ap.add_argument("--shim-views", type=int, default=2,
+                    help="views of the zero-edit shim loop (3 x rasterization + 2 x backward per view; 0 = skip)")
     ap.add_argument("--d", type=int, default=0, help="override the config's feature width (experiments only)")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-oracle work (0 = skip)")

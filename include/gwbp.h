@@ -129,6 +129,15 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam_host, void
  * back-projection launches records (role, event, batch, chunk, clock64) tuples into it; NULL disables. */
 int gwbp_debug_set_trace(void *buf, size_t bytes);
 
+/* PROFILING ONLY (bench.py `roofline.stages`): while enabled, CUDA events are recorded on the caller's stream at the
+ * stage boundaries of gwbp_view_prepare / gwbp_pack_features* / gwbp_backproject_view (process-wide, one device).
+ * gwbp_profile_read waits for the last view and returns the milliseconds of its stages (-1 = stage not run):
+ *   [0] project  [1] count scan + host read-back of the totals (the one host sync)  [2] compact  [3] depth sort
+ *   [4] tile binning  [5] feature re-layout  [6] fused back-projection kernel */
+#define GWBP_PROFILE_STAGES 7
+int gwbp_profile_enable(int on);
+int gwbp_profile_read(float *ms_host, int n);
+
 /* bytes of the packed bf16 feature buffer the GWBP_KERNEL_TC path needs (0 if D unsupported) */
 size_t gwbp_fpack_bytes(int32_t width, int32_t height, int32_t d);
 

@@ -37,6 +37,7 @@ def lib():
         L.orc_covar.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_view_margins.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -51,6 +52,11 @@ def _f32(a):
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP team size of the oracle (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().orc_set_num_threads(int(n))
 
 
 class View:

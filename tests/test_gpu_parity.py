@@ -177,7 +177,7 @@ def test_tensor_core_and_cuda_core_kernels_flip_identically(gwbp):
     feats = [S.make_feature_map_np(v, c["d"], c["height"], c["width"], 0) for v in range(c["views"])]
     a = _gpu_job(gwbp, sc, vm, K, c["width"], c["height"], feats, c["d"], "simt")
     b = _gpu_job(gwbp, sc, vm, K, c["width"], c["height"], feats, c["d"], "tc")
-    assert a.stats() == b.stats()
+    assert a.stats()["rows_nonzero"] == b.stats()["rows_nonzero"]  # (entries_walked counts whole batches: 32 vs 128)
     assert torch.equal(a.den > 1e-12, b.den > 1e-12)
     assert torch.allclose(a.den, b.den, rtol=2e-6, atol=1e-12)  # fp32 sums of identical terms in a different order
     seen = a.den > 1e-6
