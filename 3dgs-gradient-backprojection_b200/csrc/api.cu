@@ -181,7 +181,7 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     if (bin_fast_supported(n_tiles) && !(flags & GWBP_PREPARE_SORTED_KEYS)) {
         // hand-written stable counting sort fused with the emission: no (tile, index) intermediate, no radix sort;
         // the depth-ordered prefix of the per-Gaussian hit counts cuts the list into chunks of equal work
-        if (int rc = launch_gather_counts(info->n_vis, order, w, st)) return rc;
+        if (int rc = launch_gather_counts(info->n_vis, order, w, true, st)) return rc;
         if (int rc = launch_scan_counts(info->n_vis, w, st)) return rc;
         info->tile_key_bytes = 0;
         info->sorted_buf = 0;
@@ -191,7 +191,7 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     }
     // fallback for very large images (> kBinMaxTiles tiles) or when the caller asks for materialised tile keys:
     // emit (tile, index) pairs in depth order, stable CUB radix sort on the tile id, range finding
-    if (int rc = launch_gather_counts(info->n_vis, order, w, st)) return rc;
+    if (int rc = launch_gather_counts(info->n_vis, order, w, false, st)) return rc;
     if (int rc = launch_scan_counts(info->n_vis, w, st)) return rc;
     const bool key16 = n_tiles <= 65536;
     info->tile_key_bytes = key16 ? 2 : 4;

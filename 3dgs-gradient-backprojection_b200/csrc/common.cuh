@@ -106,7 +106,7 @@ int launch_pack_scene(int64_t n, const float *means, const float *quats, const f
                       const float *opac, void *geo, cudaStream_t st);
 int launch_project(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cudaStream_t st);
 int launch_compact(int64_t n, const CamDev &cam, WsDev ws, cudaStream_t st);
-int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, cudaStream_t st);
+int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, bool gather_erec, cudaStream_t st);
 int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, bool key16, cudaStream_t st);
 size_t binning_tmp_bytes(int64_t n, int64_t cap);
 int launch_scan(int64_t n, WsDev ws, cudaStream_t st);

@@ -345,15 +345,24 @@ int launch_compact(int64_t n, const CamDev &cam, WsDev ws, cudaStream_t st) {
     return 0;
 }
 
+// per-Gaussian hit counts in DEPTH order (input of the scan that positions / balances the binning) and, for the
+// sort-free binning, the 16-byte emission records gathered into depth order as well (erec_sorted may be NULL): the
+// binning warps then stream them with coalesced loads instead of chasing order[] -> erec[] one group at a time
 __global__ void __launch_bounds__(256) gather_counts_kernel(int64_t n_vis, const unsigned *__restrict__ order,
-                                                            const int *__restrict__ tpg, unsigned *__restrict__ out) {
+                                                            const int *__restrict__ tpg, unsigned *__restrict__ out,
+                                                            const uint4 *__restrict__ erec, uint4 *__restrict__ erec_sorted) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_vis) out[i] = (unsigned)tpg[order[i]];
+    if (i < n_vis) {
+        const unsigned pos = order[i];
+        out[i] = (unsigned)tpg[pos];
+        if (erec_sorted) erec_sorted[i] = erec[pos];
+    }
     if (i == n_vis) out[i] = 0u;
 }
 
-int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, cudaStream_t st) {
-    gather_counts_kernel<<<(unsigned)((n_vis + 1 + 255) / 256), 256, 0, st>>>(n_vis, order, ws.tiles_per_gauss, ws.cnt2);
+int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, bool gather_erec, cudaStream_t st) {
+    gather_counts_kernel<<<(unsigned)((n_vis + 1 + 255) / 256), 256, 0, st>>>(
+        n_vis, order, ws.tiles_per_gauss, ws.cnt2, ws.erec, gather_erec ? (uint4 *)ws.rec : nullptr);
     count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
@@ -472,7 +481,7 @@ struct BinArgs {
     CamDev cam;
     const unsigned *order;   // depth order -> packed index
     const unsigned *base2;   // [n_vis + 1] exclusive prefix of the per-Gaussian hit counts in depth order
-    const uint4 *erec;
+    const uint4 *erec;       // emission records IN DEPTH ORDER (gather_counts_kernel)
     const float4 *grec;
     const int *radii;
     const unsigned long long *scan;  // scan[n] holds the totals: visible count in the high bits
@@ -563,23 +572,27 @@ __device__ __forceinline__ void bin_walk_big(const BinArgs &a, int src, int pos,
 template <bool kOrdered, typename F>
 __device__ __forceinline__ void bin_walk_chunk(const BinArgs &a, long long lo, long long hi, unsigned *stage, F f) {
     const int lane = threadIdx.x & 31;
-    // the (order -> erec) gather of group g+1 is issued before group g is processed: two dependent DRAM round trips
-    // per 32 Gaussians would otherwise sit on the warp's serial path
-    int pos_n = 0;
-    uint4 er_n = make_uint4(0u, 0u, 0u, 0u);
-    if (lo + lane < hi) {
-        pos_n = (int)a.order[lo + lane];
-        er_n = a.erec[pos_n];
-    }
+    // records and packed indices are streamed in depth order (coalesced), two groups ahead of their use, so the
+    // warp's serial path never waits for DRAM
+    int pos_n[2] = {0, 0};
+    uint4 er_n[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (lo + 32 * k + lane < hi) {
+            pos_n[k] = (int)a.order[lo + 32 * k + lane];
+            er_n[k] = a.erec[lo + 32 * k + lane];
+        }
     for (long long g0 = lo; g0 < hi; g0 += 32) {
         const bool vis = g0 + lane < hi;
-        const int pos = pos_n;
-        const uint4 er = er_n;
-        pos_n = 0;
-        er_n = make_uint4(0u, 0u, 0u, 0u);
-        if (g0 + 32 + lane < hi) {
-            pos_n = (int)a.order[g0 + 32 + lane];
-            er_n = a.erec[pos_n];
+        const int pos = pos_n[0];
+        const uint4 er = er_n[0];
+        pos_n[0] = pos_n[1];
+        er_n[0] = er_n[1];
+        pos_n[1] = 0;
+        er_n[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (g0 + 64 + lane < hi) {
+            pos_n[1] = (int)a.order[g0 + 64 + lane];
+            er_n[1] = a.erec[g0 + 64 + lane];
         }
         const bool big = vis && (er.z & kErecBig);
         unsigned bigmask = __ballot_sync(0xffffffffu, big);
@@ -778,7 +791,7 @@ bool bin_fast_supported(int n_tiles) { return n_tiles >= 1 && n_tiles <= kBinMax
 int launch_bin(int64_t n, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, cudaStream_t st) {
     BinArgs a;
     a.cam = cam;
-    a.order = order; a.base2 = ws.base2; a.erec = ws.erec; a.grec = ws.grec; a.radii = ws.radii; a.scan = ws.scan;
+    a.order = order; a.base2 = ws.base2; a.erec = (const uint4 *)ws.rec; a.grec = ws.grec; a.radii = ws.radii; a.scan = ws.scan;
     a.n = n;
     a.counts = ws.bin_counts; a.segsum = ws.bin_seg; a.totals = ws.bin_tot;
     a.offsets = ws.offsets; a.flatten = ws.tvals[0]; a.cap = cap;

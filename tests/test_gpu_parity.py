@@ -650,7 +650,7 @@ def test_full_size_config_M_properties(gwbp):
 
 
 
-def test_rasterization_backgrounds_depth_modes_and_sh(gwbp, coracle, case, tmp_path):
+def test_rasterization_backgrounds_depth_modes_and_sh(gwbp, coracle, noracle, case, tmp_path):
     """The remaining kwargs the reference passes to `rasterization`: backgrounds (affordance demo :918),
     render_mode="RGB+D" (click_and_segment.py:251) / "RGB+ED", sh_degree=3 (backproject.py:99)."""
     sc, vm, K, _ = case

@@ -1,8 +1,8 @@
 # Round-2 GPU call A: gsplat attempt, full GPU test suite (with parity prints), short bench, launch list.
 mkdir -p gpurun_out
-bash tools/gsplat_install_attempt.sh
+#bash tools/gsplat_install_attempt.sh
 timeout 2400 python -m pytest tests -x -q -m gpu -s > gpurun_out/r02a_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r02a_pytest.log; grep "^\[parity" gpurun_out/r02a_pytest.log | head -40
-timeout 600 python bench.py --steps 48 --e2e-steps 0 --cpu-budget 0 --pool 4 > gpurun_out/r02a_quick.json 2> gpurun_out/r02a_quick.err; echo "bench rc=$?"
+timeout 600 python bench.py --steps 48 --e2e-steps 0 --cpu-budget 0 --pool 4 --shim-views 1 > gpurun_out/r02a_quick.json 2> gpurun_out/r02a_quick.err; echo "bench rc=$?"
 python - <<PY
 import json
 try:
