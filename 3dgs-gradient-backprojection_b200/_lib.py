@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgwbp.so")
 
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC = 0, 1, 2
-ABI_VERSION = 10
+ABI_VERSION = 11
 KERNEL_FPACK_READY = 0x100
 PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL, PREPARE_SORTED_KEYS = 0, 1, 2
 
@@ -59,6 +59,11 @@ SIGNATURES = {
     "gwbp_backproject_view": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.c_void_p, C.POINTER(ViewInfo),
                                         C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gwbp_lowres_adjoint_supported": (C.c_int, [C.c_int32] * 6),
+    "gwbp_backproject_view_lowres": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.c_void_p, C.POINTER(ViewInfo),
+                                               C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
+                                               C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p]),
     "gwbp_render_view": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.c_void_p, C.POINTER(ViewInfo), C.c_void_p,
                                    C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "gwbp_render_pixels": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.c_void_p, C.POINTER(ViewInfo), C.c_void_p,

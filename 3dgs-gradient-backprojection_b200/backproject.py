@@ -56,6 +56,9 @@ class BackProjector:
         # Measured on B200 (config G) this buys nothing -- every kernel involved is an HBM-bound full grid --
         # so the default keeps everything on the caller's stream.
         self.overlap_pack = False
+        # encoder-resolution maps: "adjoint" = down-sampled weights x low-res map (gwbp_backproject_view_lowres, no
+        # full-resolution intermediate); "upsample" = fused upsample into the packed operand + the full-resolution kernel
+        self.lowres_impl = "adjoint"
         self._side = None
         self._main = None
         self._copy_stream = None  # add_view_host(): upload stream, two staging buffers, the deferred view
@@ -169,7 +172,8 @@ class BackProjector:
                 fp = self._fpack
             elif self.kernel == L.KERNEL_TC:
                 raise RuntimeError(f"tcgen05 kernel does not support D={self.d}")
-        overlap = fp is not None and self.overlap_pack
+        adjoint = fp is not None and lowres_mode is not None and self.lowres_impl == "adjoint"
+        overlap = fp is not None and self.overlap_pack and not adjoint
         if overlap and self._side is None:
             # The feature re-layout (a 69k-CTA, HBM-bound grid) depends only on F, the geometry pipeline
             # (a dozen small kernels) only on the camera: run them concurrently.  The geometry stream gets
@@ -179,7 +183,7 @@ class BackProjector:
         main = self._main if overlap else cur
         if overlap:
             main.wait_stream(cur)
-        if fp is not None:  # re-layout first (own entry point, so the fused kernel can be timed on its own)
+        if fp is not None and not adjoint:  # re-layout first (own entry point, so the fused kernel can be timed on its own)
             side = self._side if overlap else main
             if overlap:
                 side.wait_stream(main)  # previous view's kernel has finished reading fpack; F is ready
@@ -206,7 +210,9 @@ class BackProjector:
                 e0.record(main)
             ratio = self.accumulate == "per_view_ratio"
             num, den = (self.num_v, self.den_v) if ratio else (self.num, self.den)
-            if kernel & L.KERNEL_FPACK_READY:
+            if adjoint:
+                view.backproject_lowres(feats, lowres_mode == "nearest", num, den, fp, self._stats)
+            elif kernel & L.KERNEL_FPACK_READY:
                 view.backproject_packed(self.d, num, den, kernel, fp, self._stats)
             else:
                 view.backproject(feats, num, den, kernel, fp, self._stats)

@@ -28,6 +28,7 @@ SOURCES = {
     "finalize.cu": [],
     "sh.cu": [],
     "backproject_tc.cu": [],
+    "backproject_lr.cu": [],
     "render_tc.cu": [],
 }
 

@@ -293,6 +293,44 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam, const
     return rc;
 }
 
+int gwbp_lowres_adjoint_supported(int32_t width, int32_t height, int32_t src_h, int32_t src_w, int32_t d, int32_t nearest) {
+    return lr_supported(width, height, src_h, src_w, d, nearest) ? 1 : 0;
+}
+
+int gwbp_backproject_view_lowres(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws,
+                                 const gwbp_view_info *info, const float *S, int32_t src_h, int32_t src_w, int64_t sH,
+                                 int64_t sW, int64_t sD, int32_t nearest, int32_t d, float *num, float *den, void *fpack,
+                                 int64_t *stats, void *stream) {
+    GWBP_REQUIRE(scene && info, "backproject_view_lowres: NULL pointer");
+    if (scene->n == 0 || info->n_isects == 0) return 0;
+    GWBP_REQUIRE(ws && S && num && den && fpack, "backproject_view_lowres: NULL pointer");
+    if (int rc = check_cam(cam)) return rc;
+    GWBP_REQUIRE(src_h >= 1 && src_w >= 1, "low-resolution map must be at least 1x1");
+    GWBP_REQUIRE(tc_supported(d), "backproject_view_lowres: tcgen05 path does not support D=%d", d);
+    gwbp_ws_layout L;
+    if (int rc = gwbp_workspace_layout(scene->n, cam->width, cam->height, info->cap_isects, &L)) return rc;
+    const TileCtx t = tile_ctx(cam, ws, L, info);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (lr_supported(cam->width, cam->height, src_h, src_w, d, nearest)) {
+        // adjoint path: weights down-sampled on the tensor cores, contracted with the low-res map itself
+        prof_mark(kEvPack0, st);
+        prof_mark(kEvPack1, st);
+        prof_mark(kEvBp0, st);
+        const int rc = launch_backproject_lr(t, S, src_h, src_w, sH, sW, sD, nearest, d, num, den, fpack, (long long *)stats, st);
+        prof_mark(kEvBp1, st);
+        return rc;
+    }
+    // windows too large for the adjoint kernel (down-sampling or mild up-sampling): fused upsample + re-layout, then the
+    // full-resolution contraction
+    prof_mark(kEvPack0, st);
+    if (int rc = launch_fpack_lowres(cam->width, cam->height, S, src_h, src_w, sH, sW, sD, nearest, d, fpack, st)) return rc;
+    prof_mark(kEvPack1, st);
+    prof_mark(kEvBp0, st);
+    const int rc = launch_backproject_tc(t, nullptr, 0, 0, 0, d, num, den, fpack, true, (long long *)stats, st);
+    prof_mark(kEvBp1, st);
+    return rc;
+}
+
 int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws, const gwbp_view_info *info,
                      const float *colors, int64_t color_stride, int32_t d, const float *background, float *render,
                      float *alpha, int32_t kernel, void *stream) {

@@ -157,6 +157,12 @@ int launch_fpack_lowres(int W, int H, const float *S, int sh, int sw, int64_t ss
 int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t sW, int64_t sD, int d,
                           float *num, float *den, void *fpack, bool fpack_ready, long long *stats, cudaStream_t st);
 
+// encoder-resolution maps: down-sampled weights x low-res map, two chained tcgen05 GEMMs (backproject_lr.cu)
+bool lr_supported(int W, int H, int sh, int sw, int d, int nearest);
+size_t lr_scratch_bytes(int sh, int sw, int d);
+int launch_backproject_lr(const TileCtx &t, const float *S, int sh, int sw, int64_t ssh, int64_t ssw, int64_t ssd,
+                          int nearest, int d, float *num, float *den, void *scratch, long long *stats, cudaStream_t st);
+
 // tcgen05 forward render (render_tc.cu)
 bool render_tc_supported(const float *colors, int64_t cstride, int d);
 int launch_render_tc(const TileCtx &t, const float *colors, int64_t cstride, int d, const float *bg, float *render,

@@ -197,6 +197,23 @@ class View:
                 stats.data_ptr() if stats is not None else None, _stream_ptr(self.scene.device)),
                 "gwbp_backproject_view")
 
+    def backproject_lowres(self, feats_low: torch.Tensor, nearest: bool, num: torch.Tensor, den: torch.Tensor,
+                           fpack: torch.Tensor, stats: Optional[torch.Tensor] = None) -> None:
+        """backproject(interpolate(feats_low)) for an encoder-resolution map [h,w,D] (any strides), without the
+        full-resolution map: gwbp_backproject_view_lowres."""
+        _require_cuda(feats_low, "feats_low")
+        assert feats_low.dtype == torch.float32 and feats_low.dim() == 3
+        d = feats_low.shape[2]
+        assert num.shape == (self.scene.n, d) and num.dtype == torch.float32 and num.is_contiguous()
+        assert den.shape == (self.scene.n,) and den.dtype == torch.float32 and den.is_contiguous()
+        sH, sW, sD = feats_low.stride()
+        with torch.cuda.device(self.scene.device):
+            L.check(L.lib().gwbp_backproject_view_lowres(
+                C.byref(self.scene.c), C.byref(self.cam), self.ws.data_ptr(), C.byref(self.info), feats_low.data_ptr(),
+                feats_low.shape[0], feats_low.shape[1], sH, sW, sD, 1 if nearest else 0, d, num.data_ptr(),
+                den.data_ptr(), fpack.data_ptr(), stats.data_ptr() if stats is not None else None,
+                _stream_ptr(self.scene.device)), "gwbp_backproject_view_lowres")
+
     def render(self, colors: torch.Tensor, background: Optional[torch.Tensor] = None, kernel: int = L.KERNEL_AUTO):
         """(render [H,W,D], alpha [H,W]) for colors [N,D] (row stride free, unit inner stride).
         kernel: KERNEL_AUTO (tcgen05 for D >= 64), KERNEL_SIMT (fp32 CUDA cores) or KERNEL_TC."""

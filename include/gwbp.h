@@ -22,6 +22,8 @@
  *                            `(render*feats).sum().backward()` and `render.sum().backward()`
  *                            (backproject.py:127-131,145-151) INCLUDING the accumulation
  *                            `gaussian_features += grad; gaussian_denoms += grad0[:,0]` (:149-150)
+ *   gwbp_backproject_view_lowres  the same after `F.interpolate(encoder_out, (H,W))` (backproject.py:108-113,236-249),
+ *                            taking the encoder-resolution map itself
  *   gwbp_render_view ....... rasterize_to_pixels forward for D-channel colours (segment.py:209-220)
  *   gwbp_render_pixels ..... the `rasterization(features, render_mode="RGB+D")` call of the click prompt,
  *                            of which only ONE pixel is read (click_and_segment.py:241-262)
@@ -43,7 +45,7 @@ extern "C" {
 #endif
 
 #define GWBP_TILE 16
-#define GWBP_ABI_VERSION 10
+#define GWBP_ABI_VERSION 11
 
 /* kernel selection for gwbp_backproject_view and gwbp_render_view */
 #define GWBP_KERNEL_AUTO 0
@@ -162,6 +164,18 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam_host, 
                           const gwbp_view_info *info_host, const float *F, int64_t sH, int64_t sW, int64_t sD,
                           int32_t d, float *num, float *den, int32_t kernel, void *fpack, int64_t *stats,
                           void *stream);
+
+/* The same accumulation for an ENCODER-RESOLUTION map S [src_h, src_w, d] (element strides sH,sW,sD), i.e.
+ *   gwbp_backproject_view(F = interpolate(S, size=(H,W), mode=bilinear|nearest))      (backproject.py:108-113, :236-249)
+ * without building F or its packed copy: the weights are down-sampled on the tensor cores (the adjoint of the
+ * up-sample) and contracted with the low-res map fetched by TMA (backproject_lr.cu).  `fpack` is scratch of at least
+ * gwbp_fpack_bytes(width, height, d) bytes.  Geometries whose per-tile window of S exceeds 6 rows x 8 texels
+ * (gwbp_lowres_adjoint_supported() == 0) silently take gwbp_pack_features_lowres + the full-resolution kernel. */
+int gwbp_lowres_adjoint_supported(int32_t width, int32_t height, int32_t src_h, int32_t src_w, int32_t d, int32_t nearest);
+int gwbp_backproject_view_lowres(const gwbp_scene *scene, const gwbp_camera *cam_host, const void *ws,
+                                 const gwbp_view_info *info_host, const float *S, int32_t src_h, int32_t src_w, int64_t sH,
+                                 int64_t sW, int64_t sD, int32_t nearest, int32_t d, float *num, float *den, void *fpack,
+                                 int64_t *stats, void *stream);
 
 /* render[H,W,d] = sum_g w(g,p) colors[g,:] (+ (1-alpha) background), alpha[H,W] = 1-T.  Every in-image pixel
  * of `render` and `alpha` is written (no pre-zeroing needed).  kernel: GWBP_KERNEL_SIMT = fp32 CUDA cores,

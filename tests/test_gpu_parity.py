@@ -197,32 +197,45 @@ def test_backprojection_feature_dims(gwbp, coracle, noracle, d):
         _check_features(bp, num_o, den_o, noracle, margin, f" D={d}/{kernel}")
 
 
-@pytest.mark.parametrize("mode,d,enc", [("nearest", 1024, 64), ("bilinear", 512, 60), ("nearest", 48, 9), ("bilinear", 16, 7)])
-def test_encoder_resolution_maps_against_the_oracle(gwbp, coracle, noracle, mode, d, enc):
+@pytest.mark.parametrize("mode,d,eh,ew,W,H,adjoint", [
+    ("nearest", 1024, 64, 64, 422, 274, True),    # DINOv2: 64 x 64 tokens, [N,1024] accumulators (backproject.py:206-249)
+    ("bilinear", 512, 60, 60, 330, 230, True),    # LSeg-shaped, windows of up to 6 x 5 texels (3 column chunks)
+    ("bilinear", 100, 24, 31, 211, 137, True),    # D not a multiple of 16, non-square map
+    ("nearest", 48, 9, 9, 211, 137, True),
+    ("bilinear", 16, 7, 7, 211, 137, True),
+    ("bilinear", 64, 64, 64, 211, 137, False),    # mild up-sampling: windows too large -> re-layout fallback
+])
+def test_encoder_resolution_maps_against_the_oracle(gwbp, coracle, noracle, mode, d, eh, ew, W, H, adjoint):
     """The DINOv2 variant (backproject.py:206-211,236-249: [N,1024] accumulators, 64x64 tokens upsampled with
     mode="nearest") and the LSeg one (:108-112, bilinear), fed with the ENCODER-resolution map: the oracle
-    upsamples with its own restatement of F.interpolate (oracle/gsplat_oracle.py::upsample) and back-projects
-    the full-resolution map; the GPU path fuses the upsample (add_view_lowres) and is also given the materialised map."""
+    upsamples with its own restatement of F.interpolate (oracle/gsplat_oracle.py::upsample) and back-projects the
+    full-resolution map; the GPU gets the low-res map (adjoint kernel: down-sampled weights x low-res map; and the
+    fused-upsample re-layout) and, for reference, the materialised full-resolution map."""
     S = gwbp.scene
-    W, H = 211, 137
     sc = S.make_scene(6000, 21)
     vm, K = S.make_cameras(2, W, H, 21)
-    rng = np.random.default_rng(d + enc)
+    rng = np.random.default_rng(d + eh)
     lows = []
     for _ in range(2):
-        low = rng.standard_normal((enc, enc, d)).astype(np.float32)
+        low = rng.standard_normal((eh, ew, d)).astype(np.float32)
         lows.append(low / np.linalg.norm(low, axis=2, keepdims=True))
     feats = [noracle.upsample(low, H, W, mode) for low in lows]
     num_o, den_o, _ = oracle_job(coracle, sc, vm, K, W, H, feats, d)
     margin = oracle_margins(coracle, sc, vm, K, W, H, den_o)
+    assert bool(gwbp._lib.lib().gwbp_lowres_adjoint_supported(W, H, eh, ew, d, int(mode == "nearest"))) == adjoint
     args = (_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities), d)
-    fused, full = gwbp.BackProjector(*args, kernel="tc"), gwbp.BackProjector(*args, kernel="tc")
+    jobs = {"adjoint": gwbp.BackProjector(*args, kernel="tc", collect_stats=True),
+            "upsample": gwbp.BackProjector(*args, kernel="tc", collect_stats=True),
+            "materialised": gwbp.BackProjector(*args, kernel="tc", collect_stats=True)}
+    jobs["upsample"].lowres_impl = "upsample"
     for v in range(2):
         planar_low = _dev(np.ascontiguousarray(np.transpose(lows[v], (2, 0, 1))))  # encoder output [D,h,w]
-        fused.add_view_lowres(vm[v], K, W, H, planar_low.permute(1, 2, 0), mode=mode)
-        full.add_view(vm[v], K, W, H, _feat_dev(feats[v]))
-    _check_features(fused, num_o, den_o, noracle, margin, f" lowres {mode} D={d} fused")
-    _check_features(full, num_o, den_o, noracle, margin, f" lowres {mode} D={d} materialised")
+        for name in ("adjoint", "upsample"):
+            jobs[name].add_view_lowres(vm[v], K, W, H, planar_low.permute(1, 2, 0), mode=mode)
+        jobs["materialised"].add_view(vm[v], K, W, H, _feat_dev(feats[v]))
+    for name, bp in jobs.items():
+        _check_features(bp, num_o, den_o, noracle, margin, f" lowres {mode} D={d} {name}")
+        assert bp.stats() == jobs["materialised"].stats(), name  # same weights, same rows
 
 
 def test_tile_culling_does_not_change_the_accumulators(gwbp, case):
@@ -679,8 +692,7 @@ def test_rasterization_backgrounds_depth_modes_and_sh(gwbp, coracle, noracle, ca
     assert np.abs(out_ed[0, ..., 3].double().cpu().numpy() - want_ed)[cover].max() < 1e-2
     # SH colours, degree 0..4 (the reference uses 3: backproject.py:99), against the oracle's independent basis
     # (associated Legendre functions, oracle/gsplat_oracle.py::sh_basis) composited by the C oracle
-    sh_np = (rng.standard_normal((sc.n, 25, 3)) * 0.4).astype(np.float32)
-    sh_np[:, 0, :] += 0.8
+    sh_np = rng.standard_normal((sc.n, 25, 3)).astype(np.float32)  # DC ~ N(0,1): the clamp at 0 bites at every degree
     for degree in (0, 1, 2, 3, 4):
         kk = (degree + 1) ** 2
         coeffs = _dev(sh_np)[:, :max(kk, 16)] if degree < 4 else _dev(sh_np)
