@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libgwbp.so")
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC = 0, 1, 2
 ABI_VERSION = 11
 KERNEL_FPACK_READY = 0x100
-PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL, PREPARE_SORTED_KEYS = 0, 1, 2
+PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL, PREPARE_COUNTING_BIN = 0, 1, 2
 
 
 class Scene(C.Structure):

@@ -178,7 +178,7 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     prof_mark(kEvDepthSort, st);
     const unsigned *order = w.dvals[dsel];
     const int n_tiles = cd.tw * cd.th;
-    if (bin_fast_supported(n_tiles) && !(flags & GWBP_PREPARE_SORTED_KEYS)) {
+    if (bin_fast_supported(n_tiles) && (flags & GWBP_PREPARE_COUNTING_BIN)) {
         // hand-written stable counting sort fused with the emission: no (tile, index) intermediate, no radix sort;
         // the depth-ordered prefix of the per-Gaussian hit counts cuts the list into chunks of equal work
         if (int rc = launch_gather_counts(info->n_vis, order, w, true, st)) return rc;
@@ -189,8 +189,7 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
         prof_mark(kEvBin, st);
         return rc;
     }
-    // fallback for very large images (> kBinMaxTiles tiles) or when the caller asks for materialised tile keys:
-    // emit (tile, index) pairs in depth order, stable CUB radix sort on the tile id, range finding
+    // default: emit (tile, index) pairs in depth order, stable radix sort on the <= 13 tile bits, range finding
     if (int rc = launch_gather_counts(info->n_vis, order, w, false, st)) return rc;
     if (int rc = launch_scan_counts(info->n_vis, w, st)) return rc;
     const bool key16 = n_tiles <= 65536;

@@ -6,9 +6,9 @@
 //
 // U = the interpolation operator (4 taps per pixel, torch align_corners=False arithmetic).  Per (tile, batch of 128
 // Gaussians) the kernel runs TWO chained tcgen05 GEMMs instead of one big one:
-//      GEMM1   W'[128 g x 48 q] = W[128 g x 256 px] . U[256 px x 48 q]     (q = the tile's window of the low-res map:
-//                                                                          6 source rows x 8 texels)
-//      GEMM2   acc[128 g x D]  = W'[128 g x 48 q]  . F_low[48 q x D]       (F_low window fetched by TMA tensor maps)
+//      GEMM1   W'[128 g x 64 q] = W[128 g x 256 px] . U[256 px x 64 q]     (q = the tile's window of the low-res map:
+//                                                                          8 source rows x 8 texels)
+//      GEMM2   acc[128 g x D]  = W'[128 g x 64 q]  . F_low[64 q x D]       (F_low window fetched by TMA tensor maps)
 // i.e. the weights are DOWN-sampled on the tensor cores (the adjoint of the up-sample) and contracted with the
 // L2-resident low-resolution map: ~1/5 of the tensor work of bp_tc_kernel, 1/4 of its shared-memory operand traffic,
 // and the weight block W is consumed by one short sweep, so the ALU warps never wait for a second column-chunk sweep.
@@ -19,10 +19,10 @@
 //   warps 12-15 converter : tcgen05.ld W' (fp32, lane = Gaussian) -> bf16 hi/lo -> A operand of GEMM2 in smem
 //   warp 16     producer  : cp.async.bulk.tensor.3d (TMA tensor map) of the F_low window, K-step by K-step
 //   warp 17     MMA       : one elected lane issues both GEMMs
-//   warp 18     U writer  : regenerates the 16-pixel-row slices of U (3 KB each, hi/lo) into a 4-slot ring per batch
+//   warp 18     U writer  : regenerates the 16-pixel-row slices of U (4 KB each, hi/lo) into a 3-slot ring per batch
 // Split-bf16 everywhere (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM): ~2^-16 per contraction.
 //
-// TMEM (512 columns): acc buffers at 0 / 192 (192 columns each), W' buffers at 384 / 432 (48 columns each).
+// TMEM (512 columns): acc buffers at 0 / 192 (192 columns each), W' buffers at 384 / 448 (64 columns each).
 // The packed low-res map (flow_pack_kernel) is [y][channel group][x][8 channels] bf16, hi and lo: a TMA box of
 // {8 texels x 8 channels, 24 groups, 2 rows} lands in shared memory directly in UMMA core-matrix order.
 #include <cuda.h>
@@ -39,19 +39,19 @@ namespace {
 
 constexpr int MB = 128;            // Gaussians per batch = UMMA M
 constexpr int KSL = 16;            // pixels per K-slice of GEMM1 (one tile row) = one UMMA K step
-constexpr int QY = 6, QX = 8;      // low-res window of a tile: source rows x texels (x padded to a core matrix)
-constexpr int NQ = QY * QX;        // 48 = GEMM1 N = GEMM2 K
-constexpr int NC2 = 192;           // feature columns per GEMM2 chunk (2 x 192 + 2 x 48 TMEM columns)
+constexpr int QY = 8, QX = 8;      // low-res window of a tile: source rows x texels (one core matrix per row)
+constexpr int NQ = QY * QX;        // 64 = GEMM1 N = GEMM2 K
+constexpr int NC2 = 192;           // feature columns per GEMM2 chunk (2 x 192 + 2 x 64 = all 512 TMEM columns)
 constexpr int NG2 = NC2 / 8;       // channel groups per chunk = TMA box extent
-constexpr int K2STEPS = NQ / 16;   // 3
+constexpr int K2STEPS = NQ / 16;   // 4
 constexpr int RING = 3;            // batches in flight between ALU and epilogue
 constexpr uint32_t A_SBO = 128, A_LBO = (MB / 8) * 128;    // W^T and W'^T: MN-major, 16 row-groups of 8 Gaussians per K-group
 constexpr int W_PART_BYTES = (kTilePix / 8) * A_LBO;       // 64 KB per hi / lo part
-constexpr int A2_PART_BYTES = (NQ / 8) * A_LBO;            // 12 KB per hi / lo part
-constexpr uint32_t U_LBO = (NQ / 8) * 128;                 // U slice: [16 px x 48 q], MN-major
-constexpr int U_PART_BYTES = KSL * NQ * 2;                 // 1.5 KB
+constexpr int A2_PART_BYTES = (NQ / 8) * A_LBO;            // 16 KB per hi / lo part
+constexpr uint32_t U_LBO = (NQ / 8) * 128;                 // U slice: [16 px x 64 q], MN-major
+constexpr int U_PART_BYTES = KSL * NQ * 2;                 // 2 KB
 constexpr int U_SLOT_BYTES = 2 * U_PART_BYTES;
-constexpr int NUSLOT = 4;
+constexpr int NUSLOT = 3;
 constexpr uint32_t F_LBO = NG2 * 128;                      // F_low stage: [16 q x 192 cols], MN-major as TMA writes it
 constexpr int F_PART_BYTES = KSL * NC2 * 2;                // 6 KB
 constexpr int F_STAGE_BYTES = 2 * F_PART_BYTES;
@@ -435,26 +435,24 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             const int db = q & 1;
             mbar_wait(bar(Smem::d1_full + db), (q >> 1) & 1);
             tc_fence_after();
-            float v[NQ];
-#pragma unroll
+            if (q >= 1) mbar_wait(bar(Smem::a2_empty), (q - 1) & 1);  // GEMM2 of the previous batch has read A2
+#pragma unroll 1
             for (int k0 = 0; k0 < NQ; k0 += 16) {
                 float t[16];
                 tmem_ld16(tmem + lane_base + (uint32_t)(TM_D1 + db * NQ + k0), t);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[k0 + i] = t[i];
+                for (int i = 0; i < 16; ++i) {
+                    const int k = k0 + i;
+                    const __nv_bfloat16 h = __float2bfloat16_rn(t[i]);
+                    const __nv_bfloat16 l = __float2bfloat16_rn(t[i] - __bfloat162float(h));
+                    const uint32_t off = (uint32_t)(k >> 3) * A_LBO + (uint32_t)(k & 7) * 16 + goff;
+                    *reinterpret_cast<__nv_bfloat16 *>(smem + Smem::a2_hi + off) = h;
+                    *reinterpret_cast<__nv_bfloat16 *>(smem + Smem::a2_lo + off) = l;
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(Smem::d1_empty + db));
-            if (q >= 1) mbar_wait(bar(Smem::a2_empty), (q - 1) & 1);  // GEMM2 of the previous batch has read A2
-#pragma unroll
-            for (int k = 0; k < NQ; ++k) {
-                const __nv_bfloat16 h = __float2bfloat16_rn(v[k]);
-                const __nv_bfloat16 l = __float2bfloat16_rn(v[k] - __bfloat162float(h));
-                const uint32_t off = (uint32_t)(k >> 3) * A_LBO + (uint32_t)(k & 7) * 16 + goff;
-                *reinterpret_cast<__nv_bfloat16 *>(smem + Smem::a2_hi + off) = h;
-                *reinterpret_cast<__nv_bfloat16 *>(smem + Smem::a2_lo + off) = l;
-            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(Smem::a2_full));
@@ -487,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
         }
     } else if (warp == kUWarp) {
         // ===================================== U writer ======================================
-        // slice ks = the interpolation weights of the tile's pixel row ks onto the 6 x 8 window: [16 px x 48 q], bf16
+        // slice ks = the interpolation weights of the tile's pixel row ks onto the 8 x 8 window: [16 px x 64 q], bf16
         // hi/lo, MN-major (a pixel's 8 consecutive q = one 16-byte core-matrix row, q = 8 * source row + texel)
         int us = 0, uuse = 0;
         for (int q = 0;; ++q) {
@@ -501,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             const int ty = tile / a.t.tw, tx = tile % a.t.tw;
             const int ylo = src_index(min(ty * kTile, a.t.H - 1), a.scale_y, a.sh, a.nearest).i0;
             const int xlo = src_index(min(tx * kTile, a.t.W - 1), a.scale_x, a.sw, a.nearest).i0;
-            // this lane's three (pixel, source row) items: item = lane + 32 i -> p = item % 16, row = item / 16
+            // this lane's four (pixel, source row) items: item = lane + 32 i -> p = item % 16, row = item / 16
             const int p = lane & 15;
             const SrcIdx sx = src_index(min(tx * kTile + p, a.t.W - 1), a.scale_x, a.sw, a.nearest);
             const int x0 = sx.i0 - xlo, x1 = sx.i1 - xlo;
@@ -514,8 +512,8 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                 if (uuse >= 1) mbar_wait(bar(Smem::u_empty + us), (uuse - 1) & 1);
                 uint8_t *blk = smem + Smem::uring + us * U_SLOT_BYTES;
 #pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int row = (lane >> 4) + 2 * i;  // source row of the window: 0..5
+                for (int i = 0; i < QY / 2; ++i) {
+                    const int row = (lane >> 4) + 2 * i;  // source row of the window: 0..7
                     const float wy = (row == y0 ? 1.0f - sy.l : 0.0f) + (row == y1 ? sy.l : 0.0f);
                     uint4 hi, lo;
                     split_bf16x2(wy * wx[0], wy * wx[1], hi.x, lo.x);
@@ -659,9 +657,8 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace
 
-// Can the adjoint kernel take this geometry?  Every tile's window of the low-res map must fit 6 source rows x 8 texels
-// (true for any up-sampling factor >= ~3.4 vertically and >= ~2.5 horizontally, e.g. 240 -> 840 x 1297 and 64 -> anything
-// larger than 256); otherwise the caller falls back to the fused-upsample re-layout + bp_tc_kernel.
+// Can the adjoint kernel take this geometry?  Every tile's window of the low-res map must fit 8 source rows x 8 texels
+// (true for any up-sampling factor >= ~2.5, e.g. 240 -> 840 x 1297 and 64 tokens -> anything larger than 160); otherwise the caller falls back to the fused-upsample re-layout + bp_tc_kernel.
 bool lr_supported(int W, int H, int sh, int sw, int d, int nearest) {
     if (!(d >= 16 && d <= 2048 && d % 4 == 0) || sh < 1 || sw < 1 || W < 1 || H < 1) return false;
     const float scale_y = (float)sh / (float)H, scale_x = (float)sw / (float)W;

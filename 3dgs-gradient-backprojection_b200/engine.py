@@ -86,12 +86,12 @@ class View:
     (= everything one `rasterization()` call computes before compositing)."""
 
     def __init__(self, scene: PackedScene, cam: L.Camera, cap_isects: Optional[int] = None,
-                 workspace: Optional[torch.Tensor] = None, tile_cull: bool = False, sorted_keys: bool = False):
+                 workspace: Optional[torch.Tensor] = None, tile_cull: bool = False, counting_bin: bool = False):
         """tile_cull=False: the intersection list is gsplat-1.4.0's (bit-exact `meta`).
         tile_cull=True : pairs that cannot reach alpha >= 1/255 on the tile are dropped before the sort
         (identical accumulators, less work) -- the BackProjector default.
-        sorted_keys=True forces the emit + radix-sort binning (the fallback used for images of more than 12 288
-        tiles) instead of the sort-free counting path; both give the same flatten_ids / isect_offsets."""
+        counting_bin=True selects the hand-written sort-free tile binning (images of <= 12 288 tiles) instead of
+        emit + radix sort; both give the same flatten_ids / isect_offsets (the radix path is faster: DESIGN.md)."""
         self.scene, self.cam = scene, cam
         n = scene.n
         cap = int(cap_isects) if cap_isects else max(1 << 16, 8 * n)
@@ -103,7 +103,7 @@ class View:
             with torch.cuda.device(scene.device):
                 rc = L.lib().gwbp_view_prepare(C.byref(scene.c), C.byref(cam), workspace.data_ptr(), workspace.numel(),
                                                cap, (L.PREPARE_TILE_CULL if tile_cull else L.PREPARE_GSPLAT_EXACT)
-                                               | (L.PREPARE_SORTED_KEYS if sorted_keys else 0),
+                                               | (L.PREPARE_COUNTING_BIN if counting_bin else 0),
                                                _stream_ptr(scene.device), C.byref(info))
             if rc == -2:  # capacity: the library told us the exact need; grow once and redo
                 cap = int(info.n_isects * 1.25) + 1024

@@ -57,9 +57,10 @@ extern "C" {
 #define GWBP_PREPARE_GSPLAT_EXACT 0 /* intersection list == gsplat-1.4.0 isect_tiles (bounding-square test) */
 #define GWBP_PREPARE_TILE_CULL 1    /* additionally drop (Gaussian, tile) pairs whose alpha stays < 1/255 on the
                                        whole tile: same accumulators, ~40 % shorter list to sort and walk */
-#define GWBP_PREPARE_SORTED_KEYS 2  /* force the emit + radix-sort binning (materialises the sorted tile ids in tkeys);
-                                       default is the sort-free counting path, which yields the same flatten_ids /
-                                       isect_offsets without them (tile_key_bytes == 0) */
+#define GWBP_PREPARE_COUNTING_BIN 2 /* tile binning by the hand-written sort-free counting path (project.cu: bin_*_kernel)
+                                       instead of emit + radix sort; same flatten_ids / isect_offsets, no sorted tile keys
+                                       (tile_key_bytes == 0); images of <= 12 288 tiles only.  Measured SLOWER than the
+                                       radix-sort path on B200 (DESIGN.md "dead ends"), hence opt-in */
 
 typedef struct gwbp_scene {
     int64_t n;        /* Gaussians */
@@ -169,7 +170,7 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam_host, 
  *   gwbp_backproject_view(F = interpolate(S, size=(H,W), mode=bilinear|nearest))      (backproject.py:108-113, :236-249)
  * without building F or its packed copy: the weights are down-sampled on the tensor cores (the adjoint of the
  * up-sample) and contracted with the low-res map fetched by TMA (backproject_lr.cu).  `fpack` is scratch of at least
- * gwbp_fpack_bytes(width, height, d) bytes.  Geometries whose per-tile window of S exceeds 6 rows x 8 texels
+ * gwbp_fpack_bytes(width, height, d) bytes.  Geometries whose per-tile window of S exceeds 8 rows x 8 texels
  * (gwbp_lowres_adjoint_supported() == 0) silently take gwbp_pack_features_lowres + the full-resolution kernel. */
 int gwbp_lowres_adjoint_supported(int32_t width, int32_t height, int32_t src_h, int32_t src_w, int32_t d, int32_t nearest);
 int gwbp_backproject_view_lowres(const gwbp_scene *scene, const gwbp_camera *cam_host, const void *ws,

@@ -95,15 +95,15 @@ def test_native_library_is_loaded(gwbp):
 
 
 @pytest.mark.parametrize("cull", [False, True])
-@pytest.mark.parametrize("sorted_keys", [False, True])
-def test_integer_stages_bit_exact(gwbp, coracle, case, cull, sorted_keys):
+@pytest.mark.parametrize("counting_bin", [False, True])
+def test_integer_stages_bit_exact(gwbp, coracle, case, cull, counting_bin):
     """cull=False: gsplat-1.4.0 isect_tiles semantics; cull=True: the exact tile-culling extension.
-    sorted_keys=False: the hand-written sort-free tile binning (default); True: emit + radix sort (large-image fallback)."""
+    counting_bin=False: emit + radix sort on the tile id (default); True: the hand-written sort-free counting path."""
     sc, vm, K, _ = case
     scene = gwbp.PackedScene(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities))
     for v in range(vm.shape[0]):
-        view = gwbp.View(scene, gwbp.make_camera(vm[v], K, 96, 64), tile_cull=cull, sorted_keys=sorted_keys)
-        assert view.info.tile_key_bytes == (2 if sorted_keys else 0)
+        view = gwbp.View(scene, gwbp.make_camera(vm[v], K, 96, 64), tile_cull=cull, counting_bin=counting_bin)
+        assert view.info.tile_key_bytes == (0 if counting_bin else 2)
         e = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[v], K, 96, 64, cull=cull).export()
         m = view.meta()
         gids = m["gaussian_ids"].cpu().numpy()
@@ -120,9 +120,9 @@ def test_integer_stages_bit_exact(gwbp, coracle, case, cull, sorted_keys):
 
 def test_integer_stages_bit_exact_config_S_and_odd_sizes(gwbp, coracle):
     S = gwbp.scene
-    # (3000, 4112, 4100): 257 x 257 = 66 049 tiles -- beyond the sort-free path (radix-sort fallback) AND beyond
-    # 16-bit tile keys (32-bit key path); (40_000, 1920, 1080): config M's 8 160 tiles (6 binning warps per CTA);
-    # the 2 000-Gaussian scenes at large images hold rectangles of more than 64 tiles (warp-cooperative emission)
+    # (3000, 4112, 4100): 257 x 257 = 66 049 tiles -- beyond 16-bit tile keys (32-bit key path) and beyond the counting
+    # path (which then silently uses the radix sort); (40_000, 1920, 1080): config M's 8 160 tiles (5 counting warps per
+    # CTA); the small scenes at large images hold rectangles of more than 64 tiles (warp-cooperative emission)
     for (n, W, H, seed) in [(50_000, 256, 256, 0), (20_000, 333, 211, 3), (5_000, 17, 15, 4), (2_000, 1297, 840, 5),
                             (40_000, 1920, 1080, 8), (700, 2200, 1400, 9), (3_000, 4112, 4100, 6)]:
         sc = S.make_scene(n, seed)
@@ -130,15 +130,15 @@ def test_integer_stages_bit_exact_config_S_and_odd_sizes(gwbp, coracle):
         scene = gwbp.PackedScene(_dev(sc.means), _dev(sc.quats), _dev(sc.scales), _dev(sc.opacities))
         for cull in (False, True):
             e = coracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[1], K, W, H, cull=cull).export()
-            for sorted_keys in (False, True):
-                view = gwbp.View(scene, gwbp.make_camera(vm[1], K, W, H), tile_cull=cull, sorted_keys=sorted_keys)
+            for counting_bin in (False, True):
+                view = gwbp.View(scene, gwbp.make_camera(vm[1], K, W, H), tile_cull=cull, counting_bin=counting_bin)
                 tiles = view.info.tile_w * view.info.tile_h
-                want = (2 if tiles <= 65536 else 4) if (sorted_keys or tiles > 12288) else 0
+                want = 0 if (counting_bin and tiles <= 12288) else (2 if tiles <= 65536 else 4)
                 assert view.info.tile_key_bytes == want, (n, W, H, view.info.tile_key_bytes)
                 m = view.meta()
-                assert np.array_equal(m["isect_ids"].cpu().numpy(), e["isect_ids"]), (n, W, H, cull, sorted_keys)
-                assert np.array_equal(m["flatten_ids"].cpu().numpy(), e["flatten_ids"]), (n, W, H, cull, sorted_keys)
-                assert np.array_equal(m["isect_offsets"].cpu().numpy()[0], e["isect_offsets"]), (n, W, H, cull, sorted_keys)
+                assert np.array_equal(m["isect_ids"].cpu().numpy(), e["isect_ids"]), (n, W, H, cull, counting_bin)
+                assert np.array_equal(m["flatten_ids"].cpu().numpy(), e["flatten_ids"]), (n, W, H, cull, counting_bin)
+                assert np.array_equal(m["isect_offsets"].cpu().numpy()[0], e["isect_offsets"]), (n, W, H, cull, counting_bin)
 
 
 @pytest.mark.parametrize("kernel", ["simt", "auto"])
