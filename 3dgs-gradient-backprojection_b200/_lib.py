@@ -10,6 +10,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libgwbp.so")
+if os.environ.get("GWBP_LIB_VARIANT") == "exp":  # tools/ only: the -DGWBP_EXPERIMENTS build (timing knobs)
+    LIB_PATH = os.path.join(_HERE, "lib", "libgwbp_exp.so")
 
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC = 0, 1, 2
 ABI_VERSION = 11

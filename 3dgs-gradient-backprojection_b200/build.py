@@ -40,7 +40,17 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """experiments=True builds lib/libgwbp_exp.so with -DGWBP_EXPERIMENTS (timing knobs read from GWBP_*_DEBUG
+    environment variables: they alter results and exist in no other build); tools/ use it, the package never does
+    unless GWBP_LIB_VARIANT=exp is set."""
+    global OBJDIR, SO
+    if experiments:
+        OBJDIR = os.path.join(HERE, "build", "exp")
+        SO = os.path.join(LIBDIR, "libgwbp_exp.so")
+    else:
+        OBJDIR = os.path.join(HERE, "build")
+        SO = os.path.join(LIBDIR, "libgwbp.so")
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
@@ -51,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            jobs.append((["nvcc", "-c", s, "-o", o] + ARCH + COMMON + extra, o))
+            jobs.append((["nvcc", "-c", s, "-o", o] + ARCH + COMMON + extra + (["-DGWBP_EXPERIMENTS"] if experiments else []), o))
 
     def run(job):
         cmd, o = job
@@ -78,4 +88,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, experiments="--experiments" in sys.argv))

@@ -164,6 +164,7 @@ struct LrArgs {
     float scale_y, scale_x;   // sh / H, sw / W as fp32 quotients (torch's area_pixel_compute_scale)
     int *unit_counter;
     long long *stats;
+    int debug;  // GWBP_LR_DEBUG (experiment builds only): 1 = skip the accumulator reductions (timing only)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, const __grid_constant__ CUtensorMap map_hi,
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                                 const int row = 16 * half + 4 * i + rsub;
                                 if (live_mask >> row & 1u) {
                                     const float4 x = *reinterpret_cast<const float4 *>(wstage + (4 * i + rsub) * EPI_PITCH + 16 * piece);
-                                    red_add_v4(a.num + grow[4 * half + i] + col, x.x, x.y, x.z, x.w);
+                                    if (!(a.debug & 1)) red_add_v4(a.num + grow[4 * half + i] + col, x.x, x.y, x.z, x.w);
                                 }
                             }
                         }
@@ -716,6 +717,11 @@ int launch_backproject_lr(const TileCtx &t, const float *S, int sh, int sw, int6
     a.scale_y = (float)sh / (float)t.H; a.scale_x = (float)sw / (float)t.W;
     a.unit_counter = (int *)t.scratch;
     a.stats = stats;
+    a.debug = 0;
+#ifdef GWBP_EXPERIMENTS
+    static const int dbg = getenv("GWBP_LR_DEBUG") ? atoi(getenv("GWBP_LR_DEBUG")) : 0;
+    a.debug = dbg;
+#endif
     GWBP_CUDA_OK(cudaMemsetAsync(a.unit_counter, 0, sizeof(int), st));
     GWBP_CUDA_OK(cudaFuncSetAttribute(bp_lr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
     const int grid = a.nunits < num_sms() ? a.nunits : num_sms();

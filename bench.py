@@ -395,7 +395,10 @@ def run_ours(args, cfg):
         rows, walked = st.get("rows_nonzero", 0) / k, st.get("entries_walked", 0) / k
         # algorithmic bytes of the fused kernel: walked entries x (4 B id + 32 B record)
         # + the feature map once + one (D+1)-float accumulator update per non-zero row
-        algo_bytes = walked * 36.0 + fmap_bytes + rows * (d + 1) * 4.0
+        lr_adjoint = args.features == "lowres" and args.kernel != "simt" and bool(
+            gwbp._lib.lib().gwbp_lowres_adjoint_supported(W, H, enc, enc, d, 0))
+        in_bytes = float(enc * enc * d * 4) if args.features == "lowres" else float(fmap_bytes)  # the map as supplied
+        algo_bytes = walked * 36.0 + (in_bytes if lr_adjoint else fmap_bytes) + rows * (d + 1) * 4.0
         achieved = algo_bytes / (ms_kernel * 1e-3) / 1e9 if ms_kernel > 0 else 0.0
         # DRAM traffic / tensor-pipe share of the dominant kernel come from an `ncu --set full` capture and are only
         # reported when that capture was taken from THESE sources (profiles/r02_traffic.json records their hash)
@@ -415,20 +418,22 @@ def run_ours(args, cfg):
         n_g, n_vis, n_is = cfg["n"], last.n_vis, last.n_isects
         tiles = ((W + 15) // 16) * ((H + 15) // 16)
         # B_view = 44 N + 40 n_vis + 68 I + HWD s_F + 4 R (D+1)   (I = the list this engine builds)
-        view_bytes = 44.0 * n_g + 40.0 * n_vis + 68.0 * n_is + fmap_bytes + 4.0 * rows * (d + 1)
+        view_bytes = 44.0 * n_g + 40.0 * n_vis + 68.0 * n_is + in_bytes + 4.0 * rows * (d + 1)
         ms_view = ms_views / args.steps
         view = {"algorithmic_bytes": view_bytes, "ms": ms_view, "achieved": view_bytes / (ms_view * 1e-3) / 1e9,
                 "formula": "SURVEY 8d: 44N + 40n_vis + 68I + 4HWD + 4R(D+1), measured n_vis, I, R"}
         view["frac"] = view["achieved"] / hbm
         stages = None
         if stage_ms is not None:
+            adjoint = args.features == "lowres" and bool(gwbp._lib.lib().gwbp_lowres_adjoint_supported(W, H, enc, enc, d, 0))
             low_bytes = (enc * enc * d * 4.0) if args.features == "lowres" else float(fmap_bytes)
             sb = {"project": 44.0 * n_g + 40.0 * n_vis,                  # SURVEY 8d "Project"
                   "count_scan_and_readback": 16.0 * n_g,                 # 8-byte counters read + prefix written
                   "compact": 16.0 * n_g + 96.0 * n_vis,                  # counters + records in, packed records + sort input out
                   "depth_sort": 16.0 * n_vis,                            # one logical pass over (key, value) pairs
                   "tile_binning": 24.0 * n_is + 4.0 * tiles,             # SURVEY 8d "Bin+sort": 12 I written + 12 I read
-                  "feature_relayout": low_bytes + float(fpack_dev_bytes),  # map read + packed operand written
+                  # map read + packed operand written (adjoint low-res path: the 2 x 118 MB pack is part of "backproject")
+                  "feature_relayout": 0.0 if adjoint else low_bytes + float(fpack_dev_bytes),
                   "backproject": algo_bytes}
             stages = []
             for name, ms in zip(gwbp._lib.PROFILE_STAGES, stage_ms):
@@ -439,7 +444,9 @@ def run_ours(args, cfg):
                            "boundaries inside the library (one sync per view to read them)"})
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                     "traffic": traffic, "tensor_pipe_pct": tensor_pct, "traffic_source": traffic_note, "peak_source": src,
-                    "kernel": "bp_simt_kernel" if args.kernel == "simt" else "bp_tc_kernel (fused composite + tcgen05 contraction + accumulate)",
+                    "kernel": "bp_simt_kernel" if args.kernel == "simt" else
+                              "bp_lr_kernel (fused composite + weight down-sample GEMM + low-res contraction + accumulate)" if lr_adjoint
+                              else "bp_tc_kernel (fused composite + tcgen05 contraction + accumulate)",
                     "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": algo_bytes,
                     "rows_nonzero_per_view": rows, "entries_walked_per_view": walked,
                     "n_vis": last.n_vis, "n_isects": last.n_isects, "stages": stages, "view": view}
@@ -465,6 +472,118 @@ def run_ours(args, cfg):
         real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_query(args):
+    """BASELINE configs[3] (segment.py query path): per view, forward 512-d feature render + text cosine mask
+    (segment.py:209-224) at garden scale.  A "step" is ONE frame: project + bin + sort + render + mask.  `value` = the
+    reference's order of operations (D-channel render -> normalise -> scores -> compare); `linear_path` = the same mask
+    from a P-channel render of the per-Gaussian scores.  One JSON line, same contract."""
+    import torch
+
+    import gwbp
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    S = gwbp.scene
+    cfg = dict(S.CONFIGS["G"])
+    if args.d:
+        cfg["d"] = args.d
+    W, H, d, V = cfg["width"], cfg["height"], cfg["d"], cfg["views"]
+    sc = S.make_scene(cfg["n"], 0)
+    vm, K = S.make_cameras(V, W, H, 0)
+    t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
+    scene = gwbp.PackedScene(t(sc.means), t(sc.quats), t(sc.scales), t(sc.opacities))
+    g = torch.Generator(device=dev).manual_seed(0)
+    feats = torch.nn.functional.normalize(torch.randn(sc.n, d, device=dev, generator=g), dim=1)  # a finished field
+    text = t(S.make_text_queries(3, d, 0))
+    scores = gwbp.gaussian_scores(feats, text)
+    steps = min(args.steps, V)
+
+    def timed(fn, n, warm):
+        for i in range(warm):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = None
+        for i in range(n):
+            r = fn(warm + i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n, r
+
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    l0 = int(gwbp._lib.lib().gwbp_launch_count())
+    ms_exact, m_exact = timed(lambda i: gwbp.render_mask_2d(scene, feats, text, 1, vm[i % V], K, W, H, exact_render=True),
+                              steps, args.warmup)
+    launches = int(gwbp._lib.lib().gwbp_launch_count()) - l0
+    clocks = sampler.stop()
+    ms_lin, m_lin = timed(lambda i: gwbp.render_mask_2d(scene, feats, text, 1, vm[i % V], K, W, H, exact_render=False,
+                                                        scores=scores), steps, args.warmup)
+    last = (args.warmup + steps - 1) % V
+    diff_paths = int((m_exact != m_lin).sum())
+    ms_3d, _ = timed(lambda i: gwbp.get_mask3d(feats, text, 1), 5, 2)
+    view = gwbp.View(scene, gwbp.make_camera(vm[last], K, W, H), tile_cull=True)
+    ms_tc, _ = timed(lambda i: view.render(feats, None, gwbp.KERNEL_TC), 5, 2)
+    # end to end: the frame's mask is read back to the host every step (segment.py:226 `.cpu()`), text prompts uploaded
+    text_host = text.cpu().pin_memory()
+    t0 = time.perf_counter()
+    k2 = min(steps, max(args.e2e_steps, 1))
+    for i in range(k2):
+        tx = text_host.to(dev, non_blocking=True)
+        m = gwbp.render_mask_2d(scene, feats, tx, 1, vm[i % V], K, W, H, exact_render=True)
+        mh = m.cpu()
+    torch.cuda.synchronize(dev)
+    e2e_fps = k2 / (time.perf_counter() - t0)
+    # parity of the masks against the CPU oracle on ONE frame (bounded CPU work)
+    parity = None
+    if args.cpu_budget > 0:
+        from oracle import c_oracle, gsplat_oracle
+
+        c_oracle.set_num_threads(os.cpu_count() or 1)
+        cv = c_oracle.View(sc.means, sc.quats, sc.scales, sc.opacities, vm[last], K, W, H)
+        tc0 = time.perf_counter()
+        r_o, a_o = cv.render(feats.cpu().numpy())
+        cpu_s = time.perf_counter() - tc0
+        m_o, s_o = gsplat_oracle.mask2d(r_o, text.cpu().numpy(), 1)
+        margin = abs(s_o[..., 0] - s_o[..., 1:].max(-1))
+        cover = a_o > 1e-3
+        me, ml = m_exact.cpu().numpy(), m_lin.cpu().numpy()
+        parity = {"frame": int(last), "pixels": int(W * H), "covered_pixels": int(cover.sum()),
+                  "differing_exact_vs_oracle": int(((me != m_o) & cover).sum()),
+                  "differing_exact_vs_oracle_margin_gt_1e-4": int(((me != m_o) & cover & (margin > 1e-4)).sum()),
+                  "differing_linear_vs_oracle_margin_gt_1e-4": int(((ml != m_o) & cover & (margin > 1e-4)).sum()),
+                  "oracle_frame_seconds": cpu_s, "oracle_threads": c_oracle.num_threads()}
+        cpu = {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": c_oracle.num_threads(), "kind": "port",
+               "sample": f"the render of ONE frame at full size with the C oracle ({cpu_s:.1f} s; mask compare excluded)"}
+    else:
+        cpu = None
+    hbm, _, src = _peaks()
+    out_bytes = W * H * d * 4.0
+    line = {"metric": "2-D query masks/s (forward 512-d feature render + text cosine mask per view)", "value": 1e3 / ms_exact,
+            "unit": "frames/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_exact,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config Q (BASELINE configs[3]): segment.py query path at garden scale", **cfg,
+                       "prompts": 3, "n_pos": 1, "l2": "every frame writes and re-reads a 2.2 GB render"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(text_host.numel() * 4 + 100),
+                    "d2h_bytes_per_step": int(W * H), "steps": k2},
+            "linear_path": {"value": 1e3 / ms_lin, "unit": "frames/s", "ms_per_step": ms_lin,
+                            "pixels_differing_from_exact_path": diff_paths,
+                            "what": "P-channel render of per-Gaussian scores f_g . t_j (computed once per query), same compare"},
+            "mask3d": {"ms": ms_3d, "gbs": sc.n * d * 4 / ms_3d / 1e6, "frac": sc.n * d * 4 / ms_3d / 1e6 / hbm},
+            "roofline": {"bound": "hbm", "kernel": "render_tc_kernel (tcgen05 forward feature render)", "kernel_ms": ms_tc,
+                         "algorithmic_bytes_per_launch": out_bytes, "achieved": out_bytes / ms_tc / 1e6, "peak": hbm,
+                         "unit": "GB/s", "frac": out_bytes / ms_tc / 1e6 / hbm, "traffic": None, "peak_source": src,
+                         "note": "floor = the 4 HWD bytes of the render that must reach DRAM"},
+            "parity": parity, "cpu_baseline": cpu}
+    real_stdout.write(json.dumps(line) + "\n")
+    real_stdout.flush()
 
 
 def main():
@@ -502,6 +621,10 @@ def main():
         if os.path.exists(gwbp._lib.LIB_PATH):
             break
         time.sleep(0.5)
+    if args.config == "Q":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_query(args)
+        return
     cfg = dict(gwbp.scene.CONFIGS[args.config])
     if args.d:
         cfg["d"] = args.d

@@ -24,6 +24,13 @@ def test_scene_generator_is_deterministic(gwbp):
     assert np.abs(np.linalg.norm(S.make_text_queries(3, 16), axis=1) - 1).max() < 1e-6
 
 
+def test_shard_rows_partition(gwbp):
+    for n, world in [(5_800_000, 8), (7, 2), (3, 4), (0, 2), (10, 3)]:
+        ranges = [gwbp.dist.shard_rows(n, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
+
+
 def test_shard_views_partition(gwbp):
     for n_views, world in [(185, 8), (7, 2), (3, 4), (0, 2)]:
         seen = sorted(v for r in range(world) for v in gwbp.dist.shard_views(n_views, r, world))
@@ -65,8 +72,16 @@ def _worker(rank, world, port, out):
         num2 += per_view_num[v]
         den2 += per_view_den[v]
     ns, ds, lo, hi = gwbp.dist.reduce_scatter_accumulators(num2, den2)
-    ok = ok and (hi - lo) == n // world and torch.allclose(ns, ref_num[lo:hi], atol=1e-6) and \
+    ok = ok and (lo, hi) == gwbp.dist.shard_rows(n, rank, world) and torch.allclose(ns, ref_num[lo:hi], atol=1e-6) and \
         torch.allclose(ds, ref_den[lo:hi], atol=1e-6)
+    # ragged N (not a multiple of the world size): the last rank owns the remainder
+    n3 = 7
+    num3 = torch.full((n3, d), float(rank + 1))
+    den3 = torch.full((n3,), gwbp.DEN_EPS + float(rank + 1))
+    ns3, ds3, lo3, hi3 = gwbp.dist.reduce_scatter_accumulators(num3, den3)
+    tot = float(sum(range(1, world + 1)))
+    ok = ok and (lo3, hi3) == gwbp.dist.shard_rows(n3, rank, world) and (hi3 == n3 if rank == world - 1 else True)
+    ok = ok and torch.allclose(ns3, torch.full((hi3 - lo3, d), tot)) and torch.allclose(ds3, torch.full((hi3 - lo3,), tot), atol=1e-6)
     out[rank] = bool(ok)
     dist.destroy_process_group()
 
