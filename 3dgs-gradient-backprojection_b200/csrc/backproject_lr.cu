@@ -13,13 +13,14 @@
 // L2-resident low-resolution map: ~1/5 of the tensor work of bp_tc_kernel, 1/4 of its shared-memory operand traffic,
 // and the weight block W is consumed by one short sweep, so the ALU warps never wait for a second column-chunk sweep.
 //
-// Persistent CTA, 1 per SM, 608 threads, warp-specialised:
+// Persistent CTA, 1 per SM, 672 threads, warp-specialised:
 //   warps 0-7   ALU       : exactly bp_tc_kernel's weight generation (thread = pixel, sequential T, bf16 hi/lo W^T)
 //   warps 8-11  epilogue  : exactly bp_tc_kernel's (tcgen05.ld -> smem transpose -> red.global.add.v4.f32 rows)
 //   warps 12-15 converter : tcgen05.ld W' (fp32, lane = Gaussian) -> bf16 hi/lo -> A operand of GEMM2 in smem
 //   warp 16     producer  : cp.async.bulk.tensor.3d (TMA tensor map) of the F_low window, K-step by K-step
 //   warp 17     MMA       : one elected lane issues both GEMMs
-//   warp 18     U writer  : regenerates the 16-pixel-row slices of U (4 KB each, hi/lo) into a 3-slot ring per batch
+//   warps 18-20 U writers : regenerate the 16-pixel-row slices of U (4 KB each, hi/lo) per batch, one ring slot per warp
+//                           (a single writer made the GEMM1 sweep wait ~600 cycles per slice: profiles/r02_bp_lr_*)
 // Split-bf16 everywhere (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM): ~2^-16 per contraction.
 //
 // TMEM (512 columns): acc buffers at 0 / 192 (192 columns each), W' buffers at 384 / 448 (64 columns each).
@@ -59,7 +60,7 @@ constexpr int NFSTAGE = 3;
 constexpr int EPI_COLS = 32, EPI_ROWS = 16, EPI_PITCH = EPI_COLS * 4 + 16;
 constexpr int TM_ACC = 0, TM_D1 = 2 * NC2;                 // TMEM column bases
 
-constexpr int kEpiWarp0 = 8, kCvtWarp0 = 12, kProducerWarp = 16, kMmaWarp = 17, kUWarp = 18, kThreads = 19 * 32;
+constexpr int kEpiWarp0 = 8, kCvtWarp0 = 12, kProducerWarp = 16, kMmaWarp = 17, kUWarp0 = 18, kThreads = (18 + NUSLOT) * 32;
 
 struct RowInfo {
     int gid[MB];
@@ -88,6 +89,7 @@ struct Smem {
     static constexpr int total = tmem_slot + 16;
 };
 static_assert(Smem::total + 256 <= 232448, "shared memory budget (227 KB) exceeded");
+static_assert(NUSLOT == 3, "the MMA warp tracks three U slots");
 static_assert(Smem::fring % 128 == 0 && Smem::uring % 128 == 0 && Smem::a2_hi % 128 == 0, "operand alignment");
 
 __device__ __forceinline__ int bar_red_popc_alu(bool pred) {
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
     auto bar = [&](int i) -> uint32_t { return sbase + Smem::bars + 8 * i; };
     RowInfo *rows = reinterpret_cast<RowInfo *>(smem + Smem::rows);
     volatile int *ctrl = reinterpret_cast<volatile int *>(smem + Smem::ctrl);
-    volatile int &s_unit = ctrl[8];
+    volatile int &s_unit = ctrl[8], &s_unit2 = ctrl[9];
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Smem::tmem_slot);
 
     if (tid == 0) {
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             mbar_init(bar(Smem::rows_ready + i), 8);
             mbar_init(bar(Smem::rows_free + i), 4);
             mbar_init(bar(Smem::ctrl_full + i), 1);
-            mbar_init(bar(Smem::ctrl_empty + i), 4);  // producer, MMA, U writer, converters (warp 12)
+            mbar_init(bar(Smem::ctrl_empty + i), 4);  // producer, MMA, U writer 0, converters (warp 12)
         }
         mbar_init_fence();
     }
@@ -211,26 +213,51 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
         int q = 0;
         long long walked = 0;
         const uint32_t wslab = (uint32_t)(tid >> 3) * A_LBO + (uint32_t)(tid & 7) * 16;
-        while (true) {
-            if (tid == 0) s_unit = atomicAdd(a.unit_counter, 1);
-            bar_sync_alu();
-            const int unit = s_unit;
-            bar_sync_alu();
-            if (unit >= a.nunits) break;
+        // Work queue, two units deep: `unit` is being processed, `unit_n` is already known, and the request for the
+        // one after that is in flight -- so the next tile's list bounds and first 128 records are fetched while this
+        // tile is processed (a tile switch otherwise costs four dependent global round trips, ~3 us, per ~2.4 batches).
+        auto first_records = [&](int s_, int e_, float4 &r0_, float4 &r1_) {
+            r0_ = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            r1_ = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid < MB && s_ + tid < e_) {
+                const int id = a.t.flatten[s_ + tid];
+                r0_ = a.t.grec[2 * (int64_t)id];
+                r1_ = a.t.grec[2 * (int64_t)id + 1];
+            }
+        };
+        if (tid == 0) {
+            s_unit = atomicAdd(a.unit_counter, 1);
+            s_unit2 = atomicAdd(a.unit_counter, 1);
+        }
+        bar_sync_alu();
+        int unit = s_unit, unit_n = s_unit2;
+        bar_sync_alu();
+        int s = 0, e = 0;
+        float4 r0, r1;
+        if (unit < a.nunits) {
+            const int tile0 = unit_to_tile(unit, a.t.tw, a.t.th, kBand);
+            s = a.t.offsets[tile0];
+            e = a.t.offsets[tile0 + 1];
+        }
+        first_records(s, e, r0, r1);
+        while (unit < a.nunits) {
+            int unit_nn = 0;
+            if (tid == 0) unit_nn = atomicAdd(a.unit_counter, 1);  // consumed at the end of this tile
+            int s_n = 0, e_n = 0;
+            if (unit_n < a.nunits) {
+                const int tile_n = unit_to_tile(unit_n, a.t.tw, a.t.th, kBand);
+                s_n = a.t.offsets[tile_n];
+                e_n = a.t.offsets[tile_n + 1];
+            }
+            float4 r0n = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), r1n = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool fetched_n = false;
             const int tile = unit_to_tile(unit, a.t.tw, a.t.th, kBand);
             const int ty = tile / a.t.tw, tx = tile % a.t.tw;
-            const int s = a.t.offsets[tile], e = a.t.offsets[tile + 1];
             const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
             const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
             const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
             bool done = !(yy < a.t.H && xx < a.t.W);
             float T = 1.0f;
-            float4 r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tid < MB && s + tid < e) {
-                const int id = a.t.flatten[s + tid];
-                r0 = a.t.grec[2 * (int64_t)id];
-                r1 = a.t.grec[2 * (int64_t)id + 1];
-            }
             for (int b = s; b < e; b += MB, ++q) {
                 if (bar_red_popc_alu(!done) == 0) break;
                 const int slot = q % RING;
@@ -250,6 +277,10 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                     mbar_arrive(bar(Smem::ctrl_full + slot));
                 }
                 bar_sync_alu();
+                if (!fetched_n) {  // the next tile's first records: in flight while this tile is processed
+                    first_records(s_n, e_n, r0n, r1n);
+                    fetched_n = true;
+                }
                 r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
                 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (tid < MB && b + MB + tid < e) {
@@ -338,6 +369,14 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                     mbar_arrive(bar(Smem::rows_ready + slot));
                 }
             }
+            // rotate the queue: the unit requested at the start of this tile becomes the next-but-one
+            if (!fetched_n) first_records(s_n, e_n, r0n, r1n);
+            if (tid == 0) s_unit = unit_nn;
+            bar_sync_alu();
+            const int unit_new = s_unit;
+            bar_sync_alu();  // everyone has read s_unit before it is overwritten
+            unit = unit_n; unit_n = unit_new;
+            s = s_n; e = e_n; r0 = r0n; r1 = r1n;
         }
         {   // exit sentinel for the other roles
             const int slot = q % RING;
@@ -484,17 +523,19 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                 }
             }
         }
-    } else if (warp == kUWarp) {
-        // ===================================== U writer ======================================
+    } else if (warp >= kUWarp0 && warp < kUWarp0 + NUSLOT) {
+        // ===================================== U writers =====================================
         // slice ks = the interpolation weights of the tile's pixel row ks onto the 8 x 8 window: [16 px x 64 q], bf16
-        // hi/lo, MN-major (a pixel's 8 consecutive q = one 16-byte core-matrix row, q = 8 * source row + texel)
-        int us = 0, uuse = 0;
+        // hi/lo, MN-major (a pixel's 8 consecutive q = one 16-byte core-matrix row, q = 8 * source row + texel).
+        // Writer j owns ring slot j and the slices ks = j, j + NUSLOT, ...
+        const int us = warp - kUWarp0;
+        int uuse = 0;
         for (int q = 0;; ++q) {
             const int slot = q % RING;
             mbar_wait(bar(Smem::ctrl_full + slot), (q / RING) & 1);
             const int unit = ctrl[slot];
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(Smem::ctrl_empty + slot));
+            if (us == 0 && lane == 0) mbar_arrive(bar(Smem::ctrl_empty + slot));
             if (unit < 0) break;
             const int tile = unit_to_tile(unit, a.t.tw, a.t.th, kBand);
             const int ty = tile / a.t.tw, tx = tile % a.t.tw;
@@ -507,11 +548,11 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             float wx[QX];
 #pragma unroll
             for (int j = 0; j < QX; ++j) wx[j] = (j == x0 ? 1.0f - sx.l : 0.0f) + (j == x1 ? sx.l : 0.0f);
-            for (int ks = 0; ks < kTilePix / KSL; ++ks) {
+            uint8_t *blk = smem + Smem::uring + us * U_SLOT_BYTES;
+            for (int ks = us; ks < kTilePix / KSL; ks += NUSLOT, ++uuse) {
                 const SrcIdx sy = src_index(min(ty * kTile + ks, a.t.H - 1), a.scale_y, a.sh, a.nearest);
                 const int y0 = sy.i0 - ylo, y1 = sy.i1 - ylo;
                 if (uuse >= 1) mbar_wait(bar(Smem::u_empty + us), (uuse - 1) & 1);
-                uint8_t *blk = smem + Smem::uring + us * U_SLOT_BYTES;
 #pragma unroll
                 for (int i = 0; i < QY / 2; ++i) {
                     const int row = (lane >> 4) + 2 * i;  // source row of the window: 0..7
@@ -528,12 +569,12 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(Smem::u_full + us));
-                if (++us == NUSLOT) { us = 0; ++uuse; }
             }
         }
     } else if (warp == kMmaWarp) {
         // ======================================= MMA =========================================
-        int us = 0, uuse = 0, fs = 0, fuse = 0;
+        int ucnt[NUSLOT] = {0, 0, 0};  // uses of each U ring slot (slice ks lives in slot ks % NUSLOT, written by writer ks % NUSLOT)
+        int fs = 0, fuse = 0;
         const uint64_t a_hi0 = umma_smem_desc(sbase + Smem::w_hi, A_LBO, A_SBO);
         const uint64_t a_lo0 = umma_smem_desc(sbase + Smem::w_lo, A_LBO, A_SBO);
         const uint64_t a2_hi0 = umma_smem_desc(sbase + Smem::a2_hi, A_LBO, A_SBO);
@@ -555,6 +596,8 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
 #pragma unroll 1
             for (int ks = 0; ks < kTilePix / KSL; ++ks) {
                 if ((ks & 1) == 0) mbar_wait(bar(Smem::w_full + (ks >> 1)), q & 1);
+                const int us = ks % NUSLOT;
+                const int uuse = us == 0 ? ucnt[0] : us == 1 ? ucnt[1] : ucnt[2];
                 mbar_wait(bar(Smem::u_full + us), uuse & 1);
                 tc_fence_after();
                 const uint64_t a_hi = a_hi0 + (uint64_t)ks * kAStep, a_lo = a_lo0 + (uint64_t)ks * kAStep;
@@ -568,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                     if (ks & 1) umma_commit(bar(Smem::w_free + (ks >> 1)));
                 }
                 __syncwarp();
-                if (++us == NUSLOT) { us = 0; ++uuse; }
+                if (us == 0) ++ucnt[0]; else if (us == 1) ++ucnt[1]; else ++ucnt[2];
             }
             if (elect_one()) umma_commit(bar(Smem::d1_full + db));
             __syncwarp();
