@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
     auto bar = [&](int i) -> uint32_t { return sbase + Smem::bars + 8 * i; };
     RowInfo *rows = reinterpret_cast<RowInfo *>(smem + Smem::rows);
     volatile int *ctrl = reinterpret_cast<volatile int *>(smem + Smem::ctrl);
-    volatile int &s_unit = ctrl[8], &s_unit2 = ctrl[9];  // work-queue broadcast slot (ALU warps only)
+    volatile int &s_unit = ctrl[8];  // work-queue broadcast slot (ALU warps only)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Smem::tmem_slot);
 
     if (tid == 0) {
@@ -170,51 +170,27 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
         int q = 0;
         long long walked = 0;
         const uint32_t wslab = (uint32_t)(tid >> 3) * A_LBO + (uint32_t)(tid & 7) * 16;  // this pixel's K-row
-        // Work queue, two units deep: `unit` is being processed, `unit_n` is already known, and the request for the
-        // one after that is in flight -- so the next tile's list bounds and first 128 records are fetched while this
-        // tile is processed (a tile switch otherwise costs four dependent global round trips, ~3 us, per ~2.4 batches).
-        auto first_records = [&](int s_, int e_, float4 &r0_, float4 &r1_) {
-            r0_ = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-            r1_ = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tid < MB && s_ + tid < e_) {
-                const int id = a.t.flatten[s_ + tid];
-                r0_ = a.t.grec[2 * (int64_t)id];
-                r1_ = a.t.grec[2 * (int64_t)id + 1];
-            }
-        };
-        if (tid == 0) {
-            s_unit = atomicAdd(a.unit_counter, 1);
-            s_unit2 = atomicAdd(a.unit_counter, 1);
-        }
-        bar_sync_alu();
-        int unit = s_unit, unit_n = s_unit2;
-        bar_sync_alu();
-        int s = 0, e = 0;
-        float4 r0, r1;
-        if (unit < a.nunits) {
-            const int tile0 = unit_to_tile(unit, a.t.tw, a.t.th, a.band);
-            s = a.t.offsets[tile0];
-            e = a.t.offsets[tile0 + 1];
-        }
-        first_records(s, e, r0, r1);
-        while (unit < a.nunits) {
-            int unit_nn = 0;
-            if (tid == 0) unit_nn = atomicAdd(a.unit_counter, 1);  // consumed at the end of this tile
-            int s_n = 0, e_n = 0;
-            if (unit_n < a.nunits) {
-                const int tile_n = unit_to_tile(unit_n, a.t.tw, a.t.th, a.band);
-                s_n = a.t.offsets[tile_n];
-                e_n = a.t.offsets[tile_n + 1];
-            }
-            float4 r0n = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), r1n = make_float4(0.f, 0.f, 0.f, 0.f);
-            bool fetched_n = false;
+        while (true) {
+            if (tid == 0) s_unit = atomicAdd(a.unit_counter, 1);
+            bar_sync_alu();
+            const int unit = s_unit;
+            bar_sync_alu();  // everyone has read s_unit before it is overwritten
+            if (unit >= a.nunits) break;
             const int tile = unit_to_tile(unit, a.t.tw, a.t.th, a.band);
             const int ty = tile / a.t.tw, tx = tile % a.t.tw;
+            const int s = a.t.offsets[tile], e = a.t.offsets[tile + 1];
             const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
             const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
             const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
             bool done = !(yy < a.t.H && xx < a.t.W);
             float T = 1.0f;
+            // prefetch the first batch's record for row `tid` (threads 0..127)
+            float4 r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid < MB && s + tid < e) {
+                const int id = a.t.flatten[s + tid];
+                r0 = a.t.grec[2 * (int64_t)id];
+                r1 = a.t.grec[2 * (int64_t)id + 1];
+            }
             for (int b = s; b < e; b += MB, ++q) {
                 if (bar_red_popc_alu(!done) == 0) break;  // also: every warp is done reading gbuf of batch q-1
                 if (warp == 0 || warp == 7) trace(warp ? 1 : 0, 0, q, 0);
@@ -237,10 +213,6 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                     mbar_arrive(bar(Smem::ctrl_full + slot));
                 }
                 bar_sync_alu();
-                if (!fetched_n) {  // the next tile's first records: in flight while this tile is processed
-                    first_records(s_n, e_n, r0n, r1n);
-                    fetched_n = true;
-                }
                 // prefetch the next batch while this one is processed
                 r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
                 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -339,14 +311,6 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 }
                 if (warp == 0 || warp == 7) trace(warp ? 1 : 0, 2, q, 0);
             }
-            // rotate the queue: the unit requested at the start of this tile becomes the next-but-one
-            if (!fetched_n) first_records(s_n, e_n, r0n, r1n);
-            if (tid == 0) s_unit = unit_nn;
-            bar_sync_alu();
-            const int unit_new = s_unit;
-            bar_sync_alu();  // everyone has read s_unit before it is overwritten
-            unit = unit_n; unit_n = unit_new;
-            s = s_n; e = e_n; r0 = r0n; r1 = r1n;
         }
         // exit sentinel for the other roles
         {
