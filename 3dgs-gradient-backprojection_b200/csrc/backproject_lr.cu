@@ -167,6 +167,7 @@ struct LrArgs {
     int *unit_counter;
     long long *stats;
     int debug;  // GWBP_LR_DEBUG (experiment builds only): 1 = skip the accumulator reductions (timing only)
+    unsigned long long *trace;  // gwbp_debug_set_trace: CTA 0 records (role, event, batch, chunk, clock64); nullptr = off
 };
 
 __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, const __grid_constant__ CUtensorMap map_hi,
@@ -205,6 +206,16 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // optional event trace (debug only): roles 0 = ALU warp 0, 1 = converter warp 12, 2 = epilogue warp 8, 3 = MMA
+    int trace_n = 0;
+    auto trace = [&](int role, int ev, int q, int c) {
+        if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_n < 4096) {
+            unsigned long long *p = a.trace + ((size_t)role * 4096 + trace_n) * 2;
+            p[0] = ((unsigned long long)ev << 48) | ((unsigned long long)(c & 0xffff) << 32) | (unsigned)q;
+            p[1] = (unsigned long long)clock64();
+            ++trace_n;
+        }
+    };
 
     if (warp < 8) {
         // ======================================= ALU =========================================
@@ -260,6 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             float T = 1.0f;
             for (int b = s; b < e; b += MB, ++q) {
                 if (bar_red_popc_alu(!done) == 0) break;
+                if (warp == 0) trace(0, 0, q, 0);
                 const int slot = q % RING;
                 if (q >= RING) mbar_wait(bar(Smem::rows_free + slot), ((q / RING) - 1) & 1);
                 if (tid < MB) {
@@ -289,6 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                     r1 = a.t.grec[2 * (int64_t)id + 1];
                 }
                 if (q >= 1) mbar_wait(bar(Smem::w_free + warp), (q - 1) & 1);
+                if (warp == 0) trace(0, 1, q, 0);
                 walked += min(MB, e - b);
                 if (__all_sync(0xffffffffu, done)) {
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -368,6 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                     mbar_arrive(bar(Smem::w_full + warp));
                     mbar_arrive(bar(Smem::rows_ready + slot));
                 }
+                if (warp == 0) trace(0, 2, q, 0);
             }
             // rotate the queue: the unit requested at the start of this tile becomes the next-but-one
             if (!fetched_n) first_records(s_n, e_n, r0n, r1n);
@@ -417,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                 const int ncols = min(NC2, a.dp - c * NC2);
                 mbar_wait(bar(Smem::acc_full + ab), (u >> 1) & 1);
                 tc_fence_after();
+                if (quarter == 0) trace(2, 0, q, c);
                 for (int c0 = 0; c0 < ncols; c0 += 32) {
                     float v[32];
                     tmem_ld32(tmem + lane_base + (uint32_t)(TM_ACC + ab * NC2 + c0), v);
@@ -445,6 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(Smem::acc_empty + ab));
+                if (quarter == 0) trace(2, 1, q, c);
             }
             if (live) {
                 atomicAdd(a.den + gid, dn);
@@ -475,7 +491,9 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             const int db = q & 1;
             mbar_wait(bar(Smem::d1_full + db), (q >> 1) & 1);
             tc_fence_after();
+            if (quarter == 0) trace(1, 0, q, 0);
             if (q >= 1) mbar_wait(bar(Smem::a2_empty), (q - 1) & 1);  // GEMM2 of the previous batch has read A2
+            if (quarter == 0) trace(1, 1, q, 0);
 #pragma unroll 1
             for (int k0 = 0; k0 < NQ; k0 += 16) {
                 float t[16];
@@ -496,6 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(Smem::a2_full));
+            if (quarter == 0) trace(1, 2, q, 0);
         }
     } else if (warp == kProducerWarp) {
         // ===================================== producer ======================================
@@ -592,6 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             const int db = q & 1;
             if (q >= 2) mbar_wait(bar(Smem::d1_empty + db), ((q >> 1) - 1) & 1);
             tc_fence_after();
+            trace(3, 0, q, 0);
             const uint32_t d1 = tmem + (uint32_t)(TM_D1 + db * NQ);
 #pragma unroll 1
             for (int ks = 0; ks < kTilePix / KSL; ++ks) {
@@ -615,9 +635,11 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             }
             if (elect_one()) umma_commit(bar(Smem::d1_full + db));
             __syncwarp();
+            trace(3, 1, q, 0);
             // ---- GEMM2: acc = W' . F_low, one 192-column chunk at a time
             mbar_wait(bar(Smem::a2_full), q & 1);
             tc_fence_after();
+            trace(3, 2, q, 0);
             for (int c = 0; c < a.nchunks; ++c) {
                 const int u = q * a.nchunks + c, ab = u & 1;
                 const int ncols = min(NC2, a.dp - c * NC2);
@@ -646,6 +668,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                     if (c == a.nchunks - 1) umma_commit(bar(Smem::a2_empty));
                 }
                 __syncwarp();
+                trace(3, 3, q, c);
             }
         }
     }
@@ -761,6 +784,7 @@ int launch_backproject_lr(const TileCtx &t, const float *S, int sh, int sw, int6
     a.unit_counter = (int *)t.scratch;
     a.stats = stats;
     a.debug = 0;
+    a.trace = (unsigned long long *)tc_trace_buffer();
 #ifdef GWBP_EXPERIMENTS
     static const int dbg = getenv("GWBP_LR_DEBUG") ? atoi(getenv("GWBP_LR_DEBUG")) : 0;
     a.debug = dbg;
