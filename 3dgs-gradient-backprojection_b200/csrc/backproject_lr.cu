@@ -201,7 +201,10 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
 
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) { mbar_init(bar(Smem::w_full + i), 1); mbar_init(bar(Smem::w_free + i), 1); }
-        for (int i = 0; i < NUSLOT; ++i) { mbar_init(bar(Smem::u_full + i), 1); mbar_init(bar(Smem::u_empty + i), 1); }
+        for (int i = 0; i < NUSLOT; ++i) {
+            mbar_init(bar(Smem::u_full + i), 1);
+            mbar_init(bar(Smem::u_empty + i), 5);  // GEMM1 has read Ux (tcgen05.commit) + the 4 converter warps have read the y taps
+        }
         for (int i = 0; i < NFSTAGE; ++i) { mbar_init(bar(Smem::f_full + i), 1); mbar_init(bar(Smem::f_empty + i), 1); }
         mbar_init(bar(Smem::d1_full), 1);
         mbar_init(bar(Smem::d1_empty), 4);
@@ -538,7 +541,10 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(Smem::d1_empty));
+            if (lane == 0) {
+                mbar_arrive(bar(Smem::d1_empty));
+                mbar_arrive(bar(Smem::u_empty + (q & 1)));  // done with this slot's y-tap table
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(Smem::a2_full));
@@ -553,7 +559,11 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                 mbar_wait(bar(Smem::ctrl_full + slot), (q / RING) & 1);
                 const int unit = ctrl[slot];
                 mbar_arrive(bar(Smem::ctrl_empty + slot));
-                if (unit < 0) break;
+                if (unit < 0) {
+                    if (a.debug & 2) printf("blk %d producer exit q=%d stage=%d use=%d\n", (int)blockIdx.x, q, stage, use);
+                    break;
+                }
+                if (a.debug & 2) printf("blk %d producer q=%d unit=%d\n", (int)blockIdx.x, q, unit);
                 const int tile = unit_to_tile(unit, a.t.tw, a.t.th, kBand);
                 const int ty = tile / a.t.tw, tx = tile % a.t.tw;
                 const int ylo = src_index(min(ty * kTile, a.t.H - 1), a.scale_y, a.sh, a.nearest).i0;
@@ -628,6 +638,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             const int unit = ctrl[slot];
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(Smem::ctrl_empty + slot));
+            if ((a.debug & 2) && lane == 0) printf("blk %d mma q=%d unit=%d fs=%d fuse=%d\n", (int)blockIdx.x, q, unit, fs, fuse);
             if (unit < 0) break;
             // ---- GEMM1: H[:, (ks, xx)] = W[:, (ks, px)] . Ux, one K-step per pixel row into its own 16 TMEM columns
             const int ub = q & 1;

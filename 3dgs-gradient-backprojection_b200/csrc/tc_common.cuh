@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace gwbp {
 namespace tc {
@@ -49,7 +50,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+#ifdef GWBP_EXPERIMENTS  // experiment builds name the barriers that never completed (shared-memory byte address);
+        // time-based, because try_wait may suspend the thread for a system-dependent time per call
+        if ((++spins & 1023u) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            static __device__ unsigned long long t_first = 0;
+            if (t_first == 0) atomicCAS(&t_first, 0ull, now);
+            (void)t_first;
+        }
+        if (spins == (1u << 16) || spins == (1u << 19) || spins == (1u << 21))
+            printf("mbar_wait slow: block %d thread %d barrier smem+0x%x parity %u spins %u\n", (int)blockIdx.x, (int)threadIdx.x,
+                   bar, parity, spins);
+        if (spins > (1u << 24)) __trap();
+#else
         if (++spins > (1u << 26)) __trap();
+#endif
     }
 }
 
