@@ -138,6 +138,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {  // completed by tmem_ld_wait()
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
 // TMA: 3-D tensor-map box -> shared memory, completion counted on an mbarrier
 __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
     asm volatile(
@@ -516,25 +523,53 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             if (q >= 1) mbar_wait(bar(Smem::a2_empty), (q - 1) & 1);  // GEMM2 of the previous batch has read A2
             if (quarter == 0) trace(1, 1, q, 0);
             const float4 *ytab = reinterpret_cast<const float4 *>(smem + Smem::uring + (q & 1) * U_SLOT_BYTES + 2 * U_PART_BYTES);
-#pragma unroll 1
-            for (int yy = 0; yy < QY; ++yy) {
-                float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-                for (int py = 0; py < kTilePix / KSL; ++py) {
-                    const float4 yt = ytab[py];  // (y0 - ylo, y1 - ylo, 1 - ly, ly), warp-uniform
-                    const float wy = (__float_as_int(yt.x) == yy ? yt.z : 0.0f) + (__float_as_int(yt.y) == yy ? yt.w : 0.0f);
-                    if (wy != 0.0f) {
-                        float v[8];
-                        tmem_ld8(tmem + lane_base + (uint32_t)(TM_D1 + py * NU), v);
+            // one TMEM load per pixel row (the next one in flight while this one is scattered onto its <= 2 source rows);
+            // the 8 x 8 outputs stay in registers, the row selection is warp-uniform
+            float o[QY][8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o[j] = fmaf(wy, v[j], o[j]);
+            for (int yy = 0; yy < QY; ++yy)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[yy][j] = 0.0f;
+            uint32_t va[8], vb[8];
+            tmem_ld8_issue(tmem + lane_base + (uint32_t)TM_D1, va);
+#pragma unroll 1
+            for (int py = 0; py < kTilePix / KSL; py += 2) {
+                tmem_ld_wait();
+                tmem_ld8_issue(tmem + lane_base + (uint32_t)(TM_D1 + (py + 1) * NU), vb);
+                {
+                    const float4 yt = ytab[py];  // (y0 - ylo, y1 - ylo, 1 - ly, ly), warp-uniform
+                    const int y0 = __float_as_int(yt.x), y1 = __float_as_int(yt.y);
+#pragma unroll
+                    for (int yy = 0; yy < QY; ++yy) {
+                        const float wy = (y0 == yy ? yt.z : 0.0f) + (y1 == yy ? yt.w : 0.0f);
+                        if (y0 == yy || y1 == yy) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[yy][j] = fmaf(wy, __uint_as_float(va[j]), o[yy][j]);
+                        }
                     }
                 }
+                tmem_ld_wait();
+                if (py + 2 < kTilePix / KSL) tmem_ld8_issue(tmem + lane_base + (uint32_t)(TM_D1 + (py + 2) * NU), va);
+                {
+                    const float4 yt = ytab[py + 1];
+                    const int y0 = __float_as_int(yt.x), y1 = __float_as_int(yt.y);
+#pragma unroll
+                    for (int yy = 0; yy < QY; ++yy) {
+                        const float wy = (y0 == yy ? yt.z : 0.0f) + (y1 == yy ? yt.w : 0.0f);
+                        if (y0 == yy || y1 == yy) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[yy][j] = fmaf(wy, __uint_as_float(vb[j]), o[yy][j]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int yy = 0; yy < QY; ++yy) {
                 uint4 hi, lo;
-                split_bf16x2(o[0], o[1], hi.x, lo.x);
-                split_bf16x2(o[2], o[3], hi.y, lo.y);
-                split_bf16x2(o[4], o[5], hi.z, lo.z);
-                split_bf16x2(o[6], o[7], hi.w, lo.w);
+                split_bf16x2(o[yy][0], o[yy][1], hi.x, lo.x);
+                split_bf16x2(o[yy][2], o[yy][3], hi.y, lo.y);
+                split_bf16x2(o[yy][4], o[yy][5], hi.z, lo.z);
+                split_bf16x2(o[yy][6], o[yy][7], hi.w, lo.w);
                 const uint32_t off = (uint32_t)yy * A_LBO + goff;
                 *reinterpret_cast<uint4 *>(smem + Smem::a2_hi + off) = hi;
                 *reinterpret_cast<uint4 *>(smem + Smem::a2_lo + off) = lo;
