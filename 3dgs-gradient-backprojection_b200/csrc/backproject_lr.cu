@@ -4,34 +4,33 @@
 //
 //      num[g, :] += sum_p w(g,p) * (U F_low)[p, :]  =  sum_q ( sum_p w(g,p) U[p,q] ) F_low[q, :]
 //
-// U = the interpolation operator (4 taps per pixel, torch align_corners=False arithmetic), which is SEPARABLE:
-// U[(py,px),(yy,xx)] = Uy[py,yy] * Ux[px,xx].  Per (tile, batch of 128 Gaussians) the kernel runs TWO chained tcgen05
-// stages instead of one big GEMM:
-//      GEMM1   H[128 g x (py, xx)] = W[128 g x (py, px)] . Ux[px x xx]   one K = 16 MMA per pixel row py against the SAME
-//                                                                       tiny operand Ux [16 px x 8 texels] (1 KB, static
-//                                                                       per tile): the weights down-sampled along x
-//      convert W'[g, (yy, xx)]     = sum_py Uy[py, yy] * H[g, (py, xx)]   <= 2 taps per pixel row, in registers while the
-//                                                                       converter warps move TMEM -> bf16 hi/lo -> smem
-//      GEMM2   acc[128 g x D]      = W'[128 g x 64 q] . F_low[64 q x D]   q = the tile's 8 x 8 window of the low-res map,
-//                                                                       fetched by TMA tensor maps
-// i.e. the weights are DOWN-sampled (the adjoint of the up-sample) and contracted with the L2-resident low-resolution
-// map: ~1/6 of the tensor work of bp_tc_kernel, 1/4 of its shared-memory operand traffic, and the weight block W is
-// consumed by one short sweep, so the ALU warps never wait for a second column-chunk sweep.  (A first version contracted
-// W with the full U [256 px x 64 q]; regenerating its 16 slices per batch made the GEMM1 sweep take 10.9 k of a 27 k-cycle
-// batch period -- profiles/r02_lr_trace.txt.)
+// U = the interpolation operator (4 taps per pixel, torch align_corners=False arithmetic).  Per (tile, batch of 128
+// Gaussians) the kernel runs TWO chained tcgen05 GEMMs instead of one big one:
+//      GEMM1   W'[128 g x 64 q] = W[128 g x 256 px] . U[256 px x 64 q]     (q = the tile's window of the low-res map:
+//                                                                          8 source rows x 8 texels)
+//      GEMM2   acc[128 g x D]  = W'[128 g x 64 q]  . F_low[64 q x D]       (F_low window fetched by TMA tensor maps)
+// i.e. the weights are DOWN-sampled on the tensor cores (the adjoint of the up-sample) and contracted with the
+// L2-resident low-resolution map: ~1/5 of the tensor work of bp_tc_kernel, 1/4 of its shared-memory operand traffic,
+// and the weight block W is consumed by one short sweep, so the ALU warps never wait for a second column-chunk sweep.
 //
-// Persistent CTA, 1 per SM, 608 threads, warp-specialised:
+// Persistent CTA, 1 per SM, 672 threads, warp-specialised:
 //   warps 0-7   ALU       : exactly bp_tc_kernel's weight generation (thread = pixel, sequential T, bf16 hi/lo W^T)
 //   warps 8-11  epilogue  : exactly bp_tc_kernel's (tcgen05.ld -> smem transpose -> red.global.add.v4.f32 rows)
-//   warps 12-15 converter : tcgen05.ld H (fp32, lane = Gaussian), y-interpolation, bf16 hi/lo -> K-major A operand of GEMM2
+//   warps 12-15 converter : tcgen05.ld W' (fp32, lane = Gaussian) -> bf16 hi/lo -> A operand of GEMM2 in smem
 //   warp 16     producer  : cp.async.bulk.tensor.3d (TMA tensor map) of the F_low window, K-step by K-step
 //   warp 17     MMA       : one elected lane issues both GEMMs
-//   warp 18     U writer  : per batch, Ux (hi/lo) and the y-tap table of the tile
+//   warps 18-20 U writers : regenerate the 16-pixel-row slices of U (4 KB each, hi/lo) per batch, one ring slot per warp
+//                           (a single writer made the GEMM1 sweep wait ~600 cycles per slice: profiles/r02_bp_lr_*)
 // Split-bf16 everywhere (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM): ~2^-16 per contraction.
 //
-// TMEM (512 columns): acc buffers at 0 / 128 (128 columns each), H at 256 (16 pixel rows x 16 columns, 8 of them used).
+// Measured alternative (git history, "separable down-sampling"): contracting x on the tensor cores against a static 1 KB
+// operand (16 MMAs of N = 16 per batch) and applying the y taps in the converters removes the U writers, but the 16 tiny
+// MMAs still take ~6 k cycles to issue (~125 cycles each, size-independent) and the converters' 16 dependent TMEM
+// loads ~9 k: 1.17 ms against 1.08 ms for this version (profiles/r02_lr_trace_separable.txt).
+//
+// TMEM (512 columns): acc buffers at 0 / 192 (192 columns each), W' buffers at 384 / 448 (64 columns each).
 // The packed low-res map (flow_pack_kernel) is [y][channel group][x][8 channels] bf16, hi and lo: a TMA box of
-// {8 texels x 8 channels, 16 groups, 2 rows} lands in shared memory directly in UMMA core-matrix order.
+// {8 texels x 8 channels, 24 groups, 2 rows} lands in shared memory directly in UMMA core-matrix order.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -47,27 +46,26 @@ namespace {
 constexpr int MB = 128;            // Gaussians per batch = UMMA M
 constexpr int KSL = 16;            // pixels per K-slice of GEMM1 (one tile row) = one UMMA K step
 constexpr int QY = 8, QX = 8;      // low-res window of a tile: source rows x texels (one core matrix per row)
-constexpr int NQ = QY * QX;        // 64 = GEMM2 K
-constexpr int NU = 16;             // GEMM1 N: 8 texel columns + 8 zero columns (the smallest UMMA N for M = 128)
-constexpr int NC2 = 128;           // feature columns per GEMM2 chunk (2 x 128 + 16 x 16 = all 512 TMEM columns)
+constexpr int NQ = QY * QX;        // 64 = GEMM1 N = GEMM2 K
+constexpr int NC2 = 192;           // feature columns per GEMM2 chunk (2 x 192 + 2 x 64 = all 512 TMEM columns)
 constexpr int NG2 = NC2 / 8;       // channel groups per chunk = TMA box extent
 constexpr int K2STEPS = NQ / 16;   // 4
 constexpr int RING = 3;            // batches in flight between ALU and epilogue
-constexpr uint32_t A_SBO = 128, A_LBO = (MB / 8) * 128;    // W^T (MN-major) and W' (K-major): 16 row-groups of 8 Gaussians per K-group
+constexpr uint32_t A_SBO = 128, A_LBO = (MB / 8) * 128;    // W^T and W'^T: MN-major, 16 row-groups of 8 Gaussians per K-group
 constexpr int W_PART_BYTES = (kTilePix / 8) * A_LBO;       // 64 KB per hi / lo part
 constexpr int A2_PART_BYTES = (NQ / 8) * A_LBO;            // 16 KB per hi / lo part
-constexpr uint32_t U_LBO = (NU / 8) * 128;                 // Ux: [16 px x 16 cols], MN-major
-constexpr int U_PART_BYTES = KSL * NU * 2;                 // 512 B
-constexpr int U_SLOT_BYTES = 2 * U_PART_BYTES + 256;       // hi | lo | y-tap table (16 x float4)
-constexpr int NUSLOT = 2;                                  // per-batch slots
-constexpr uint32_t F_LBO = NG2 * 128;                      // F_low stage: [16 q x 128 cols], MN-major as TMA writes it
-constexpr int F_PART_BYTES = KSL * NC2 * 2;                // 4 KB
+constexpr uint32_t U_LBO = (NQ / 8) * 128;                 // U slice: [16 px x 64 q], MN-major
+constexpr int U_PART_BYTES = KSL * NQ * 2;                 // 2 KB
+constexpr int U_SLOT_BYTES = 2 * U_PART_BYTES;
+constexpr int NUSLOT = 3;
+constexpr uint32_t F_LBO = NG2 * 128;                      // F_low stage: [16 q x 192 cols], MN-major as TMA writes it
+constexpr int F_PART_BYTES = KSL * NC2 * 2;                // 6 KB
 constexpr int F_STAGE_BYTES = 2 * F_PART_BYTES;
-constexpr int NFSTAGE = 4;
+constexpr int NFSTAGE = 3;
 constexpr int EPI_COLS = 32, EPI_ROWS = 16, EPI_PITCH = EPI_COLS * 4 + 16;
 constexpr int TM_ACC = 0, TM_D1 = 2 * NC2;                 // TMEM column bases
 
-constexpr int kEpiWarp0 = 8, kCvtWarp0 = 12, kProducerWarp = 16, kMmaWarp = 17, kUWarp = 18, kThreads = 19 * 32;
+constexpr int kEpiWarp0 = 8, kCvtWarp0 = 12, kProducerWarp = 16, kMmaWarp = 17, kUWarp0 = 18, kThreads = (18 + NUSLOT) * 32;
 
 struct RowInfo {
     int gid[MB];
@@ -88,14 +86,15 @@ struct Smem {
     static constexpr int ctrl = rows + RING * (int)sizeof(RowInfo);
     static constexpr int bars = ctrl + 64;
     static constexpr int w_full = 0, w_free = 8, u_full = 16, u_empty = u_full + NUSLOT, f_full = u_empty + NUSLOT,
-                         f_empty = f_full + NFSTAGE, d1_full = f_empty + NFSTAGE, d1_empty = d1_full + 1,
-                         a2_full = d1_empty + 1, a2_empty = a2_full + 1, acc_full = a2_empty + 1, acc_empty = acc_full + 2,
+                         f_empty = f_full + NFSTAGE, d1_full = f_empty + NFSTAGE, d1_empty = d1_full + 2,
+                         a2_full = d1_empty + 2, a2_empty = a2_full + 1, acc_full = a2_empty + 1, acc_empty = acc_full + 2,
                          rows_ready = acc_empty + 2, rows_free = rows_ready + RING, ctrl_full = rows_free + RING,
                          ctrl_empty = ctrl_full + RING, nbars = ctrl_empty + RING;
     static constexpr int tmem_slot = bars + nbars * 8;
     static constexpr int total = tmem_slot + 16;
 };
 static_assert(Smem::total + 256 <= 232448, "shared memory budget (227 KB) exceeded");
+static_assert(NUSLOT == 3, "the MMA warp tracks three U slots");
 static_assert(Smem::fring % 128 == 0 && Smem::uring % 128 == 0 && Smem::a2_hi % 128 == 0, "operand alignment");
 
 __device__ __forceinline__ int bar_red_popc_alu(bool pred) {
@@ -124,25 +123,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// 32 lanes x 8 columns of fp32
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {  // completed by tmem_ld_wait()
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
 }
 
 // TMA: 3-D tensor-map box -> shared memory, completion counted on an mbarrier
@@ -208,14 +188,11 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
 
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) { mbar_init(bar(Smem::w_full + i), 1); mbar_init(bar(Smem::w_free + i), 1); }
-        for (int i = 0; i < NUSLOT; ++i) {
-            mbar_init(bar(Smem::u_full + i), 1);
-            mbar_init(bar(Smem::u_empty + i), 5);  // GEMM1 has read Ux (tcgen05.commit) + the 4 converter warps have read the y taps
-        }
+        for (int i = 0; i < NUSLOT; ++i) { mbar_init(bar(Smem::u_full + i), 1); mbar_init(bar(Smem::u_empty + i), 1); }
         for (int i = 0; i < NFSTAGE; ++i) { mbar_init(bar(Smem::f_full + i), 1); mbar_init(bar(Smem::f_empty + i), 1); }
-        mbar_init(bar(Smem::d1_full), 1);
-        mbar_init(bar(Smem::d1_empty), 4);
         for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(Smem::d1_full + i), 1);
+            mbar_init(bar(Smem::d1_empty + i), 4);
             mbar_init(bar(Smem::acc_full + i), 1);
             mbar_init(bar(Smem::acc_empty + i), 4);
         }
@@ -504,12 +481,11 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
         }
     } else if (warp >= kCvtWarp0 && warp < kCvtWarp0 + 4) {
         // ===================================== converter =====================================
-        // H[g, (py, xx)] (fp32 in TMEM, lane = Gaussian row) -> W'[g, (yy, xx)] = sum_py Uy[py, yy] H[g, (py, xx)]
-        // -> bf16 hi/lo, K-major A operand of GEMM2: a Gaussian's 8 texels of one source row = one 16-byte row
+        // W' (fp32 in TMEM, lane = Gaussian row) -> bf16 hi/lo, MN-major A operand of GEMM2 (same layout as W^T)
         const int quarter = warp & 3;
         const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
         const int g = 32 * quarter + lane;
-        const uint32_t goff = (uint32_t)(g >> 3) * A_SBO + (uint32_t)(g & 7) * 16;
+        const uint32_t goff = (uint32_t)(g >> 3) * A_SBO + (uint32_t)(g & 7) * 2;
         for (int q = 0;; ++q) {
             const int slot = q % RING;
             mbar_wait(bar(Smem::ctrl_full + slot), (q / RING) & 1);
@@ -517,69 +493,29 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             __syncwarp();
             if (quarter == 0 && lane == 0) mbar_arrive(bar(Smem::ctrl_empty + slot));
             if (unit < 0) break;
-            mbar_wait(bar(Smem::d1_full), q & 1);
+            const int db = q & 1;
+            mbar_wait(bar(Smem::d1_full + db), (q >> 1) & 1);
             tc_fence_after();
             if (quarter == 0) trace(1, 0, q, 0);
             if (q >= 1) mbar_wait(bar(Smem::a2_empty), (q - 1) & 1);  // GEMM2 of the previous batch has read A2
             if (quarter == 0) trace(1, 1, q, 0);
-            const float4 *ytab = reinterpret_cast<const float4 *>(smem + Smem::uring + (q & 1) * U_SLOT_BYTES + 2 * U_PART_BYTES);
-            // one TMEM load per pixel row (the next one in flight while this one is scattered onto its <= 2 source rows);
-            // the 8 x 8 outputs stay in registers, the row selection is warp-uniform
-            float o[QY][8];
-#pragma unroll
-            for (int yy = 0; yy < QY; ++yy)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[yy][j] = 0.0f;
-            uint32_t va[8], vb[8];
-            tmem_ld8_issue(tmem + lane_base + (uint32_t)TM_D1, va);
 #pragma unroll 1
-            for (int py = 0; py < kTilePix / KSL; py += 2) {
-                tmem_ld_wait();
-                tmem_ld8_issue(tmem + lane_base + (uint32_t)(TM_D1 + (py + 1) * NU), vb);
-                {
-                    const float4 yt = ytab[py];  // (y0 - ylo, y1 - ylo, 1 - ly, ly), warp-uniform
-                    const int y0 = __float_as_int(yt.x), y1 = __float_as_int(yt.y);
+            for (int k0 = 0; k0 < NQ; k0 += 16) {
+                float t[16];
+                tmem_ld16(tmem + lane_base + (uint32_t)(TM_D1 + db * NQ + k0), t);
 #pragma unroll
-                    for (int yy = 0; yy < QY; ++yy) {
-                        const float wy = (y0 == yy ? yt.z : 0.0f) + (y1 == yy ? yt.w : 0.0f);
-                        if (y0 == yy || y1 == yy) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) o[yy][j] = fmaf(wy, __uint_as_float(va[j]), o[yy][j]);
-                        }
-                    }
+                for (int i = 0; i < 16; ++i) {
+                    const int k = k0 + i;
+                    const __nv_bfloat16 h = __float2bfloat16_rn(t[i]);
+                    const __nv_bfloat16 l = __float2bfloat16_rn(t[i] - __bfloat162float(h));
+                    const uint32_t off = (uint32_t)(k >> 3) * A_LBO + (uint32_t)(k & 7) * 16 + goff;
+                    *reinterpret_cast<__nv_bfloat16 *>(smem + Smem::a2_hi + off) = h;
+                    *reinterpret_cast<__nv_bfloat16 *>(smem + Smem::a2_lo + off) = l;
                 }
-                tmem_ld_wait();
-                if (py + 2 < kTilePix / KSL) tmem_ld8_issue(tmem + lane_base + (uint32_t)(TM_D1 + (py + 2) * NU), va);
-                {
-                    const float4 yt = ytab[py + 1];
-                    const int y0 = __float_as_int(yt.x), y1 = __float_as_int(yt.y);
-#pragma unroll
-                    for (int yy = 0; yy < QY; ++yy) {
-                        const float wy = (y0 == yy ? yt.z : 0.0f) + (y1 == yy ? yt.w : 0.0f);
-                        if (y0 == yy || y1 == yy) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) o[yy][j] = fmaf(wy, __uint_as_float(vb[j]), o[yy][j]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int yy = 0; yy < QY; ++yy) {
-                uint4 hi, lo;
-                split_bf16x2(o[yy][0], o[yy][1], hi.x, lo.x);
-                split_bf16x2(o[yy][2], o[yy][3], hi.y, lo.y);
-                split_bf16x2(o[yy][4], o[yy][5], hi.z, lo.z);
-                split_bf16x2(o[yy][6], o[yy][7], hi.w, lo.w);
-                const uint32_t off = (uint32_t)yy * A_LBO + goff;
-                *reinterpret_cast<uint4 *>(smem + Smem::a2_hi + off) = hi;
-                *reinterpret_cast<uint4 *>(smem + Smem::a2_lo + off) = lo;
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bar(Smem::d1_empty));
-                mbar_arrive(bar(Smem::u_empty + (q & 1)));  // done with this slot's y-tap table
-            }
+            if (lane == 0) mbar_arrive(bar(Smem::d1_empty + db));
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(Smem::a2_full));
@@ -594,11 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                 mbar_wait(bar(Smem::ctrl_full + slot), (q / RING) & 1);
                 const int unit = ctrl[slot];
                 mbar_arrive(bar(Smem::ctrl_empty + slot));
-                if (unit < 0) {
-                    if (a.debug & 2) printf("blk %d producer exit q=%d stage=%d use=%d\n", (int)blockIdx.x, q, stage, use);
-                    break;
-                }
-                if (a.debug & 2) printf("blk %d producer q=%d unit=%d\n", (int)blockIdx.x, q, unit);
+                if (unit < 0) break;
                 const int tile = unit_to_tile(unit, a.t.tw, a.t.th, kBand);
                 const int ty = tile / a.t.tw, tx = tile % a.t.tw;
                 const int ylo = src_index(min(ty * kTile, a.t.H - 1), a.scale_y, a.sh, a.nearest).i0;
@@ -615,92 +547,98 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                 }
             }
         }
-    } else if (warp == kUWarp) {
-        // ===================================== U writer ======================================
-        // per batch: Ux [16 px x 16 cols] (cols 0-7 = the x taps of pixel column px on the window's 8 texels, cols 8-15
-        // zero), bf16 hi/lo, MN-major; and the y-tap table of the tile's 16 pixel rows for the converters
+    } else if (warp >= kUWarp0 && warp < kUWarp0 + NUSLOT) {
+        // ===================================== U writers =====================================
+        // slice ks = the interpolation weights of the tile's pixel row ks onto the 8 x 8 window: [16 px x 64 q], bf16
+        // hi/lo, MN-major (a pixel's 8 consecutive q = one 16-byte core-matrix row, q = 8 * source row + texel).
+        // Writer j owns ring slot j and the slices ks = j, j + NUSLOT, ...
+        const int us = warp - kUWarp0;
+        int uuse = 0;
         for (int q = 0;; ++q) {
             const int slot = q % RING;
             mbar_wait(bar(Smem::ctrl_full + slot), (q / RING) & 1);
             const int unit = ctrl[slot];
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(Smem::ctrl_empty + slot));
+            if (us == 0 && lane == 0) mbar_arrive(bar(Smem::ctrl_empty + slot));
             if (unit < 0) break;
             const int tile = unit_to_tile(unit, a.t.tw, a.t.th, kBand);
             const int ty = tile / a.t.tw, tx = tile % a.t.tw;
             const int ylo = src_index(min(ty * kTile, a.t.H - 1), a.scale_y, a.sh, a.nearest).i0;
             const int xlo = src_index(min(tx * kTile, a.t.W - 1), a.scale_x, a.sw, a.nearest).i0;
-            const int ub = q & 1;
-            if (q >= 2) mbar_wait(bar(Smem::u_empty + ub), ((q >> 1) - 1) & 1);
-            uint8_t *blk = smem + Smem::uring + ub * U_SLOT_BYTES;
-            const int p = lane & 15, ng = lane >> 4;
-            uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-            if (ng == 0) {
-                const SrcIdx sx = src_index(min(tx * kTile + p, a.t.W - 1), a.scale_x, a.sw, a.nearest);
-                const int x0 = sx.i0 - xlo, x1 = sx.i1 - xlo;
-                float wx[QX];
+            // this lane's four (pixel, source row) items: item = lane + 32 i -> p = item % 16, row = item / 16
+            const int p = lane & 15;
+            const SrcIdx sx = src_index(min(tx * kTile + p, a.t.W - 1), a.scale_x, a.sw, a.nearest);
+            const int x0 = sx.i0 - xlo, x1 = sx.i1 - xlo;
+            float wx[QX];
 #pragma unroll
-                for (int j = 0; j < QX; ++j) wx[j] = (j == x0 ? 1.0f - sx.l : 0.0f) + (j == x1 ? sx.l : 0.0f);
-                split_bf16x2(wx[0], wx[1], hi.x, lo.x);
-                split_bf16x2(wx[2], wx[3], hi.y, lo.y);
-                split_bf16x2(wx[4], wx[5], hi.z, lo.z);
-                split_bf16x2(wx[6], wx[7], hi.w, lo.w);
+            for (int j = 0; j < QX; ++j) wx[j] = (j == x0 ? 1.0f - sx.l : 0.0f) + (j == x1 ? sx.l : 0.0f);
+            uint8_t *blk = smem + Smem::uring + us * U_SLOT_BYTES;
+            for (int ks = us; ks < kTilePix / KSL; ks += NUSLOT, ++uuse) {
+                const SrcIdx sy = src_index(min(ty * kTile + ks, a.t.H - 1), a.scale_y, a.sh, a.nearest);
+                const int y0 = sy.i0 - ylo, y1 = sy.i1 - ylo;
+                if (uuse >= 1) mbar_wait(bar(Smem::u_empty + us), (uuse - 1) & 1);
+#pragma unroll
+                for (int i = 0; i < QY / 2; ++i) {
+                    const int row = (lane >> 4) + 2 * i;  // source row of the window: 0..7
+                    const float wy = (row == y0 ? 1.0f - sy.l : 0.0f) + (row == y1 ? sy.l : 0.0f);
+                    uint4 hi, lo;
+                    split_bf16x2(wy * wx[0], wy * wx[1], hi.x, lo.x);
+                    split_bf16x2(wy * wx[2], wy * wx[3], hi.y, lo.y);
+                    split_bf16x2(wy * wx[4], wy * wx[5], hi.z, lo.z);
+                    split_bf16x2(wy * wx[6], wy * wx[7], hi.w, lo.w);
+                    const uint32_t off = (uint32_t)(p >> 3) * U_LBO + (uint32_t)row * 128 + (uint32_t)(p & 7) * 16;
+                    *reinterpret_cast<uint4 *>(blk + off) = hi;
+                    *reinterpret_cast<uint4 *>(blk + U_PART_BYTES + off) = lo;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(Smem::u_full + us));
             }
-            const uint32_t off = (uint32_t)(p >> 3) * U_LBO + (uint32_t)ng * 128 + (uint32_t)(p & 7) * 16;
-            *reinterpret_cast<uint4 *>(blk + off) = hi;
-            *reinterpret_cast<uint4 *>(blk + U_PART_BYTES + off) = lo;
-            if (lane < kTilePix / KSL) {
-                const SrcIdx sy = src_index(min(ty * kTile + lane, a.t.H - 1), a.scale_y, a.sh, a.nearest);
-                reinterpret_cast<float4 *>(blk + 2 * U_PART_BYTES)[lane] =
-                    make_float4(__int_as_float(sy.i0 - ylo), __int_as_float(sy.i1 - ylo), 1.0f - sy.l, sy.l);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(Smem::u_full + ub));
         }
     } else if (warp == kMmaWarp) {
         // ======================================= MMA =========================================
+        int ucnt[NUSLOT] = {0, 0, 0};  // uses of each U ring slot (slice ks lives in slot ks % NUSLOT, written by writer ks % NUSLOT)
         int fs = 0, fuse = 0;
         const uint64_t a_hi0 = umma_smem_desc(sbase + Smem::w_hi, A_LBO, A_SBO);
         const uint64_t a_lo0 = umma_smem_desc(sbase + Smem::w_lo, A_LBO, A_SBO);
         const uint64_t a2_hi0 = umma_smem_desc(sbase + Smem::a2_hi, A_LBO, A_SBO);
         const uint64_t a2_lo0 = umma_smem_desc(sbase + Smem::a2_lo, A_LBO, A_SBO);
         constexpr uint64_t kAStep = (2 * A_LBO) >> 4;  // start-address advance per 16-element K-slice (W and W')
-        constexpr uint32_t idesc1 = umma_idesc_bf16(MB, NU, true, true);
+        constexpr uint32_t idesc1 = umma_idesc_bf16(MB, NQ, true, true);
         for (int q = 0;; ++q) {
             const int slot = q % RING;
             mbar_wait(bar(Smem::ctrl_full + slot), (q / RING) & 1);
             const int unit = ctrl[slot];
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(Smem::ctrl_empty + slot));
-            if ((a.debug & 2) && lane == 0) printf("blk %d mma q=%d unit=%d fs=%d fuse=%d\n", (int)blockIdx.x, q, unit, fs, fuse);
             if (unit < 0) break;
-            // ---- GEMM1: H[:, (ks, xx)] = W[:, (ks, px)] . Ux, one K-step per pixel row into its own 16 TMEM columns
-            const int ub = q & 1;
-            if (q >= 1) mbar_wait(bar(Smem::d1_empty), (q - 1) & 1);
-            mbar_wait(bar(Smem::u_full + ub), (q >> 1) & 1);
+            // ---- GEMM1: W' = W . U into D1[q & 1]
+            const int db = q & 1;
+            if (q >= 2) mbar_wait(bar(Smem::d1_empty + db), ((q >> 1) - 1) & 1);
             tc_fence_after();
             trace(3, 0, q, 0);
-            const uint32_t ubase = sbase + Smem::uring + ub * U_SLOT_BYTES;
-            const uint64_t u_hi = umma_smem_desc(ubase, U_LBO, 128), u_lo = umma_smem_desc(ubase + U_PART_BYTES, U_LBO, 128);
+            const uint32_t d1 = tmem + (uint32_t)(TM_D1 + db * NQ);
 #pragma unroll 1
             for (int ks = 0; ks < kTilePix / KSL; ++ks) {
                 if ((ks & 1) == 0) mbar_wait(bar(Smem::w_full + (ks >> 1)), q & 1);
+                const int us = ks % NUSLOT;
+                const int uuse = us == 0 ? ucnt[0] : us == 1 ? ucnt[1] : ucnt[2];
+                mbar_wait(bar(Smem::u_full + us), uuse & 1);
                 tc_fence_after();
                 const uint64_t a_hi = a_hi0 + (uint64_t)ks * kAStep, a_lo = a_lo0 + (uint64_t)ks * kAStep;
-                const uint32_t d1 = tmem + (uint32_t)(TM_D1 + ks * NU);
+                const uint32_t ub = sbase + Smem::uring + us * U_SLOT_BYTES;
+                const uint64_t u_hi = umma_smem_desc(ub, U_LBO, 128), u_lo = umma_smem_desc(ub + U_PART_BYTES, U_LBO, 128);
                 if (elect_one()) {
-                    umma_bf16(d1, a_hi, u_hi, idesc1, 0u);
+                    umma_bf16(d1, a_hi, u_hi, idesc1, ks > 0 ? 1u : 0u);
                     umma_bf16(d1, a_hi, u_lo, idesc1, 1u);
                     umma_bf16(d1, a_lo, u_hi, idesc1, 1u);
+                    umma_commit(bar(Smem::u_empty + us));
                     if (ks & 1) umma_commit(bar(Smem::w_free + (ks >> 1)));
                 }
                 __syncwarp();
+                if (us == 0) ++ucnt[0]; else if (us == 1) ++ucnt[1]; else ++ucnt[2];
             }
-            if (elect_one()) {
-                umma_commit(bar(Smem::u_empty + ub));
-                umma_commit(bar(Smem::d1_full));
-            }
+            if (elect_one()) umma_commit(bar(Smem::d1_full + db));
             __syncwarp();
             trace(3, 1, q, 0);
             // ---- GEMM2: acc = W' . F_low, one 192-column chunk at a time
@@ -710,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             for (int c = 0; c < a.nchunks; ++c) {
                 const int u = q * a.nchunks + c, ab = u & 1;
                 const int ncols = min(NC2, a.dp - c * NC2);
-                const uint32_t idesc2 = umma_idesc_bf16(MB, ncols, false, true);  // A = W' K-major, B = F_low MN-major
+                const uint32_t idesc2 = umma_idesc_bf16(MB, ncols, true, true);
                 if (u >= 2) mbar_wait(bar(Smem::acc_empty + ab), ((u >> 1) - 1) & 1);
                 tc_fence_after();
                 const uint32_t d2 = tmem + (uint32_t)(TM_ACC + ab * NC2);

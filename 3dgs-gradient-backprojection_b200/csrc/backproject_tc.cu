@@ -357,9 +357,9 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 mbar_wait(bar(Smem::acc_full + ab), (u >> 1) & 1);
                 tc_fence_after();
                 if (quarter == 0) trace(2, 0, q, c);
-                // 32-column blocks, the TMEM load of block k+1 in flight while block k is staged and reduced (the load
-                // latency was fully exposed 8 times per chunk: ~10 k cycles per chunk in the clock64 trace)
-                auto reduce_block = [&](const uint32_t (&v)[32], int c0) {
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tmem + lane_base + (uint32_t)(ab * NCMAX + c0), v);
                     const int col = c * NCMAX + c0 + 4 * piece;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {  // lanes 0-15, then lanes 16-31 stage their rows
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                         if (live && (lane >> 4) == half) {
 #pragma unroll
                             for (int i = 0; i < 32; i += 4)
-                                *reinterpret_cast<uint4 *>(srow + 4 * i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                *reinterpret_cast<float4 *>(srow + 4 * i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                         }
                         __syncwarp();
                         if (col < a.d) {
@@ -380,19 +380,6 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                                 }
                             }
                         }
-                    }
-                };
-                const uint32_t tbase = tmem + lane_base + (uint32_t)(ab * NCMAX);
-                uint32_t va[32], vb[32];
-                tmem_ld32_issue(tbase, va);
-                for (int c0 = 0; c0 < ncols; c0 += 64) {
-                    tmem_ld_wait();
-                    if (c0 + 32 < ncols) tmem_ld32_issue(tbase + (uint32_t)(c0 + 32), vb);
-                    reduce_block(va, c0);
-                    if (c0 + 32 < ncols) {
-                        tmem_ld_wait();
-                        if (c0 + 64 < ncols) tmem_ld32_issue(tbase + (uint32_t)(c0 + 64), va);
-                        reduce_block(vb, c0 + 32);
                     }
                 }
                 tc_fence_before();
