@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import gwbp  # noqa: E402
-from helpers import oracle_job, row_cosine, row_rel_err  # noqa: E402
+from helpers import oracle_job, oracle_margins, row_cosine, row_rel_err  # noqa: E402
 from oracle import c_oracle, gsplat_oracle  # noqa: E402
 
 
@@ -27,6 +27,7 @@ def run(name, n, views, W, H, d, seed=0, enc=24):
     num_o, den_o, st = oracle_job(c_oracle, sc, vm, K, W, H, feats, d)
     f_o = gsplat_oracle.finalize(num_o, den_o + 1e-12)
     sel = den_o > 1e-6
+    margin = oracle_margins(c_oracle, sc, vm, K, W, H, den_o)[sel]  # smallest relative distance to a compositing threshold
     print(f"== {name}: N={n} views={views} {W}x{H} D={d}; rows with den>1e-6: {int(sel.sum())}; "
           f"oracle rows_nonzero={sum(s['rows_nonzero'] for s in st)} pairs={sum(s['pairs'] for s in st)}")
     for kernel in ("simt", "tc"):
@@ -43,6 +44,10 @@ def run(name, n, views, W, H, d, seed=0, enc=24):
         cos, _ = row_cosine(f[sel], f_o[sel])
         den_rel = np.abs(den[sel] - den_o[sel]) / den_o[sel]
         mask_eq = np.array_equal(den > 5e-13, den_o > 0)
+        bad = (rel > 1e-4) | (cos < 0.9999) | (den_rel > 1e-4)
+        print(f"  [{kernel:4s}] rows above a bar: {int(bad.sum())}, of which NOT within 1e-5 of a threshold: "
+              f"{int((bad & ~(margin < 1e-5)).sum())}; rows within 1e-5 of a threshold: {100 * float((margin < 1e-5).mean()):.2f} % of all; "
+              f"other rows: rel max {rel[~bad].max():.3e} cos min {cos[~bad].min():.8f} den rel max {den_rel[~bad].max():.3e}")
         print(f"  [{kernel:4s}] feature row rel-err: max {rel.max():.3e} p99.9 {np.percentile(rel, 99.9):.3e} "
               f"median {np.median(rel):.3e} | rows > 1e-4: {int((rel > 1e-4).sum())} | cosine min {cos.min():.8f} | "
               f"den rel-err p99.9 {np.percentile(den_rel, 99.9):.3e} max {den_rel.max():.3e} | prune mask identical: {mask_eq} | "
