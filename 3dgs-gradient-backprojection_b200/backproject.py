@@ -52,10 +52,12 @@ class BackProjector:
         self.n_views = 0
         self.last_view: Optional[View] = None
         self.kernel_events = None  # set to [] to record (start, end) CUDA events around the fused kernel
-        # The feature re-layout depends only on F, so it CAN run on a second stream next to projection/binning.
-        # Measured on B200 (config G) this buys nothing -- every kernel involved is an HBM-bound full grid --
-        # so the default keeps everything on the caller's stream.
-        self.overlap_pack = False
+        # The feature re-layout depends only on F, so it runs on a second stream next to projection/binning of the
+        # same view.  Measured on B200 (config G, profiles/r02_overlap_pack.txt): 2.80 -> 2.65 ms per view.  The gain is
+        # bounded because the projection kernel fills every SM's register file, so the two only share SMs at the
+        # geometry pipeline's small sorts and at kernel tails; a persistent re-layout grid meant to co-reside with it was
+        # 1.5x slower on its own and still serialised (an SM's L1/shared split only changes when the SM is empty).
+        self.overlap_pack = True
         # encoder-resolution maps: "adjoint" = down-sampled weights x low-res map (gwbp_backproject_view_lowres, no
         # full-resolution intermediate); "upsample" = fused upsample into the packed operand + the full-resolution kernel
         self.lowres_impl = "adjoint"

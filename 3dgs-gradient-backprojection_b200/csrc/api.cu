@@ -124,6 +124,7 @@ int gwbp_workspace_layout(int64_t n, int32_t width, int32_t height, int64_t cap,
         L->bin_seg = o; o = align_up(o + sizeof(unsigned) * (size_t)nseg * tiles_pad + 16);
         L->bin_tot = o; o = align_up(o + sizeof(unsigned) * (size_t)tiles_pad + 16);
     }
+    L->front = o; o = align_up(o + sizeof(unsigned long long) * (size_t)(4 + (n + 255) / 256));
     L->cub_tmp_bytes = binning_tmp_bytes(n, c1);
     L->cub_tmp = o; o = align_up(o + L->cub_tmp_bytes);
     L->total = o;
@@ -157,21 +158,19 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     info->cap_isects = cap;
 
     prof_mark(kEvProject0, st);
-    if (int rc = launch_project(n, scene->geo, cd, w, st)) return rc;
+    if (int rc = launch_project_pack(n, scene->geo, cd, w, st)) return rc;  // projection + tile test + ordered compaction
     prof_mark(kEvProject1, st);
-    if (int rc = launch_scan(n, w, st)) return rc;
-    unsigned long long totals = 0;
-    GWBP_CUDA_OK(cudaMemcpyAsync(&totals, w.scan + n, sizeof(totals), cudaMemcpyDeviceToHost, st));
+    unsigned long long totals[2] = {0ull, 0ull};  // intersections, visible Gaussians (separate 64-bit counters)
+    GWBP_CUDA_OK(cudaMemcpyAsync(totals, w.front + 1, sizeof(totals), cudaMemcpyDeviceToHost, st));
     GWBP_CUDA_OK(cudaStreamSynchronize(st));
     prof_mark(kEvCounts, st);
-    info->n_vis = (int64_t)(totals >> kVisShift);
-    info->n_isects = (int64_t)(totals & kTileCountMask);
+    info->n_vis = (int64_t)totals[1];
+    info->n_isects = totals[0] > (unsigned long long)INT64_MAX ? INT64_MAX : (int64_t)totals[0];
     if (info->n_isects > cap) {
         set_error("intersection capacity exceeded: need %lld, workspace sized for %lld",
                   (long long)info->n_isects, (long long)cap);
         return -2;
     }
-    if (int rc = launch_compact(n, cd, w, st)) return rc;
     prof_mark(kEvCompact, st);
     int dsel = 0;
     if (int rc = launch_depth_sort(info->n_vis, w, &dsel, st)) return rc;

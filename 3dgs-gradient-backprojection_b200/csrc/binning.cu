@@ -21,16 +21,6 @@ size_t binning_tmp_bytes(int64_t n, int64_t cap) {
     return (m + 255) & ~(size_t)255;
 }
 
-int launch_scan(int64_t n, WsDev ws, cudaStream_t st) {
-    size_t need = 0;
-    GWBP_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, need, ws.cnt, ws.scan, (long long)(n + 1), st));
-    GWBP_REQUIRE(need <= ws.cub_tmp_bytes, "scan scratch too small: %zu > %zu", need, ws.cub_tmp_bytes);
-    size_t b = ws.cub_tmp_bytes;
-    GWBP_CUDA_OK(cub::DeviceScan::ExclusiveSum(ws.cub_tmp, b, ws.cnt, ws.scan, (long long)(n + 1), st));
-    count_launches(2);  // DeviceScanInitKernel + DeviceScanKernel
-    return 0;
-}
-
 template <typename K, typename V>
 static int sort_pairs(K *k0, K *k1, V *v0, V *v1, int64_t n, int bits, WsDev ws, int *sorted_buf, cudaStream_t st) {
     *sorted_buf = 0;

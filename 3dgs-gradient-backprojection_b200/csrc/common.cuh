@@ -68,6 +68,7 @@ struct WsDev {
     int *offsets;
     long long *stats;
     unsigned *bin_counts, *bin_seg, *bin_tot;  // sort-free tile binning tables (project.cu)
+    unsigned long long *front;                 // ticket, totals and chained-scan status words of project_pack_kernel
     void *cub_tmp;
     size_t cub_tmp_bytes;
 };
@@ -94,6 +95,7 @@ inline WsDev ws_view(void *base, const gwbp_ws_layout &L) {
     w.bin_counts = (unsigned *)(b + L.bin_counts);
     w.bin_seg = (unsigned *)(b + L.bin_seg);
     w.bin_tot = (unsigned *)(b + L.bin_tot);
+    w.front = (unsigned long long *)(b + L.front);
     w.cub_tmp = (void *)(b + L.cub_tmp);
     w.cub_tmp_bytes = L.cub_tmp_bytes;
     return w;
@@ -104,12 +106,11 @@ CamDev make_cam(const gwbp_camera &c);
 // ---- stage launchers (one per .cu) -------------------------------------------------------
 int launch_pack_scene(int64_t n, const float *means, const float *quats, const float *scales,
                       const float *opac, void *geo, cudaStream_t st);
-int launch_project(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cudaStream_t st);
-int launch_compact(int64_t n, const CamDev &cam, WsDev ws, cudaStream_t st);
+// projection + tile test + ordered compaction in one kernel; totals land in ws.front[1] (intersections), [2] (visible)
+int launch_project_pack(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cudaStream_t st);
 int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, bool gather_erec, cudaStream_t st);
 int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, bool key16, cudaStream_t st);
 size_t binning_tmp_bytes(int64_t n, int64_t cap);
-int launch_scan(int64_t n, WsDev ws, cudaStream_t st);
 int launch_depth_sort(int64_t n_vis, WsDev ws, int *sorted_buf, cudaStream_t st);
 int launch_scan_counts(int64_t n_vis, WsDev ws, cudaStream_t st);
 // key16: tile ids are stored as uint16 in the tkeys buffers (tiles <= 65536): 25 % less sort traffic

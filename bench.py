@@ -235,6 +235,8 @@ def run_ours(args, cfg):
     t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
     bp = gwbp.BackProjector(t(sc.means), t(sc.quats), t(sc.scales), t(sc.opacities), d, kernel=args.kernel,
                             collect_stats=True)
+    if args.overlap_pack >= 0:
+        bp.overlap_pack = bool(args.overlap_pack)
     enc = 240 if min(W, H) >= 480 else 24
     pool_n = max(1, min(V, args.pool))
     pool = [S.make_feature_map_torch(v, d, H, W, dev, 0, enc_res=enc) for v in range(pool_n)]
@@ -608,6 +610,9 @@ def main():
     ap.add_argument("--d", type=int, default=0, help="override the config's feature width (experiments only)")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU-oracle work (0 = skip)")
+    ap.add_argument("--overlap-pack", type=int, default=-1,
+                    help="1/0: force the feature re-layout onto / off a second stream next to projection + binning "
+                         "(-1 = the BackProjector default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     import gwbp

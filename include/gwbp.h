@@ -97,6 +97,8 @@ typedef struct gwbp_ws_layout {
     size_t bin_counts; /* uint32 [chunks][tiles] per-chunk tile histograms -> exclusive prefixes (sort-free binning) */
     size_t bin_seg;    /* uint32 [segments][tiles] */
     size_t bin_tot;    /* uint32 [tiles]  intersections per tile */
+    size_t front;     /* uint64 [4 + ceil(n/256)] front-end control block: CTA ticket, intersection / visible totals,
+                         one chained-scan status word per projection CTA */
     size_t cub_tmp;   /* scratch for scan / sort */
     size_t cub_tmp_bytes;
 } gwbp_ws_layout;
