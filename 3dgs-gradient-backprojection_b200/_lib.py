@@ -14,9 +14,9 @@ if os.environ.get("GWBP_LIB_VARIANT") == "exp":  # tools/ only: the -DGWBP_EXPER
     LIB_PATH = os.path.join(_HERE, "lib", "libgwbp_exp.so")
 
 KERNEL_AUTO, KERNEL_SIMT, KERNEL_TC = 0, 1, 2
-ABI_VERSION = 11
+ABI_VERSION = 12
 KERNEL_FPACK_READY = 0x100
-PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL, PREPARE_COUNTING_BIN = 0, 1, 2
+PREPARE_GSPLAT_EXACT, PREPARE_TILE_CULL, PREPARE_COUNTING_BIN, PREPARE_SUPERTILE = 0, 1, 2, 4
 
 
 class Scene(C.Structure):
@@ -32,13 +32,15 @@ class WsLayout(C.Structure):
     _fields_ = [(k, C.c_size_t) for k in ("total", "cnt", "scan", "rec", "mask", "grec", "erec", "radii",
                                           "tiles_per_gauss", "dkeys0", "dkeys1", "dvals0", "dvals1", "cnt2", "base2",
                                           "tkeys0", "tkeys1", "tvals0", "tvals1", "offsets", "stats", "bin_counts", "bin_seg",
-                                          "bin_tot", "front", "cub_tmp",
+                                          "bin_tot", "spg", "svals", "front", "cub_tmp",
                                           "cub_tmp_bytes")]
 
 
 class ViewInfo(C.Structure):
     _fields_ = [("n_vis", C.c_int64), ("n_isects", C.c_int64), ("cap_isects", C.c_int64), ("tile_w", C.c_int32),
-                ("tile_h", C.c_int32), ("sorted_buf", C.c_int32), ("tile_key_bytes", C.c_int32)]
+                ("tile_h", C.c_int32), ("sorted_buf", C.c_int32), ("tile_key_bytes", C.c_int32),
+                ("list_kind", C.c_int32), ("super_w", C.c_int32), ("super_h", C.c_int32), ("reserved", C.c_int32),
+                ("n_entries", C.c_int64)]
 
 
 # name -> (restype, argtypes); kept in one table so tests can check it against include/gwbp.h

@@ -28,7 +28,7 @@ DEN_EPS = 1e-12  # backproject.py:63
 class BackProjector:
     def __init__(self, means, quats, scales, opacities, feature_dim: int, device=None, kernel: str = "auto",
                  cap_isects: Optional[int] = None, collect_stats: bool = False, tile_cull: bool = True,
-                 accumulate: str = "sum"):
+                 accumulate: str = "sum", supertile: bool = True):
         """accumulate="sum": num += num_v, den += den_v, features = num/den (backproject.py:149-150,166).
         accumulate="per_view_ratio": features += mean-scaled num_v / (mean-scaled den_v + 1e-12) per view
         (affordance_transfer/demo_affordance_transfer.py:768-800); `num` then holds that sum."""
@@ -46,6 +46,9 @@ class BackProjector:
         self.kernel = {"auto": L.KERNEL_AUTO, "simt": L.KERNEL_SIMT, "tc": L.KERNEL_TC}[kernel]
         self.cap = cap_isects
         self.tile_cull = bool(tile_cull)
+        # views handed to the tcgen05 kernels are binned into 8 x 4-tile supertiles (~2.4x fewer list entries, one
+        # radix pass); views that fall back to the CUDA-core kernel keep per-tile lists
+        self.supertile = bool(supertile)
         self._ws: Optional[torch.Tensor] = None
         self._fpack: Optional[torch.Tensor] = None
         self._stats = torch.zeros(4, dtype=torch.int64, device=self.device) if collect_stats else None
@@ -203,7 +206,8 @@ class BackProjector:
                 feats.record_stream(side)
             kernel = (L.KERNEL_TC if kernel == L.KERNEL_AUTO else kernel) | L.KERNEL_FPACK_READY
         with torch.cuda.stream(main):
-            view = View(self.scene, cam, self.cap, self._ws, self.tile_cull)
+            view = View(self.scene, cam, self.cap, self._ws, self.tile_cull,
+                        supertile=self.supertile and fp is not None and self.kernel != L.KERNEL_SIMT)
             self._ws, self.cap = view.ws, view.cap  # keep (possibly grown) workspace for the next view
             if overlap:
                 main.wait_stream(self._side)

@@ -69,6 +69,8 @@ static TileCtx tile_ctx(const gwbp_camera *cam, const void *ws, const gwbp_ws_la
     t.grec = w.grec;
     t.flatten = w.tvals[info->sorted_buf];
     t.offsets = w.offsets;
+    t.sents = info->list_kind == 1 ? (const uint2 *)w.svals[info->sorted_buf] : nullptr;
+    t.nsx = info->super_w;
     t.scratch = w.stats;
     t.dead = (char *)const_cast<void *>(ws) + L.cnt;
     t.dead_bytes = L.grec - L.cnt;
@@ -124,6 +126,8 @@ int gwbp_workspace_layout(int64_t n, int32_t width, int32_t height, int64_t cap,
         L->bin_seg = o; o = align_up(o + sizeof(unsigned) * (size_t)nseg * tiles_pad + 16);
         L->bin_tot = o; o = align_up(o + sizeof(unsigned) * (size_t)tiles_pad + 16);
     }
+    L->spg = o; o = align_up(o + sizeof(int) * n1);
+    L->svals = o; o = align_up(o + sizeof(unsigned long long) * c1);
     L->front = o; o = align_up(o + sizeof(unsigned long long) * (size_t)(4 + (n + 255) / 256));
     L->cub_tmp_bytes = binning_tmp_bytes(n, c1);
     L->cub_tmp = o; o = align_up(o + L->cub_tmp_bytes);
@@ -152,6 +156,9 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     WsDev w = ws_view(ws, L);
     CamDev cd = make_cam(*cam);
     cd.cull = (flags & GWBP_PREPARE_TILE_CULL) ? 1 : 0;
+    cd.super = (flags & GWBP_PREPARE_SUPERTILE) ? 1 : 0;
+    cd.nsx = (cd.tw + kSuperW - 1) / kSuperW;
+    const int nsy = (cd.th + kSuperH - 1) / kSuperH, n_super = cd.nsx * nsy;
     const int64_t n = scene->n;
     memset(info, 0, sizeof(*info));
     info->tile_w = cd.tw; info->tile_h = cd.th;
@@ -160,7 +167,7 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     prof_mark(kEvProject0, st);
     if (int rc = launch_project_pack(n, scene->geo, cd, w, st)) return rc;  // projection + tile test + ordered compaction
     prof_mark(kEvProject1, st);
-    unsigned long long totals[2] = {0ull, 0ull};  // intersections, visible Gaussians (separate 64-bit counters)
+    unsigned long long totals[3] = {0ull, 0ull, 0ull};  // intersections, visible Gaussians, supertile entries (64-bit each)
     GWBP_CUDA_OK(cudaMemcpyAsync(totals, w.front + 1, sizeof(totals), cudaMemcpyDeviceToHost, st));
     GWBP_CUDA_OK(cudaStreamSynchronize(st));
     prof_mark(kEvCounts, st);
@@ -171,12 +178,31 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
                   (long long)info->n_isects, (long long)cap);
         return -2;
     }
+    info->n_entries = cd.super ? (int64_t)totals[2] : info->n_isects;
     prof_mark(kEvCompact, st);
     int dsel = 0;
     if (int rc = launch_depth_sort(info->n_vis, w, &dsel, st)) return rc;
     prof_mark(kEvDepthSort, st);
     const unsigned *order = w.dvals[dsel];
     const int n_tiles = cd.tw * cd.th;
+    if (cd.super) {
+        // supertile lists: one entry per (Gaussian, 8 x 4-tile supertile) in depth order, ONE stable radix pass on the
+        // supertile id while there are <= 256 of them, ranges per supertile in `offsets`
+        info->list_kind = 1;
+        info->super_w = cd.nsx; info->super_h = nsy;
+        if (int rc = launch_gather_counts(info->n_vis, order, w, false, st, true)) return rc;
+        if (int rc = launch_scan_counts(info->n_vis, w, st)) return rc;
+        const int kb = n_super <= 256 ? 1 : n_super <= 65536 ? 2 : 4;
+        info->tile_key_bytes = kb;
+        if (int rc = launch_emit_super(info->n_vis, cd, order, w, cap, kb, st)) return rc;
+        int sorted = 0, sbits = 1;
+        while ((1 << sbits) < n_super) ++sbits;
+        if (int rc = launch_super_sort(info->n_entries, sbits, w, kb, &sorted, st)) return rc;
+        info->sorted_buf = sorted;
+        const int rc = launch_offsets(info->n_entries, n_super, w.tkeys[sorted], kb == 2, w.offsets, st, kb == 1);
+        prof_mark(kEvBin, st);
+        return rc;
+    }
     if (bin_fast_supported(n_tiles) && (flags & GWBP_PREPARE_COUNTING_BIN)) {
         // hand-written stable counting sort fused with the emission: no (tile, index) intermediate, no radix sort;
         // the depth-ordered prefix of the per-Gaussian hit counts cuts the list into chunks of equal work
@@ -285,6 +311,7 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam, const
         return rc;
     }
     GWBP_REQUIRE(k == GWBP_KERNEL_SIMT, "unknown kernel id %d", kernel);
+    GWBP_REQUIRE(info->list_kind == 0, "the CUDA-core kernel needs per-tile lists (view prepared with GWBP_PREPARE_SUPERTILE)");
     prof_mark(kEvBp0, st);
     const int rc = launch_backproject_simt(t, F, sH, sW, sD, d, num, den, (long long *)stats, st);
     prof_mark(kEvBp1, st);
@@ -338,6 +365,7 @@ int gwbp_render_view(const gwbp_scene *scene, const gwbp_camera *cam, const void
     if (int rc = check_cam(cam)) return rc;
     GWBP_REQUIRE(d >= 1, "channel count must be >= 1 (got %d)", d);
     GWBP_REQUIRE(color_stride >= d, "color_stride (%lld) < d (%d)", (long long)color_stride, d);
+    GWBP_REQUIRE(info->list_kind == 0, "render_view needs per-tile lists (view prepared with GWBP_PREPARE_SUPERTILE)");
     gwbp_ws_layout L;
     if (int rc = gwbp_workspace_layout(scene->n, cam->width, cam->height, info->cap_isects, &L)) return rc;
     const TileCtx t = tile_ctx(cam, ws, L, info);
@@ -363,6 +391,7 @@ int gwbp_render_pixels(const gwbp_scene *scene, const gwbp_camera *cam, const vo
         return 0;
     }
     GWBP_REQUIRE(ws && colors, "render_pixels: NULL pointer");
+    GWBP_REQUIRE(info->list_kind == 0, "render_pixels needs per-tile lists (view prepared with GWBP_PREPARE_SUPERTILE)");
     if (int rc = check_cam(cam)) return rc;
     GWBP_REQUIRE(color_stride >= d, "color_stride (%lld) < d (%d)", (long long)color_stride, d);
     gwbp_ws_layout L;

@@ -35,6 +35,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "lister.cuh"
 #include "tc_common.cuh"
 
 namespace gwbp {
@@ -65,7 +66,8 @@ constexpr int NFSTAGE = 3;
 constexpr int EPI_COLS = 32, EPI_ROWS = 16, EPI_PITCH = EPI_COLS * 4 + 16;
 constexpr int TM_ACC = 0, TM_D1 = 2 * NC2;                 // TMEM column bases
 
-constexpr int kEpiWarp0 = 8, kCvtWarp0 = 12, kProducerWarp = 16, kMmaWarp = 17, kUWarp0 = 18, kThreads = (18 + NUSLOT) * 32;
+constexpr int kEpiWarp0 = 8, kCvtWarp0 = 12, kProducerWarp = 16, kMmaWarp = 17, kUWarp0 = 18, kListerWarp0 = 18 + NUSLOT,
+              kThreads = (20 + NUSLOT) * 32;  // + two lister warps
 
 struct RowInfo {
     int gid[MB];
@@ -84,12 +86,14 @@ struct Smem {
     static constexpr int gbuf = stage_out + 4 * EPI_ROWS * EPI_PITCH;
     static constexpr int rows = gbuf + MB * 24;
     static constexpr int ctrl = rows + RING * (int)sizeof(RowInfo);
-    static constexpr int bars = ctrl + 64;
+    static constexpr int lring = ctrl + 64;  // lst::Ring: id batches from the lister warp
+    static constexpr int bars = lring + lst::NLISTERS * (int)sizeof(lst::Ring);
     static constexpr int w_full = 0, w_free = 8, u_full = 16, u_empty = u_full + NUSLOT, f_full = u_empty + NUSLOT,
                          f_empty = f_full + NFSTAGE, d1_full = f_empty + NFSTAGE, d1_empty = d1_full + 2,
                          a2_full = d1_empty + 2, a2_empty = a2_full + 1, acc_full = a2_empty + 1, acc_empty = acc_full + 2,
                          rows_ready = acc_empty + 2, rows_free = rows_ready + RING, ctrl_full = rows_free + RING,
-                         ctrl_empty = ctrl_full + RING, nbars = ctrl_empty + RING;
+                         ctrl_empty = ctrl_full + RING, l_full = ctrl_empty + RING, l_free = l_full + lst::NL,
+                         nbars = l_full + lst::NLISTERS * 2 * lst::NL;  // per lister: full[NL], free[NL]
     static constexpr int tmem_slot = bars + nbars * 8;
     static constexpr int total = tmem_slot + 16;
 };
@@ -155,13 +159,7 @@ __host__ __device__ __forceinline__ SrcIdx src_index(int o, float scale, int n_s
 }
 
 constexpr int kBand = 4;
-__device__ __forceinline__ int unit_to_tile(int unit, int tw, int th, int kband) {
-    const int per_band = kband * tw;
-    const int band = unit / per_band, r = unit - band * per_band;
-    const int hb = min(kband, th - band * kband);
-    const int tx = r / hb, ty = band * kband + (r - tx * hb);
-    return ty * tw + tx;
-}
+using lst::unit_to_tile;
 
 struct LrArgs {
     TileCtx t;
@@ -183,7 +181,6 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
     auto bar = [&](int i) -> uint32_t { return sbase + Smem::bars + 8 * i; };
     RowInfo *rows = reinterpret_cast<RowInfo *>(smem + Smem::rows);
     volatile int *ctrl = reinterpret_cast<volatile int *>(smem + Smem::ctrl);
-    volatile int &s_unit = ctrl[8], &s_unit2 = ctrl[9];
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Smem::tmem_slot);
 
     if (tid == 0) {
@@ -203,6 +200,13 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
             mbar_init(bar(Smem::rows_free + i), 4);
             mbar_init(bar(Smem::ctrl_full + i), 1);
             mbar_init(bar(Smem::ctrl_empty + i), 4);  // producer, MMA, U writer 0, converters (warp 12)
+        }
+        for (int r = 0; r < lst::NLISTERS; ++r) {
+            for (int i = 0; i < lst::NL; ++i) {
+                mbar_init(bar(Smem::l_full + 2 * lst::NL * r + i), 1);
+                mbar_init(bar(Smem::l_free + 2 * lst::NL * r + i), 8);
+            }
+            reinterpret_cast<lst::Ring *>(smem + Smem::lring)[r].abort_unit = -1;
         }
         mbar_init_fence();
     }
@@ -226,56 +230,87 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
         // ======================================= ALU =========================================
         // identical to bp_tc_kernel's ALU role (same pair arithmetic, same W^T layout, same den butterfly)
         float4 *gbuf = reinterpret_cast<float4 *>(smem + Smem::gbuf);
-        int q = 0;
+        lst::Ring *rings = reinterpret_cast<lst::Ring *>(smem + Smem::lring);
+        // lr = the ring (lister) the current tile comes from; qlc / alive_c = batches consumed from it / it still has
+        // tiles; qlo / alive_o = the same for the other ring (scalars, swapped at a ring switch: no local-memory arrays)
+        int q = 0, lr = 0, qlc = 0, qlo = 0;
+        bool alive_c = true, alive_o = true;
         long long walked = 0;
         const uint32_t wslab = (uint32_t)(tid >> 3) * A_LBO + (uint32_t)(tid & 7) * 16;
-        // Work queue, two units deep: `unit` is being processed, `unit_n` is already known, and the request for the
-        // one after that is in flight -- so the next tile's list bounds and first 128 records are fetched while this
-        // tile is processed (a tile switch otherwise costs four dependent global round trips, ~3 us, per ~2.4 batches).
-        auto first_records = [&](int s_, int e_, float4 &r0_, float4 &r1_) {
-            r0_ = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-            r1_ = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tid < MB && s_ + tid < e_) {
-                const int id = a.t.flatten[s_ + tid];
-                r0_ = a.t.grec[2 * (int64_t)id];
-                r1_ = a.t.grec[2 * (int64_t)id + 1];
+        // The next batch to process, as handed over by the lister warp (which owns the work queue and runs a few
+        // batches ahead, across tile boundaries): its tile, size, whether it closes the tile, and (threads 0..127) the
+        // record of its row `tid`, loaded while the previous batch is processed.
+        int nu = -1, nn = 0, nlast = 1;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto fetch = [&]() {  // next batch of ring lr
+            lst::Ring *ring = rings + lr;
+            const int ls = qlc % lst::NL;
+            mbar_wait(bar(Smem::l_full + 2 * lst::NL * lr + ls), (qlc / lst::NL) & 1);
+            nu = ring->unit[ls]; nn = ring->n[ls]; nlast = ring->last[ls];
+            r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid < MB && tid < nn) {
+                const int id = ring->ids[ls][tid];
+                r0 = a.t.grec[2 * (int64_t)id];
+                r1 = a.t.grec[2 * (int64_t)id + 1];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(Smem::l_free + 2 * lst::NL * lr + ls));
+            ++qlc;
+        };
+        // first batch of the next tile: the listers take alternate tiles, so it comes from the other ring while that
+        // lister still has tiles (a lister that has published its exit marker is never read again)
+        auto fetch_next_tile = [&]() {
+            while (true) {
+                if (alive_o) {
+                    lr ^= 1;
+                    const int tq = qlc; qlc = qlo; qlo = tq;
+                    const bool ta = alive_c; alive_c = alive_o; alive_o = ta;
+                } else if (!alive_c) {
+                    nu = -1; nn = 0; nlast = 1;
+                    return;
+                }
+                fetch();
+                if (nu >= 0) return;
+                alive_c = false;
             }
         };
-        if (tid == 0) {
-            s_unit = atomicAdd(a.unit_counter, 1);
-            s_unit2 = atomicAdd(a.unit_counter, 1);
-        }
-        bar_sync_alu();
-        int unit = s_unit, unit_n = s_unit2;
-        bar_sync_alu();
-        int s = 0, e = 0;
-        float4 r0, r1;
-        if (unit < a.nunits) {
-            const int tile0 = unit_to_tile(unit, a.t.tw, a.t.th, kBand);
-            s = a.t.offsets[tile0];
-            e = a.t.offsets[tile0 + 1];
-        }
-        first_records(s, e, r0, r1);
-        while (unit < a.nunits) {
-            int unit_nn = 0;
-            if (tid == 0) unit_nn = atomicAdd(a.unit_counter, 1);  // consumed at the end of this tile
-            int s_n = 0, e_n = 0;
-            if (unit_n < a.nunits) {
-                const int tile_n = unit_to_tile(unit_n, a.t.tw, a.t.th, kBand);
-                s_n = a.t.offsets[tile_n];
-                e_n = a.t.offsets[tile_n + 1];
+        lr = 1;
+        fetch_next_tile();  // ring 0 first
+        int unit = -2;
+        float2 npx = make_float2(0.f, 0.f), npy = make_float2(0.f, 0.f);
+        bool done = true;
+        float T = 1.0f;
+        while (nu >= 0) {
+            if (nu != unit) {  // first batch of a new tile
+                unit = nu;
+                const int tile = unit_to_tile(unit, a.t.tw, a.t.th, kBand);
+                const int ty = tile / a.t.tw, tx = tile % a.t.tw;
+                const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
+                const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
+                npx = make_float2(-px, -px);
+                npy = make_float2(-py, -py);
+                done = !(yy < a.t.H && xx < a.t.W);
+                T = 1.0f;
             }
-            float4 r0n = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), r1n = make_float4(0.f, 0.f, 0.f, 0.f);
-            bool fetched_n = false;
-            const int tile = unit_to_tile(unit, a.t.tw, a.t.th, kBand);
-            const int ty = tile / a.t.tw, tx = tile % a.t.tw;
-            const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
-            const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
-            const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
-            bool done = !(yy < a.t.H && xx < a.t.W);
-            float T = 1.0f;
-            for (int b = s; b < e; b += MB, ++q) {
-                if (bar_red_popc_alu(!done) == 0) break;
+            const int n_cur = nn;
+            const bool last_cur = nlast != 0;
+            if (n_cur == 0) {  // empty closing batch of a tile
+                fetch_next_tile();
+                continue;
+            }
+            {
+                if (bar_red_popc_alu(!done) == 0) {
+                    // every pixel of the tile is finished: tell the lister and skip the tile's remaining batches
+                    if (!last_cur) {
+                        if (tid == 0) rings[lr].abort_unit = unit;
+                        do {
+                            fetch();
+                        } while (!nlast);
+                    }
+                    fetch_next_tile();
+                    continue;
+                }
                 if (warp == 0) trace(0, 0, q, 0);
                 const int slot = q % RING;
                 if (q >= RING) mbar_wait(bar(Smem::rows_free + slot), ((q / RING) - 1) & 1);
@@ -294,20 +329,11 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                     mbar_arrive(bar(Smem::ctrl_full + slot));
                 }
                 bar_sync_alu();
-                if (!fetched_n) {  // the next tile's first records: in flight while this tile is processed
-                    first_records(s_n, e_n, r0n, r1n);
-                    fetched_n = true;
-                }
-                r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                r1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tid < MB && b + MB + tid < e) {
-                    const int id = a.t.flatten[b + MB + tid];
-                    r0 = a.t.grec[2 * (int64_t)id];
-                    r1 = a.t.grec[2 * (int64_t)id + 1];
-                }
+                // the next batch (of this tile or the next one): its record loads are in flight during this batch
+                if (last_cur) fetch_next_tile(); else fetch();
                 if (q >= 1) mbar_wait(bar(Smem::w_free + warp), (q - 1) & 1);
                 if (warp == 0) trace(0, 1, q, 0);
-                walked += min(MB, e - b);
+                walked += n_cur;
                 if (__all_sync(0xffffffffu, done)) {
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 4
@@ -387,15 +413,8 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                     mbar_arrive(bar(Smem::rows_ready + slot));
                 }
                 if (warp == 0) trace(0, 2, q, 0);
+                ++q;
             }
-            // rotate the queue: the unit requested at the start of this tile becomes the next-but-one
-            if (!fetched_n) first_records(s_n, e_n, r0n, r1n);
-            if (tid == 0) s_unit = unit_nn;
-            bar_sync_alu();
-            const int unit_new = s_unit;
-            bar_sync_alu();  // everyone has read s_unit before it is overwritten
-            unit = unit_n; unit_n = unit_new;
-            s = s_n; e = e_n; r0 = r0n; r1 = r1n;
         }
         {   // exit sentinel for the other roles
             const int slot = q % RING;
@@ -595,6 +614,11 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                 if (lane == 0) mbar_arrive(bar(Smem::u_full + us));
             }
         }
+    } else if (warp >= kListerWarp0) {
+        // ====================================== listers ======================================
+        const int r = warp - kListerWarp0;
+        lst::run_lister(a.t, a.unit_counter, a.nunits, kBand, reinterpret_cast<lst::Ring *>(smem + Smem::lring) + r,
+                        bar(Smem::l_full + 2 * lst::NL * r));
     } else if (warp == kMmaWarp) {
         // ======================================= MMA =========================================
         int ucnt[NUSLOT] = {0, 0, 0};  // uses of each U ring slot (slice ks lives in slot ks % NUSLOT, written by writer ks % NUSLOT)

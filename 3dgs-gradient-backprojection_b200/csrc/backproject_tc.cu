@@ -33,6 +33,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "lister.cuh"
 #include "tc_common.cuh"
 
 namespace gwbp {
@@ -53,7 +54,7 @@ constexpr int EPI_COLS = 32;                             // columns per epilogue
 constexpr int EPI_ROWS = 16;                             // rows staged per round and warp (half of the warp's 32)
 constexpr int EPI_PITCH = EPI_COLS * 4 + 16;             // padded row pitch (144 B): conflict-free 16-byte stores
 
-constexpr int kEpiWarp0 = 8, kProducerWarp = 13, kMmaWarp = 14, kThreads = 480;
+constexpr int kEpiWarp0 = 8, kListerWarp0 = 12, kProducerWarp = 13, kMmaWarp = 14, kListerWarp1 = 15, kThreads = 512;
 
 struct RowInfo {
     int gid[MB];
@@ -67,19 +68,21 @@ struct Smem {
     static constexpr int w_lo = W_PART_BYTES;
     static constexpr int fring = 2 * W_PART_BYTES;
     static constexpr int stage_out = fring + NSTAGE * STAGE_BYTES;   // epilogue staging: 4 warps x EPI_ROWS x EPI_PITCH
-    static constexpr int gbuf = stage_out + 4 * EPI_ROWS * EPI_PITCH;  // 128 x 2 float4
-    static constexpr int rows = gbuf + MB * 32;
+    static constexpr int gbuf = stage_out + 4 * EPI_ROWS * EPI_PITCH;  // 64 Gaussian pairs x 3 float4
+    static constexpr int rows = gbuf + MB * 24;
     static constexpr int ctrl = rows + RING * (int)sizeof(RowInfo);  // int[RING]
-    static constexpr int bars = ctrl + 64;
+    static constexpr int lring = ctrl + 64;                           // lst::Ring: id batches from the lister warp
+    static constexpr int bars = lring + lst::NLISTERS * (int)sizeof(lst::Ring);
     // barrier indices
     static constexpr int w_full = 0, w_free = 8, f_full = 16, f_empty = f_full + NSTAGE,
                          acc_full = f_empty + NSTAGE, acc_empty = acc_full + 2, rows_ready = acc_empty + 2,
                          rows_free = rows_ready + RING, ctrl_full = rows_free + RING, ctrl_empty = ctrl_full + RING,
-                         nbars = ctrl_empty + RING;
+                         l_full = ctrl_empty + RING, l_free = l_full + lst::NL,
+                         nbars = l_full + lst::NLISTERS * 2 * lst::NL;  // per lister: full[NL], free[NL]
     static constexpr int tmem_slot = bars + nbars * 8;
     static constexpr int total = tmem_slot + 16;
 };
-static_assert(RING <= 8, "ctrl[8] is the work-queue slot");
+static_assert(sizeof(lst::Ring) % 8 == 0, "mbarriers behind the ring stay 8-byte aligned");
 static_assert(Smem::total + 256 <= 232448, "shared memory budget (227 KB) exceeded");
 
 __device__ __forceinline__ int bar_red_popc_alu(bool pred) {
@@ -98,18 +101,9 @@ __device__ __forceinline__ void bar_sync_alu() { asm volatile("bar.sync 1, 256;"
 // Optional event trace (debug/profiling only: gwbp_debug_set_trace).  CTA 0 records
 // (role, event, batch, chunk, clock64) tuples: roles 0/1 = ALU warp 0/7, 2 = epilogue warp 0, 3 = MMA.
 constexpr int kTraceRoles = 4, kTraceCap = 4096;
-// Tile visiting order.  Work units are handed out in bands of kBand tile rows, column-major inside a band,
-// so that the ~148 tiles in flight form a compact block: the (typically 2x2..3x3) tiles that touch one
-// Gaussian are processed close together in time and their row reductions merge in the 126 MB L2 instead
-// of each costing a DRAM read-modify-write of the 2 KB accumulator row.
-constexpr int kBand = 4;   // measured at config G: 2 -> 1.063, 4 -> 1.056, 8 -> 1.082, 16 -> 1.092 ms, whole image -> 1.096
-__device__ __forceinline__ int unit_to_tile(int unit, int tw, int th, int kband) {
-    const int per_band = kband * tw;
-    const int band = unit / per_band, r = unit - band * per_band;
-    const int hb = min(kband, th - band * kband);
-    const int tx = r / hb, ty = band * kband + (r - tx * hb);
-    return ty * tw + tx;
-}
+constexpr int kBand = 4;   // tile rows per band of the visiting order (lst::unit_to_tile); measured at config G:
+                           // 2 -> 1.063, 4 -> 1.056, 8 -> 1.082, 16 -> 1.092 ms, whole image -> 1.096
+using lst::unit_to_tile;
 
 struct TcArgs {
     unsigned long long *trace;  // [kTraceRoles][kTraceCap][2] or nullptr
@@ -134,7 +128,6 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
     auto bar = [&](int i) -> uint32_t { return sbase + Smem::bars + 8 * i; };
     RowInfo *rows = reinterpret_cast<RowInfo *>(smem + Smem::rows);
     volatile int *ctrl = reinterpret_cast<volatile int *>(smem + Smem::ctrl);
-    volatile int &s_unit = ctrl[8];  // work-queue broadcast slot (ALU warps only)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Smem::tmem_slot);
 
     if (tid == 0) {
@@ -146,6 +139,13 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             mbar_init(bar(Smem::rows_free + i), 4);
             mbar_init(bar(Smem::ctrl_full + i), 1);
             mbar_init(bar(Smem::ctrl_empty + i), 2);
+        }
+        for (int r = 0; r < lst::NLISTERS; ++r) {
+            for (int i = 0; i < lst::NL; ++i) {
+                mbar_init(bar(Smem::l_full + 2 * lst::NL * r + i), 1);
+                mbar_init(bar(Smem::l_free + 2 * lst::NL * r + i), 8);
+            }
+            reinterpret_cast<lst::Ring *>(smem + Smem::lring)[r].abort_unit = -1;
         }
         mbar_init_fence();
     }
@@ -167,32 +167,86 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
     if (warp < 8) {
         // ======================================= ALU =========================================
         float4 *gbuf = reinterpret_cast<float4 *>(smem + Smem::gbuf);
-        int q = 0;
+        lst::Ring *rings = reinterpret_cast<lst::Ring *>(smem + Smem::lring);
+        // lr = the ring (lister) the current tile comes from; qlc / alive_c = batches consumed from it / it still has
+        // tiles; qlo / alive_o = the same for the other ring (scalars, swapped at a ring switch: no local-memory arrays)
+        int q = 0, lr = 0, qlc = 0, qlo = 0;
+        bool alive_c = true, alive_o = true;
         long long walked = 0;
         const uint32_t wslab = (uint32_t)(tid >> 3) * A_LBO + (uint32_t)(tid & 7) * 16;  // this pixel's K-row
-        while (true) {
-            if (tid == 0) s_unit = atomicAdd(a.unit_counter, 1);
-            bar_sync_alu();
-            const int unit = s_unit;
-            bar_sync_alu();  // everyone has read s_unit before it is overwritten
-            if (unit >= a.nunits) break;
-            const int tile = unit_to_tile(unit, a.t.tw, a.t.th, a.band);
-            const int ty = tile / a.t.tw, tx = tile % a.t.tw;
-            const int s = a.t.offsets[tile], e = a.t.offsets[tile + 1];
-            const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
-            const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
-            const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
-            bool done = !(yy < a.t.H && xx < a.t.W);
-            float T = 1.0f;
-            // prefetch the first batch's record for row `tid` (threads 0..127)
-            float4 r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (tid < MB && s + tid < e) {
-                const int id = a.t.flatten[s + tid];
+        // The next batch to process, as handed over by the lister warp: its tile (work unit), size, whether it closes
+        // the tile, and (threads 0..127) the record of its row `tid`, loaded while the previous batch is processed.
+        int nu = -1, nn = 0, nlast = 1;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto fetch = [&]() {  // next batch of ring lr
+            lst::Ring *ring = rings + lr;
+            const int ls = qlc % lst::NL;
+            mbar_wait(bar(Smem::l_full + 2 * lst::NL * lr + ls), (qlc / lst::NL) & 1);
+            nu = ring->unit[ls]; nn = ring->n[ls]; nlast = ring->last[ls];
+            r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tid < MB && tid < nn) {
+                const int id = ring->ids[ls][tid];
                 r0 = a.t.grec[2 * (int64_t)id];
                 r1 = a.t.grec[2 * (int64_t)id + 1];
             }
-            for (int b = s; b < e; b += MB, ++q) {
-                if (bar_red_popc_alu(!done) == 0) break;  // also: every warp is done reading gbuf of batch q-1
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(Smem::l_free + 2 * lst::NL * lr + ls));
+            ++qlc;
+        };
+        // first batch of the next tile: the listers take alternate tiles, so it comes from the other ring while that
+        // lister still has tiles (a lister that has published its exit marker is never read again)
+        auto fetch_next_tile = [&]() {
+            while (true) {
+                if (alive_o) {
+                    lr ^= 1;
+                    const int tq = qlc; qlc = qlo; qlo = tq;
+                    const bool ta = alive_c; alive_c = alive_o; alive_o = ta;
+                } else if (!alive_c) {
+                    nu = -1; nn = 0; nlast = 1;
+                    return;
+                }
+                fetch();
+                if (nu >= 0) return;
+                alive_c = false;
+            }
+        };
+        lr = 1;
+        fetch_next_tile();  // ring 0 first
+        int unit = -2;
+        float2 npx = make_float2(0.f, 0.f), npy = make_float2(0.f, 0.f);
+        bool done = true;
+        float T = 1.0f;
+        while (nu >= 0) {
+            if (nu != unit) {  // first batch of a new tile
+                unit = nu;
+                const int tile = unit_to_tile(unit, a.t.tw, a.t.th, a.band);
+                const int ty = tile / a.t.tw, tx = tile % a.t.tw;
+                const int yy = ty * kTile + (tid >> 4), xx = tx * kTile + (tid & 15);
+                const float px = (float)xx + 0.5f, py = (float)yy + 0.5f;
+                npx = make_float2(-px, -px);
+                npy = make_float2(-py, -py);
+                done = !(yy < a.t.H && xx < a.t.W);
+                T = 1.0f;
+            }
+            const int n_cur = nn;
+            const bool last_cur = nlast != 0;
+            if (n_cur == 0) {  // empty closing batch of a tile
+                fetch_next_tile();
+                continue;
+            }
+            {
+                if (bar_red_popc_alu(!done) == 0) {  // also: every warp is done reading gbuf of batch q-1
+                    // every pixel of the tile is finished: tell the lister and skip the tile's remaining batches
+                    if (!last_cur) {
+                        if (tid == 0) rings[lr].abort_unit = unit;
+                        do {
+                            fetch();
+                        } while (!nlast);
+                    }
+                    fetch_next_tile();
+                    continue;
+                }
                 if (warp == 0 || warp == 7) trace(warp ? 1 : 0, 0, q, 0);
                 const int slot = q % RING;
                 if (q >= RING) mbar_wait(bar(Smem::rows_free + slot), ((q / RING) - 1) & 1);
@@ -213,17 +267,11 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                     mbar_arrive(bar(Smem::ctrl_full + slot));
                 }
                 bar_sync_alu();
-                // prefetch the next batch while this one is processed
-                r0 = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                r1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (tid < MB && b + MB + tid < e) {
-                    const int id = a.t.flatten[b + MB + tid];
-                    r0 = a.t.grec[2 * (int64_t)id];
-                    r1 = a.t.grec[2 * (int64_t)id + 1];
-                }
+                // the next batch (of this tile or the next one): its record loads are in flight during this batch
+                if (last_cur) fetch_next_tile(); else fetch();
                 if (q >= 1) mbar_wait(bar(Smem::w_free + warp), (q - 1) & 1);
                 if (warp == 0 || warp == 7) trace(warp ? 1 : 0, 1, q, 0);
-                walked += min(MB, e - b);
+                walked += n_cur;
                 if (__all_sync(0xffffffffu, done)) {
                     // this warp's 32 pixels are finished: its slab of W is all zero
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -310,6 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                     mbar_arrive(bar(Smem::rows_ready + slot));
                 }
                 if (warp == 0 || warp == 7) trace(warp ? 1 : 0, 2, q, 0);
+                ++q;
             }
         }
         // exit sentinel for the other roles
@@ -399,6 +448,11 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
             for (int o = 16; o; o >>= 1) live_rows += __shfl_xor_sync(0xffffffffu, live_rows, o);
             if (lane == 0) atomicAdd((unsigned long long *)&a.stats[0], (unsigned long long)live_rows);
         }
+    } else if (warp == kListerWarp0 || warp == kListerWarp1) {
+        // ====================================== listers ======================================
+        const int r = warp == kListerWarp1;
+        lst::run_lister(a.t, a.unit_counter, a.nunits, a.band, reinterpret_cast<lst::Ring *>(smem + Smem::lring) + r,
+                        bar(Smem::l_full + 2 * lst::NL * r));
     } else if (warp == kProducerWarp) {
         // ===================================== producer ======================================
         if (lane == 0) {

@@ -65,6 +65,17 @@ int launch_tile_sort(int64_t n_isects, int tile_bits, WsDev ws, bool key16, int 
     return sort_pairs(ws.tkeys[0], ws.tkeys[1], ws.tvals[0], ws.tvals[1], n_isects, tile_bits, ws, sorted_buf, st);
 }
 
+// supertile lists: stable sort of the depth-ordered (supertile id, packed index | tile mask << 32) entries by supertile id
+int launch_super_sort(int64_t n_entries, int bits, WsDev ws, int key_bytes, int *sorted_buf, cudaStream_t st) {
+    if (key_bytes == 1)
+        return sort_pairs((unsigned char *)ws.tkeys[0], (unsigned char *)ws.tkeys[1], ws.svals[0], ws.svals[1], n_entries,
+                          bits, ws, sorted_buf, st);
+    if (key_bytes == 2)
+        return sort_pairs((unsigned short *)ws.tkeys[0], (unsigned short *)ws.tkeys[1], ws.svals[0], ws.svals[1], n_entries,
+                          bits, ws, sorted_buf, st);
+    return sort_pairs(ws.tkeys[0], ws.tkeys[1], ws.svals[0], ws.svals[1], n_entries, bits, ws, sorted_buf, st);
+}
+
 // offsets[t] = first sorted position whose tile id >= t; offsets[n_tiles] = n_isects.  Each thread scans kPer
 // consecutive keys (the list is sorted, so tile boundaries are where neighbours differ).
 template <typename KT>
@@ -100,11 +111,13 @@ __global__ void __launch_bounds__(256) offsets_kernel(int64_t n_isects, int n_ti
     }
 }
 
-int launch_offsets(int64_t n_isects, int n_tiles, const void *keys, bool key16, int *offsets, cudaStream_t st) {
+int launch_offsets(int64_t n_isects, int n_tiles, const void *keys, bool key16, int *offsets, cudaStream_t st, bool key8) {
     const int64_t work = n_isects > 0 ? n_isects : (int64_t)n_tiles + 1;
-    const int per = key16 ? 16 : 8;  // keys per thread (offsets_kernel::kPer)
+    const int per = key8 ? 32 : key16 ? 16 : 8;  // keys per thread (offsets_kernel::kPer)
     const unsigned blocks = (unsigned)((work + 256 * per - 1) / (256 * per));
-    if (key16)
+    if (key8)
+        offsets_kernel<<<blocks, 256, 0, st>>>(n_isects, n_tiles, (const unsigned char *)keys, offsets);
+    else if (key16)
         offsets_kernel<<<blocks, 256, 0, st>>>(n_isects, n_tiles, (const unsigned short *)keys, offsets);
     else
         offsets_kernel<<<blocks, 256, 0, st>>>(n_isects, n_tiles, (const unsigned *)keys, offsets);

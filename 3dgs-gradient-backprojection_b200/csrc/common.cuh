@@ -53,7 +53,10 @@ struct CamDev {
     float near_plane, far_plane, radius_clip, eps2d;
     int W, H, tw, th;
     int cull;  // exact tile culling (GWBP_PREPARE_TILE_CULL)
+    int super; // supertile binning (GWBP_PREPARE_SUPERTILE): also count the (Gaussian, supertile) entries
+    int nsx;   // supertiles per row
 };
+constexpr int kSuperW = GWBP_SUPER_W, kSuperH = GWBP_SUPER_H;  // tiles per supertile: 8 x 4 = one 32-bit tile mask
 
 // Typed view of the caller's workspace.
 struct WsDev {
@@ -68,6 +71,8 @@ struct WsDev {
     int *offsets;
     long long *stats;
     unsigned *bin_counts, *bin_seg, *bin_tot;  // sort-free tile binning tables (project.cu)
+    int *spg;                                  // supertile entries per packed Gaussian
+    unsigned long long *svals[2];              // (packed index | tile mask << 32) entries, sort double buffer
     unsigned long long *front;                 // ticket, totals and chained-scan status words of project_pack_kernel
     void *cub_tmp;
     size_t cub_tmp_bytes;
@@ -95,6 +100,9 @@ inline WsDev ws_view(void *base, const gwbp_ws_layout &L) {
     w.bin_counts = (unsigned *)(b + L.bin_counts);
     w.bin_seg = (unsigned *)(b + L.bin_seg);
     w.bin_tot = (unsigned *)(b + L.bin_tot);
+    w.spg = (int *)(b + L.spg);
+    w.svals[0] = (unsigned long long *)(b + L.tvals0);  // tvals0 and tvals1 are adjacent: 8 * cap bytes
+    w.svals[1] = (unsigned long long *)(b + L.svals);
     w.front = (unsigned long long *)(b + L.front);
     w.cub_tmp = (void *)(b + L.cub_tmp);
     w.cub_tmp_bytes = L.cub_tmp_bytes;
@@ -108,14 +116,20 @@ int launch_pack_scene(int64_t n, const float *means, const float *quats, const f
                       const float *opac, void *geo, cudaStream_t st);
 // projection + tile test + ordered compaction in one kernel; totals land in ws.front[1] (intersections), [2] (visible)
 int launch_project_pack(int64_t n, const void *geo, const CamDev &cam, WsDev ws, cudaStream_t st);
-int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, bool gather_erec, cudaStream_t st);
+int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, bool gather_erec, cudaStream_t st,
+                         bool super_counts = false);
+// supertile binning: (supertile id, packed index | tile mask << 32) entries in depth order, stable sort on the id, ranges
+int launch_emit_super(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, int key_bytes,
+                      cudaStream_t st);
+int launch_super_sort(int64_t n_entries, int bits, WsDev ws, int key_bytes, int *sorted_buf, cudaStream_t st);
 int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, bool key16, cudaStream_t st);
 size_t binning_tmp_bytes(int64_t n, int64_t cap);
 int launch_depth_sort(int64_t n_vis, WsDev ws, int *sorted_buf, cudaStream_t st);
 int launch_scan_counts(int64_t n_vis, WsDev ws, cudaStream_t st);
 // key16: tile ids are stored as uint16 in the tkeys buffers (tiles <= 65536): 25 % less sort traffic
 int launch_tile_sort(int64_t n_isects, int tile_bits, WsDev ws, bool key16, int *sorted_buf, cudaStream_t st);
-int launch_offsets(int64_t n_isects, int n_tiles, const void *tkeys, bool key16, int *offsets, cudaStream_t st);
+int launch_offsets(int64_t n_isects, int n_tiles, const void *tkeys, bool key16, int *offsets, cudaStream_t st,
+                   bool key8 = false);
 // sort-free stable tile binning (project.cu): counting pass, three scans, ordered scatter -> offsets + flatten (tvals[0])
 bool bin_fast_supported(int n_tiles);
 size_t bin_table_bytes(int n_tiles, int *chunks_pad, int *tiles_pad, int *nseg, int *chunks, int *wpc);
@@ -126,7 +140,9 @@ void count_launches(int k);
 struct TileCtx {
     const float4 *grec;
     const int *flatten;
-    const int *offsets;
+    const int *offsets;          // per-tile ranges over flatten, or (sents != nullptr) per-supertile ranges over sents
+    const uint2 *sents;          // supertile lists: (packed index, mask of the supertile's 8 x 4 tiles), depth-ordered
+    int nsx;                     // supertiles per row
     long long *scratch;  // 16 device int64 in the workspace (work-queue counters)
     void *dead;          // workspace regions that are dead once the view is prepared (counts, scans, unpacked
     size_t dead_bytes;   // records, hit masks): scratch for the kernels that run on a prepared view

@@ -37,6 +37,8 @@ CamDev make_cam(const gwbp_camera &c) {
     d.near_plane = c.near_plane; d.far_plane = c.far_plane;
     d.radius_clip = c.radius_clip; d.eps2d = c.eps2d;
     d.cull = 0;
+    d.super = 0;
+    d.nsx = (d.tw + kSuperW - 1) / kSuperW;
     return d;
 }
 
@@ -158,6 +160,75 @@ __device__ __forceinline__ CullGauss shfl_cull(const CullGauss &g, int src) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Supertile binning (GWBP_PREPARE_SUPERTILE): a supertile is kSuperW x kSuperH = 8 x 4 tiles.  Per Gaussian and
+// supertile ONE list entry carries the 32-bit mask of the supertile's tiles the Gaussian hits (bit = ly * 8 + lx).
+// super_walk_small() enumerates the entries of a rectangle of <= 64 tiles from its row-major hit mask; the counting
+// (projection kernel) and the emission use the same enumeration, so they cannot disagree.
+// ---------------------------------------------------------------------------------------------
+template <typename F>
+__device__ __forceinline__ void super_walk_small(unsigned long long mk, int x0, int y0, int bw, int nsx, F f) {
+    if (!mk) return;
+    const unsigned long long rowmask = bw < 64 ? ((1ull << bw) - 1ull) : ~0ull;
+    const int nrows = (63 - __clzll((long long)mk)) / bw + 1;  // rows of the rectangle that hold a set bit
+    const int sy1 = (y0 + nrows - 1) / kSuperH, sx1 = (x0 + bw - 1) / kSuperW;
+    for (int sy = y0 / kSuperH; sy <= sy1; ++sy)
+        for (int sx = x0 / kSuperW; sx <= sx1; ++sx) {
+            const int off = x0 - sx * kSuperW;  // column x0 relative to the supertile's first column
+            unsigned sub = 0u;
+#pragma unroll
+            for (int ly = 0; ly < kSuperH; ++ly) {
+                const int rr = sy * kSuperH + ly - y0;
+                if (rr >= 0 && rr < nrows) {
+                    const unsigned long long rowbits = (mk >> (rr * bw)) & rowmask;
+                    const unsigned long long b8 = off >= 0 ? (rowbits << off) : (rowbits >> (-off));
+                    sub |= (unsigned)(b8 & 0xffull) << (kSuperW * ly);
+                }
+            }
+            if (sub) f(sy * nsx + sx, sub);
+        }
+}
+
+// Number of entries super_walk_small() produces, without building the masks: per supertile ROW the union of the
+// rectangle rows that fall into it, then the 8-column groups (aligned to the supertile grid) that hold a set bit.
+__device__ __forceinline__ unsigned super_count_small(unsigned long long mk, int x0, int y0, int bw) {
+    if (!mk) return 0u;
+    const unsigned long long rowmask = bw < 64 ? ((1ull << bw) - 1ull) : ~0ull;
+    const int off = x0 & (kSuperW - 1);
+    unsigned cnt = 0u;
+    int ty = y0;
+    unsigned long long rest = mk;
+    while (rest) {
+        unsigned long long cols = 0ull;
+        const int sy = ty / kSuperH;
+        do {
+            cols |= rest & rowmask;
+            rest = bw < 64 ? rest >> bw : 0ull;
+            ++ty;
+        } while (rest && ty / kSuperH == sy);
+        const unsigned long long lo = cols << off;
+        const unsigned hi = off ? (unsigned)(cols >> (64 - off)) : 0u;  // columns that spill into a ninth group
+        cnt += (unsigned)__popc(__vcmpne4((unsigned)lo, 0u) & 0x01010101u) +
+               (unsigned)__popc(__vcmpne4((unsigned)(lo >> 32), 0u) & 0x01010101u) + (hi != 0u ? 1u : 0u);
+    }
+    return cnt;
+}
+
+// One rectangle of more than 64 tiles, walked supertile by supertile by the whole warp (lane = tile of the supertile).
+// f(supertile id, mask) is called converged for every supertile of the rectangle's range, mask may be 0.
+template <typename F>
+__device__ __forceinline__ void super_walk_big(const CullGauss &sg, int x0, int x1, int y0, int y1, const CamDev &cam, F f) {
+    const int lane = threadIdx.x & 31;
+    const int lx = lane % kSuperW, ly = lane / kSuperW;
+    for (int sy = y0 / kSuperH; sy <= (y1 - 1) / kSuperH; ++sy)
+        for (int sx = x0 / kSuperW; sx <= (x1 - 1) / kSuperW; ++sx) {
+            const int tx = sx * kSuperW + lx, ty = sy * kSuperH + ly;
+            const bool inside = tx >= x0 && tx < x1 && ty >= y0 && ty < y1;
+            const bool hit = inside && (!cam.cull || tile_hit(sg, tx, ty, cam.W, cam.H));
+            f(sy * cam.nsx + sx, __ballot_sync(0xffffffffu, hit));
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
 // EWA projection + tile test + ORDERED COMPACTION in one pass: one thread per Gaussian.
 //
 // Visible Gaussians are written straight to their packed position (ascending index = gsplat's packed=True order):
@@ -169,7 +240,7 @@ __device__ __forceinline__ CullGauss shfl_cull(const CullGauss &g, int src) {
 // ---------------------------------------------------------------------------------------------
 constexpr unsigned kErecBig = 0x80000000u;
 constexpr unsigned long long kDescAgg = 1ull << 62, kDescIncl = 2ull << 62, kDescVal = (1ull << 62) - 1ull;
-constexpr int kFrontHdr = 4;  // front[0] = ticket, [1] = intersections, [2] = visible Gaussians, [3] reserved, then descriptors
+constexpr int kFrontHdr = 4;  // front[0] unused, [1] = intersections, [2] = visible Gaussians, [3] = supertile entries, then status words
 
 __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long *p) {
     unsigned long long v;
@@ -244,7 +315,8 @@ __global__ void __launch_bounds__(kProjThreads) project_pack_kernel(int64_t n, i
                                                            const float2 *__restrict__ geo2, CamDev cam,
                                                            unsigned long long *__restrict__ front,
                                                            float4 *__restrict__ grec, int *__restrict__ radii,
-                                                           int *__restrict__ tpg, uint4 *__restrict__ erec,
+                                                           int *__restrict__ tpg, int *__restrict__ spg,
+                                                           uint4 *__restrict__ erec,
                                                            unsigned *__restrict__ dkeys, unsigned *__restrict__ dvals,
                                                            unsigned long long *__restrict__ scan_n) {
     // The look-back costs a few L2 round trips (microseconds) while a CTA lives ~8 us: done by the compute warps it
@@ -254,13 +326,14 @@ __global__ void __launch_bounds__(kProjThreads) project_pack_kernel(int64_t n, i
     // barrier 1 (arrive only) and each picks up its base through its own barrier 2 + warp (with the scanner alone).
     // CTAs are chained in blockIdx order, as in CUB's device scan (1-D grids are dispatched in order).
     __shared__ unsigned s_wcount[8], s_wbase[8], s_done;
-    __shared__ unsigned long long s_tiles;
+    __shared__ unsigned long long s_tiles, s_ents;
     const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5;
     const bool scanner = wip == 8;
     const unsigned vb = blockIdx.x;
     if (threadIdx.x == kProjPerCta) {
         s_done = 0u;
         s_tiles = 0ull;
+        s_ents = 0ull;
     }
     if (scanner) {
         asm volatile("bar.sync 1, %0;" ::"r"(kProjThreads) : "memory");  // the eight counts (and s_done / s_tiles) are in place
@@ -390,7 +463,7 @@ __global__ void __launch_bounds__(kProjThreads) project_pack_kernel(int64_t n, i
             mk = ((unsigned long long)s_mask[wip][lane][1] << 32) | s_mask[wip][lane][0];
             tiles = (unsigned)__popcll(mk);
         }
-        unsigned m = __ballot_sync(0xffffffffu, big);
+        unsigned m = cam.super ? 0u : __ballot_sync(0xffffffffu, big);
         while (m) {
             const int src = __ffs(m) - 1;
             m &= m - 1;
@@ -406,17 +479,46 @@ __global__ void __launch_bounds__(kProjThreads) project_pack_kernel(int64_t n, i
             if (lane == src) tiles = hits;
         }
     }
+    unsigned sent = 0;  // (Gaussian, supertile) entries of this Gaussian
+    if (cam.super) {
+        if (ok && !big) sent = super_count_small(mk, x0, y0, bw);
+        unsigned m = __ballot_sync(0xffffffffu, big);
+        if (m) {
+            const CullGauss cgb = cull_setup(m2x, m2y, con_x, con_y, con_z, a.w);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const CullGauss sg = shfl_cull(cgb, src);
+                const int sx0 = __shfl_sync(0xffffffffu, x0, src), sx1 = __shfl_sync(0xffffffffu, x1, src);
+                const int sy0 = __shfl_sync(0xffffffffu, y0, src), sy1 = __shfl_sync(0xffffffffu, y1, src);
+                unsigned hits = 0, ents = 0;
+                super_walk_big(sg, sx0, sx1, sy0, sy1, cam, [&](int, unsigned hm) {
+                    hits += (unsigned)__popc(hm);
+                    ents += hm != 0u;
+                });
+                if (lane == src) {
+                    tiles = hits;
+                    sent = ents;
+                }
+            }
+        }
+    }
     // ---- ordered compaction: CTA-local ranks + chained scan over the CTAs ----
     unsigned long long wt = ok ? (unsigned long long)tiles : 0ull;
 #pragma unroll
     for (int o = 16; o; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
     asm volatile("bar.sync %0, 64;" ::"r"(2 + wip) : "memory");  // this warp's base is in s_wbase (s_done / s_tiles are set)
-    if (lane == 0) {  // the CTA's last warp adds the CTA's intersections to the view's total
+    unsigned long long we = ok ? (unsigned long long)sent : 0ull;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) we += __shfl_xor_sync(0xffffffffu, we, o);
+    if (lane == 0) {  // the CTA's last warp adds the CTA's intersections (and supertile entries) to the view's totals
         if (wt) atomicAdd(&s_tiles, wt);
+        if (we) atomicAdd(&s_ents, we);
         __threadfence_block();
         if (atomicAdd(&s_done, 1u) == 7u) {
-            const unsigned long long bt = atomicAdd(&s_tiles, 0ull);
+            const unsigned long long bt = atomicAdd(&s_tiles, 0ull), be = atomicAdd(&s_ents, 0ull);
             if (bt) atomicAdd(front + 1, bt);
+            if (be) atomicAdd(front + 3, be);
         }
     }
     if (ok) {
@@ -425,6 +527,7 @@ __global__ void __launch_bounds__(kProjThreads) project_pack_kernel(int64_t n, i
         grec[2 * (int64_t)pos + 1] = make_float4(con_x, con_y, con_z, z);
         radii[pos] = radius;
         tpg[pos] = (int)tiles;
+        if (cam.super) spg[pos] = (int)sent;
         erec[pos] = big ? make_uint4(0u, 0u, kErecBig, 0u)
                         : make_uint4((unsigned)mk, (unsigned)(mk >> 32),
                                      (unsigned)x0 | ((unsigned)y0 << 12) | ((unsigned)(bw - 1) << 24), 0u);
@@ -442,7 +545,7 @@ int launch_project_pack(int64_t n, const void *geo, const CamDev &cam, WsDev ws,
     const float2 *g2 = (const float2 *)(g1 + n);
     // look-back window: 64 predecessors per step (measured at config G: 32 / 64 / 128 / 256 -> 0.380 / 0.374 / 0.379 / 0.401 ms)
     project_pack_kernel<2><<<(unsigned)nblocks, kProjThreads, 0, st>>>(n, nblocks, g0, g1, g2, cam, ws.front, ws.grec, ws.radii,
-                                                              ws.tiles_per_gauss, ws.erec, ws.dkeys[0], ws.dvals[0],
+                                                              ws.tiles_per_gauss, ws.spg, ws.erec, ws.dkeys[0], ws.dvals[0],
                                                               ws.scan + n);
     count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
@@ -464,9 +567,10 @@ __global__ void __launch_bounds__(256) gather_counts_kernel(int64_t n_vis, const
     if (i == n_vis) out[i] = 0u;
 }
 
-int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, bool gather_erec, cudaStream_t st) {
+int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, bool gather_erec, cudaStream_t st,
+                         bool super_counts) {
     gather_counts_kernel<<<(unsigned)((n_vis + 1 + 255) / 256), 256, 0, st>>>(
-        n_vis, order, ws.tiles_per_gauss, ws.cnt2, ws.erec, gather_erec ? (uint4 *)ws.rec : nullptr);
+        n_vis, order, super_counts ? ws.spg : ws.tiles_per_gauss, ws.cnt2, ws.erec, gather_erec ? (uint4 *)ws.rec : nullptr);
     count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;
@@ -554,6 +658,110 @@ int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev w
     else
         emit_kernel<unsigned><<<blocks, 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.erec,
                                                       ws.tkeys[0], ws.tvals[0], cap);
+    count_launches(1);
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Supertile emission in DEPTH order: thread i takes the i-th nearest visible Gaussian and writes one
+// (supertile id, packed index | tile mask << 32) entry per supertile it reaches.  A stable sort on the supertile id
+// (<= 8 bits up to 1920 x 1088: one radix pass) leaves every supertile's entries in (depth, packed index) order; the
+// back-projection kernels pick the entries whose mask has their tile's bit.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEmitStage = 1536;  // entries a CTA stages in shared memory (256 Gaussians x ~1.7 entries on average)
+template <typename KT>
+__global__ void __launch_bounds__(256) emit_super_kernel(int64_t n_vis, CamDev cam, const unsigned *__restrict__ order,
+                                                         const unsigned *__restrict__ base2,
+                                                         const float4 *__restrict__ grec, const int *__restrict__ radii,
+                                                         const uint4 *__restrict__ erec, KT *__restrict__ skeys,
+                                                         unsigned long long *__restrict__ svals, int64_t cap) {
+    // A CTA's entries are one contiguous run of the output (base2 is the prefix in depth order).  Threads write theirs
+    // at per-thread offsets -- 1- or 2-byte keys and 8-byte values, i.e. partial sectors all over the run -- so the
+    // run is assembled in shared memory and copied out with coalesced stores (0.13 -> ~0.06 ms at config G).  A CTA whose
+    // run does not fit (huge rectangles) writes directly.
+    __shared__ unsigned long long s_val[kEmitStage];
+    __shared__ KT s_key[kEmitStage];
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t i = i0 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool vis = i < n_vis;
+    const long long cta_lo = base2[i0], cta_hi = base2[min(i0 + (int64_t)blockDim.x, n_vis)];
+    const bool staged = cta_hi - cta_lo <= kEmitStage && cta_hi <= cap;
+    int pos = 0;
+    long long base = 0;
+    uint4 er = make_uint4(0u, 0u, 0u, 0u);
+    if (vis) {
+        pos = (int)order[i];
+        base = base2[i];
+        er = erec[pos];
+    }
+    auto put = [&](long long o, int st, unsigned long long v) {
+        if (staged) {
+            s_key[o - cta_lo] = (KT)st;
+            s_val[o - cta_lo] = v;
+        } else if (o < cap) {
+            skeys[o] = (KT)st;
+            svals[o] = v;
+        }
+    };
+    const bool big = vis && (er.z & kErecBig);
+    if (vis && !big) {
+        long long o = base;
+        super_walk_small(((unsigned long long)er.y << 32) | er.x, (int)(er.z & 0xfffu), (int)((er.z >> 12) & 0xfffu),
+                         (int)((er.z >> 24) & 0x3fu) + 1, cam.nsx, [&](int st, unsigned sub) {
+                             put(o, st, (unsigned long long)(unsigned)pos | ((unsigned long long)sub << 32));
+                             ++o;
+                         });
+    }
+    unsigned m = __ballot_sync(0xffffffffu, big);
+    if (m) {  // rare: rectangles of more than 64 tiles are re-tested and emitted by the whole warp
+        int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+        CullGauss cg = {};
+        if (big) {
+            const float4 r0 = grec[2 * (int64_t)pos], r1 = grec[2 * (int64_t)pos + 1];
+            tile_rect(r0.x, r0.y, radii[pos], cam.tw, cam.th, x0, x1, y0, y1);
+            if (cam.cull) cg = cull_setup(r0.x, r0.y, r1.x, r1.y, r1.z, r0.z);
+        }
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const CullGauss sg = shfl_cull(cg, src);
+            const int sx0 = __shfl_sync(0xffffffffu, x0, src), sx1 = __shfl_sync(0xffffffffu, x1, src);
+            const int sy0 = __shfl_sync(0xffffffffu, y0, src), sy1 = __shfl_sync(0xffffffffu, y1, src);
+            const int spos = __shfl_sync(0xffffffffu, pos, src);
+            long long sbase = __shfl_sync(0xffffffffu, base, src);
+            super_walk_big(sg, sx0, sx1, sy0, sy1, cam, [&](int st, unsigned hm) {
+                if (hm) {
+                    if (lane == 0) put(sbase, st, (unsigned long long)(unsigned)spos | ((unsigned long long)hm << 32));
+                    ++sbase;
+                }
+            });
+        }
+    }
+    if (staged) {
+        __syncthreads();
+        const int cnt = (int)(cta_hi - cta_lo);
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+            skeys[cta_lo + k] = s_key[k];
+            svals[cta_lo + k] = s_val[k];
+        }
+    }
+}
+
+int launch_emit_super(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, int key_bytes,
+                      cudaStream_t st) {
+    if (n_vis == 0) return 0;
+    const unsigned blocks = (unsigned)((n_vis + 255) / 256);
+    if (key_bytes == 1)
+        emit_super_kernel<unsigned char><<<blocks, 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.erec,
+                                                                 (unsigned char *)ws.tkeys[0], ws.svals[0], cap);
+    else if (key_bytes == 2)
+        emit_super_kernel<unsigned short><<<blocks, 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.erec,
+                                                                  (unsigned short *)ws.tkeys[0], ws.svals[0], cap);
+    else
+        emit_super_kernel<unsigned><<<blocks, 256, 0, st>>>(n_vis, cam, order, ws.base2, ws.grec, ws.radii, ws.erec,
+                                                            ws.tkeys[0], ws.svals[0], cap);
     count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
     return 0;

@@ -86,13 +86,23 @@ class View:
     (= everything one `rasterization()` call computes before compositing)."""
 
     def __init__(self, scene: PackedScene, cam: L.Camera, cap_isects: Optional[int] = None,
-                 workspace: Optional[torch.Tensor] = None, tile_cull: bool = False, counting_bin: bool = False):
+                 workspace: Optional[torch.Tensor] = None, tile_cull: bool = False, counting_bin: bool = False,
+                 supertile: bool = False):
         """tile_cull=False: the intersection list is gsplat-1.4.0's (bit-exact `meta`).
         tile_cull=True : pairs that cannot reach alpha >= 1/255 on the tile are dropped before the sort
         (identical accumulators, less work) -- the BackProjector default.
         counting_bin=True selects the hand-written sort-free tile binning (images of <= 12 288 tiles) instead of
-        emit + radix sort; both give the same flatten_ids / isect_offsets (the radix path is faster: DESIGN.md)."""
+        emit + radix sort; both give the same flatten_ids / isect_offsets (the radix path is faster: DESIGN.md).
+        supertile=True bins into 8 x 4-tile supertiles (one entry per Gaussian and supertile with a 32-bit tile mask;
+        one radix pass): only the tcgen05 back-projection kernels read such lists (backproject_packed /
+        backproject_lowres); meta(), render*() and the CUDA-core kernel need the per-tile lists."""
         self.scene, self.cam = scene, cam
+        self._flags = ((L.PREPARE_TILE_CULL if tile_cull else L.PREPARE_GSPLAT_EXACT)
+                       | (L.PREPARE_COUNTING_BIN if counting_bin else 0) | (L.PREPARE_SUPERTILE if supertile else 0))
+        self._prepare(cap_isects, workspace)
+
+    def _prepare(self, cap_isects, workspace) -> None:
+        scene, cam = self.scene, self.cam
         n = scene.n
         cap = int(cap_isects) if cap_isects else max(1 << 16, 8 * n)
         while True:
@@ -102,9 +112,7 @@ class View:
             info = L.ViewInfo()
             with torch.cuda.device(scene.device):
                 rc = L.lib().gwbp_view_prepare(C.byref(scene.c), C.byref(cam), workspace.data_ptr(), workspace.numel(),
-                                               cap, (L.PREPARE_TILE_CULL if tile_cull else L.PREPARE_GSPLAT_EXACT)
-                                               | (L.PREPARE_COUNTING_BIN if counting_bin else 0),
-                                               _stream_ptr(scene.device), C.byref(info))
+                                               cap, self._flags, _stream_ptr(scene.device), C.byref(info))
             if rc == -2:  # capacity: the library told us the exact need; grow once and redo
                 cap = int(info.n_isects * 1.25) + 1024
                 workspace = None
@@ -112,6 +120,13 @@ class View:
             L.check(rc, "gwbp_view_prepare")
             break
         self.ws, self.layout, self.info, self.cap = workspace, lay, info, cap
+
+    def _ensure_tile_lists(self) -> None:
+        """Supertile lists are read by the tcgen05 back-projection kernels only.  Anything else (meta(), render*(), the
+        CUDA-core kernel) needs gsplat's per-tile lists: re-bin this view in place (same workspace, same camera)."""
+        if self.info.list_kind != 0:
+            self._flags &= ~L.PREPARE_SUPERTILE
+            self._prepare(self.cap, self.ws)
 
     # typed windows into the workspace (zero-copy; valid while self.ws is alive)
     def _win(self, off: int, count: int, dtype) -> torch.Tensor:
@@ -126,12 +141,18 @@ class View:
     def n_isects(self) -> int:
         return int(self.info.n_isects)
 
+    @property
+    def n_entries(self) -> int:
+        """Sorted list entries: n_isects for per-tile lists, (Gaussian, supertile) pairs for supertile lists."""
+        return int(self.info.n_entries)
+
     def grec(self) -> torch.Tensor:
         return self._win(self.layout.grec, 8 * self.n_vis, torch.float32).view(self.n_vis, 8)
 
     def meta(self) -> dict:
         """The gsplat `meta` dict (packed=True semantics; the reference reads `means2d` and
         `gaussian_ids`: affordance_transfer/demo_affordance_transfer.py:392-395)."""
+        self._ensure_tile_lists()
         g = self.grec()
         nv, ni = self.n_vis, self.n_isects
         sb = self.info.sorted_buf
@@ -176,6 +197,8 @@ class View:
         assert num.shape == (self.scene.n, d) and num.dtype == torch.float32 and num.is_contiguous()
         assert den.shape == (self.scene.n,) and den.dtype == torch.float32 and den.is_contiguous()
         sH, sW, sD = feats.stride()
+        if (kernel & 0xFF) != L.KERNEL_TC:
+            self._ensure_tile_lists()
         with torch.cuda.device(self.scene.device):
             L.check(L.lib().gwbp_backproject_view(
                 C.byref(self.scene.c), C.byref(self.cam), self.ws.data_ptr(), C.byref(self.info), feats.data_ptr(),
@@ -224,6 +247,7 @@ class View:
             colors = colors.contiguous()
         d = colors.shape[1]
         H, W = self.cam.height, self.cam.width
+        self._ensure_tile_lists()
         alloc = torch.empty if self.n_isects else torch.zeros  # the kernels write every pixel
         out = alloc(H, W, d, dtype=torch.float32, device=colors.device)
         alpha = alloc(H, W, dtype=torch.float32, device=colors.device)
@@ -260,6 +284,7 @@ class View:
             assert extra.numel() == self.scene.n, "extra must be [N]"
         out = torch.zeros(k, d + (extra is not None), dtype=torch.float32, device=colors.device)
         alpha = torch.zeros(k, dtype=torch.float32, device=colors.device)
+        self._ensure_tile_lists()
         if k and self.n_isects:
             with torch.cuda.device(self.scene.device):
                 L.check(L.lib().gwbp_render_pixels(

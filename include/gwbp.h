@@ -45,7 +45,7 @@ extern "C" {
 #endif
 
 #define GWBP_TILE 16
-#define GWBP_ABI_VERSION 11
+#define GWBP_ABI_VERSION 12
 
 /* kernel selection for gwbp_backproject_view and gwbp_render_view */
 #define GWBP_KERNEL_AUTO 0
@@ -61,6 +61,15 @@ extern "C" {
                                        instead of emit + radix sort; same flatten_ids / isect_offsets, no sorted tile keys
                                        (tile_key_bytes == 0); images of <= 12 288 tiles only.  Measured SLOWER than the
                                        radix-sort path on B200 (DESIGN.md "dead ends"), hence opt-in */
+
+#define GWBP_PREPARE_SUPERTILE 4    /* bin into SUPERTILES of 8 x 4 tiles (128 x 64 px): one (supertile, depth-ordered) entry
+                                       = (packed index, 32-bit mask of the tiles hit) per Gaussian and supertile, ~2.4x fewer
+                                       entries to emit and sort, and <= 256 supertiles up to 1920 x 1088 = ONE 8-bit sort
+                                       pass.  The tcgen05 back-projection kernels filter a supertile's list down to their
+                                       tile on the fly (same Gaussians, same order, same results); every other consumer
+                                       needs the per-tile lists.  view_info.list_kind == 1 */
+#define GWBP_SUPER_W 8
+#define GWBP_SUPER_H 4
 
 typedef struct gwbp_scene {
     int64_t n;        /* Gaussians */
@@ -97,6 +106,8 @@ typedef struct gwbp_ws_layout {
     size_t bin_counts; /* uint32 [chunks][tiles] per-chunk tile histograms -> exclusive prefixes (sort-free binning) */
     size_t bin_seg;    /* uint32 [segments][tiles] */
     size_t bin_tot;    /* uint32 [tiles]  intersections per tile */
+    size_t spg;       /* int32  [n]     supertile entries per packed Gaussian (GWBP_PREPARE_SUPERTILE) */
+    size_t svals;     /* uint64 [cap]   second buffer of the (packed index | tile mask << 32) entries; the first is tvals0..tvals1 */
     size_t front;     /* uint64 [4 + ceil(n/256)] front-end control block: CTA ticket, intersection / visible totals,
                          one chained-scan status word per projection CTA */
     size_t cub_tmp;   /* scratch for scan / sort */
@@ -109,7 +120,13 @@ typedef struct gwbp_view_info {
     int32_t tile_w, tile_h;
     int32_t sorted_buf; /* which of tkeys0/tkeys1, tvals0/tvals1 holds the sorted result */
     int32_t tile_key_bytes; /* 0: sort-free binning, no tile keys materialised (flatten_ids in tvals0); 2 or 4: element
-                               size of the sorted tkeys buffer of the radix-sort path (16-bit keys when tiles <= 65536) */
+                               size of the sorted tkeys buffer of the radix-sort path (16-bit keys when tiles <= 65536);
+                               supertile lists: 1, 2 or 4 */
+    int32_t list_kind;      /* 0: per-tile lists (flatten_ids + isect_offsets); 1: per-supertile lists (GWBP_PREPARE_SUPERTILE):
+                               `offsets` holds super_w * super_h + 1 supertile ranges over the sorted 64-bit entries */
+    int32_t super_w, super_h; /* supertiles per row / column (list_kind 1) */
+    int32_t reserved;
+    int64_t n_entries;      /* sorted list entries: == n_isects for per-tile lists, (Gaussian, supertile) pairs otherwise */
 } gwbp_view_info;
 
 /* counters filled by gwbp_backproject_view when `stats` != NULL (device int64[4]):

@@ -51,8 +51,8 @@ def test_struct_sizes_match_header(gwbp):
     L = gwbp._lib
     assert ctypes.sizeof(L.Scene) == 16
     assert ctypes.sizeof(L.Camera) == 16 * 4 + 9 * 4 + 2 * 4 + 4 * 4
-    assert ctypes.sizeof(L.ViewInfo) == 40
-    assert ctypes.sizeof(L.WsLayout) == 27 * ctypes.sizeof(ctypes.c_size_t)
+    assert ctypes.sizeof(L.ViewInfo) == 64
+    assert ctypes.sizeof(L.WsLayout) == 29 * ctypes.sizeof(ctypes.c_size_t)
 
 
 def test_rasterization_signature_matches_gsplat(gwbp):

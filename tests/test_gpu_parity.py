@@ -254,6 +254,41 @@ def test_tile_culling_does_not_change_the_accumulators(gwbp, case):
     assert torch.equal(d0 > 1e-12, d1 > 1e-12)
 
 
+@pytest.mark.parametrize("cull", [False, True])
+@pytest.mark.parametrize("scale_mul,W,H", [(1.0, 256, 256), (1.0, 422, 274), (6.0, 330, 230), (25.0, 211, 137)])
+def test_supertile_lists_give_the_per_tile_results(gwbp, scale_mul, W, H, cull):
+    """BackProjector bins views for the tcgen05 kernels into 8 x 4-tile supertiles (one entry per Gaussian and
+    supertile + a 32-bit tile mask, filtered per tile by the kernels' lister warp).  Same Gaussians in the same order as
+    the per-tile lists: identical walk / row counters, identical intersection counts, accumulators equal up to the
+    order of the fp32 atomic adds.  scale_mul blows the Gaussians up so that rectangles of more than 64 tiles (the
+    warp-cooperative path) and masks spanning several supertiles occur; odd image sizes give partial supertiles."""
+    S = gwbp.scene
+    sc = S.make_scene(20000, 3)
+    scales = (sc.scales * scale_mul).astype(np.float32)
+    vm, K = S.make_cameras(3, W, H, 3)
+    d = 32
+    feats = [_feat_dev(S.make_feature_map_np(v, d, H, W, 3)) for v in range(3)]
+    out = []
+    for sup in (False, True):
+        bp = gwbp.BackProjector(_dev(sc.means), _dev(sc.quats), _dev(scales), _dev(sc.opacities), d, kernel="tc",
+                                collect_stats=True, tile_cull=cull, supertile=sup)
+        counts = []
+        for v in range(3):
+            view = bp.add_view(vm[v], K, W, H, feats[v])
+            assert view.info.list_kind == int(sup)
+            counts.append((view.n_vis, view.n_isects))
+            if sup:
+                assert 0 < view.n_entries <= view.n_isects
+        out.append((bp.num.clone(), bp.den.clone(), bp.stats(), counts))
+    (n0, d0, s0, c0), (n1, d1, s1, c1) = out
+    assert c0 == c1 and s0 == s1, (c0, c1, s0, s1)
+    assert torch.equal(d0 > 1e-12, d1 > 1e-12)
+    assert torch.allclose(d0, d1, rtol=2e-6, atol=1e-12)
+    seen = d0 > 1e-6
+    err = (n0[seen] - n1[seen]).norm(dim=1) / n0[seen].norm(dim=1).clamp_min(1e-9)
+    assert float(err.max()) < 2e-5, float(err.max())
+
+
 def test_tile_culling_config_S_identical_results(gwbp):
     """Tile culling is ON by default in BackProjector and is not part of gsplat: at config S (50k Gaussians, 8 views
     of 256x256) the culled and the gsplat-exact intersection lists must give the same non-zero rows, the same prune
