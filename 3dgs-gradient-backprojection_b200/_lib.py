@@ -32,8 +32,8 @@ class WsLayout(C.Structure):
     _fields_ = [(k, C.c_size_t) for k in ("total", "cnt", "scan", "rec", "mask", "grec", "erec", "radii",
                                           "tiles_per_gauss", "dkeys0", "dkeys1", "dvals0", "dvals1", "cnt2", "base2",
                                           "tkeys0", "tkeys1", "tvals0", "tvals1", "offsets", "stats", "bin_counts", "bin_seg",
-                                          "bin_tot", "spg", "svals", "front", "cub_tmp",
-                                          "cub_tmp_bytes")]
+                                          "bin_tot", "spg", "svals", "front", "sort_tmp",
+                                          "sort_tmp_bytes")]
 
 
 class ViewInfo(C.Structure):

@@ -129,8 +129,8 @@ int gwbp_workspace_layout(int64_t n, int32_t width, int32_t height, int64_t cap,
     L->spg = o; o = align_up(o + sizeof(int) * n1);
     L->svals = o; o = align_up(o + sizeof(unsigned long long) * c1);
     L->front = o; o = align_up(o + sizeof(unsigned long long) * (size_t)(4 + (n + 255) / 256));
-    L->cub_tmp_bytes = binning_tmp_bytes(n, c1);
-    L->cub_tmp = o; o = align_up(o + L->cub_tmp_bytes);
+    L->sort_tmp_bytes = binning_tmp_bytes(n, c1);
+    L->sort_tmp = o; o = align_up(o + L->sort_tmp_bytes);
     L->total = o;
     return 0;
 }

@@ -74,8 +74,8 @@ struct WsDev {
     int *spg;                                  // supertile entries per packed Gaussian
     unsigned long long *svals[2];              // (packed index | tile mask << 32) entries, sort double buffer
     unsigned long long *front;                 // ticket, totals and chained-scan status words of project_pack_kernel
-    void *cub_tmp;
-    size_t cub_tmp_bytes;
+    void *sort_tmp;
+    size_t sort_tmp_bytes;
 };
 
 inline WsDev ws_view(void *base, const gwbp_ws_layout &L) {
@@ -104,8 +104,8 @@ inline WsDev ws_view(void *base, const gwbp_ws_layout &L) {
     w.svals[0] = (unsigned long long *)(b + L.tvals0);  // tvals0 and tvals1 are adjacent: 8 * cap bytes
     w.svals[1] = (unsigned long long *)(b + L.svals);
     w.front = (unsigned long long *)(b + L.front);
-    w.cub_tmp = (void *)(b + L.cub_tmp);
-    w.cub_tmp_bytes = L.cub_tmp_bytes;
+    w.sort_tmp = (void *)(b + L.sort_tmp);
+    w.sort_tmp_bytes = L.sort_tmp_bytes;
     return w;
 }
 

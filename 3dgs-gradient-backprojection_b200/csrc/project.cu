@@ -17,6 +17,7 @@
 // roundings (bit-exactness against the FMA-free oracle) and the exact tile test on ~7 candidate tiles per visible
 // Gaussian it is instruction-issue-bound (ncu: issue slots 84 % busy, DRAM 20 %), see DESIGN.md.
 #include "common.cuh"
+#include "chain.cuh"
 
 namespace gwbp {
 
@@ -239,73 +240,7 @@ __device__ __forceinline__ void super_walk_big(const CullGauss &sg, int x0, int 
 // hit masks: 56 B written and read back per Gaussian).
 // ---------------------------------------------------------------------------------------------
 constexpr unsigned kErecBig = 0x80000000u;
-constexpr unsigned long long kDescAgg = 1ull << 62, kDescIncl = 2ull << 62, kDescVal = (1ull << 62) - 1ull;
 constexpr int kFrontHdr = 4;  // front[0] unused, [1] = intersections, [2] = visible Gaussians, [3] = supertile entries, then status words
-
-__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// Chained scan with decoupled look-back over the CTAs (ticket order).  chained_publish() makes a CTA's aggregate
-// visible as soon as it is known; chained_lookback(), called later by ONE WARP of the CTA, walks back over the
-// predecessors' status words -- 256 per step (8 per lane, nearest first), because all CTAs of a wave publish at about the
-// same time and the nearest word that already holds an inclusive prefix is typically a whole wave (~600 CTAs) away --
-// publishes the CTA's inclusive prefix and returns the exclusive one (all lanes).
-__device__ __forceinline__ void chained_publish(unsigned long long *desc, unsigned vb, unsigned long long agg) {
-    st_relaxed(desc + vb, (vb == 0 ? kDescIncl : kDescAgg) | agg);
-}
-template <int kLookPerLane>
-__device__ __forceinline__ unsigned long long chained_lookback(unsigned long long *desc, unsigned vb, unsigned long long agg) {
-    const int lane = threadIdx.x & 31;
-    unsigned long long excl = 0ull;
-    if (vb > 0) {
-        long long j = (long long)vb - 1;
-        while (true) {
-            // word u*32 + lane of the window = predecessor j - (u*32 + lane): every load instruction reads 256 contiguous
-            // bytes (8 sectors).  [With 8 consecutive words per lane a window cost 256 sector requests and the ~600
-            // resident look-back warps saturated the L2 request rate: ~4 us per round trip.]
-            unsigned long long dsc[kLookPerLane];
-#pragma unroll
-            for (int u = 0; u < kLookPerLane; ++u) {  // all loads of a step are in flight together
-                const long long idx = j - (long long)(u * 32 + lane);
-                dsc[u] = idx >= 0 ? ld_relaxed(desc + idx) : kDescIncl;
-            }
-            while (true) {  // rare: a predecessor has started (dispatch order) but not published yet
-                bool ready = true;
-#pragma unroll
-                for (int u = 0; u < kLookPerLane; ++u) ready = ready && (dsc[u] >> 62) != 0ull;
-                if (__all_sync(0xffffffffu, ready)) break;
-                __nanosleep(64);
-#pragma unroll
-                for (int u = 0; u < kLookPerLane; ++u)
-                    if ((dsc[u] >> 62) == 0ull) dsc[u] = ld_relaxed(desc + (j - (long long)(u * 32 + lane)));
-            }
-            unsigned long long v = 0ull;
-            bool found = false;
-#pragma unroll
-            for (int u = 0; u < kLookPerLane; ++u) {  // nearest group of 32 first
-                if (!found) {
-                    const unsigned imask = __ballot_sync(0xffffffffu, (dsc[u] >> 62) == 2ull);
-                    const int first = __ffs(imask) - 1;  // nearest word of this group that holds an inclusive prefix
-                    if (first < 0 || lane <= first) v += dsc[u] & kDescVal;
-                    found = first >= 0;
-                }
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            excl += v;
-            if (found) break;
-            j -= 32 * kLookPerLane;
-        }
-        if (lane == 0) st_relaxed(desc + vb, kDescIncl | (excl + agg));
-    }
-    return excl;
-}
 
 constexpr int kProjPerCta = 256;                  // Gaussians per CTA: warps 0-7, one thread each
 constexpr int kProjThreads = kProjPerCta + 32;    // + warp 8: ticket and chained scan only

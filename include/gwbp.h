@@ -110,8 +110,8 @@ typedef struct gwbp_ws_layout {
     size_t svals;     /* uint64 [cap]   second buffer of the (packed index | tile mask << 32) entries; the first is tvals0..tvals1 */
     size_t front;     /* uint64 [4 + ceil(n/256)] front-end control block: CTA ticket, intersection / visible totals,
                          one chained-scan status word per projection CTA */
-    size_t cub_tmp;   /* scratch for scan / sort */
-    size_t cub_tmp_bytes;
+    size_t sort_tmp;   /* scratch for scan / sort */
+    size_t sort_tmp_bytes;
 } gwbp_ws_layout;
 
 typedef struct gwbp_view_info {

@@ -34,8 +34,8 @@ def test_layout_and_argument_validation_without_gpu(gwbp):
     assert lib.gwbp_workspace_layout(1000, 64, 48, 5000, ctypes.byref(lay)) == 0
     offs = [lay.cnt, lay.scan, lay.rec, lay.mask, lay.grec, lay.erec, lay.radii, lay.tiles_per_gauss, lay.dkeys0,
             lay.dkeys1, lay.dvals0, lay.dvals1, lay.cnt2, lay.base2, lay.tkeys0, lay.tkeys1, lay.tvals0, lay.tvals1,
-            lay.offsets, lay.stats, lay.bin_counts, lay.bin_seg, lay.bin_tot, lay.cub_tmp]
-    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and lay.total >= lay.cub_tmp + lay.cub_tmp_bytes
+            lay.offsets, lay.stats, lay.bin_counts, lay.bin_seg, lay.bin_tot, lay.sort_tmp]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and lay.total >= lay.sort_tmp + lay.sort_tmp_bytes
     assert lib.gwbp_workspace_layout(-5, 64, 48, 10, ctypes.byref(lay)) < 0
     assert "n out of range" in L.last_error()
     assert lib.gwbp_workspace_layout(10, 0, 48, 10, ctypes.byref(lay)) < 0
