@@ -79,11 +79,19 @@ SIGNATURES = {
     "gwbp_sh_colors": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "gwbp_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "gwbp_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
+    "gwbp_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gwbp_ipc_close": (C.c_int, [C.c_void_p]),
+    "gwbp_peer_reduce_supported": (C.c_int, [C.c_int32, C.c_int32]),
+    "gwbp_peer_reduce_finalize": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64,
+                                            C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gwbp_mask3d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                               C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gwbp_mask2d": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                               C.c_void_p]),
 }
+
+IPC_HANDLE_BYTES, MAX_PEERS = 64, 8
 
 PROFILE_STAGES = ("project", "count_scan_and_readback", "compact", "depth_sort", "tile_binning", "feature_relayout",
                   "backproject")

@@ -1,5 +1,6 @@
 // extern "C" surface of libgwbp.so (see include/gwbp.h for the contract and the reference
 // call sites each entry point replaces).
+#include <cuda.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -429,6 +430,63 @@ int gwbp_finalize(const float *num, const float *den, float *out, int64_t n, int
     if (n == 0) return 0;
     GWBP_REQUIRE(num && den && out, "finalize: NULL pointer");
     return launch_finalize(num, den, out, n, d, (cudaStream_t)stream);
+}
+
+// ---- peer memory (CUDA IPC) + the fused closing step ----
+int gwbp_ipc_export(const void *ptr, void *handle_out, int64_t *offset_out) {
+    GWBP_REQUIRE(ptr && handle_out && offset_out, "ipc_export: NULL pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == GWBP_IPC_HANDLE_BYTES, "IPC handle size");
+    typedef CUresult (*RangeFn)(CUdeviceptr *, size_t *, CUdeviceptr);
+    static RangeFn range = nullptr;
+    if (!range) {
+        void *fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            range = (RangeFn)fp;
+    }
+    GWBP_REQUIRE(range != nullptr, "cuMemGetAddressRange is not available from this driver");
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    const CUresult r = range(&base, &size, (CUdeviceptr)ptr);
+    GWBP_REQUIRE(r == CUDA_SUCCESS, "cuMemGetAddressRange failed (%d): not a device allocation?", (int)r);
+    cudaIpcMemHandle_t h;
+    GWBP_CUDA_OK(cudaIpcGetMemHandle(&h, (void *)base));  // fails for VMM memory (expandable segments): caller falls back
+    memcpy(handle_out, &h, sizeof(h));
+    *offset_out = (int64_t)((CUdeviceptr)ptr - base);
+    return 0;
+}
+
+int gwbp_ipc_open(const void *handle, void **base_out) {
+    GWBP_REQUIRE(handle && base_out, "ipc_open: NULL pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    GWBP_CUDA_OK(cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int gwbp_ipc_close(void *base) {
+    if (!base) return 0;
+    GWBP_CUDA_OK(cudaIpcCloseMemHandle(base));
+    return 0;
+}
+
+int gwbp_peer_reduce_supported(int32_t world, int32_t d) { return peer_reduce_supported(world, d) ? 1 : 0; }
+
+int gwbp_peer_reduce_finalize(const void *const *num_ptrs, const void *const *den_ptrs, int32_t world, int64_t lo,
+                              int64_t rows, int32_t d, float eps, float *out_feat, float *out_num, float *out_den,
+                              void *stream) {
+    GWBP_REQUIRE(peer_reduce_supported(world, d), "peer_reduce_finalize: unsupported shape (world=%d, d=%d)", world, d);
+    GWBP_REQUIRE(lo >= 0 && rows >= 0, "peer_reduce_finalize: bad row range");
+    if (rows == 0) return 0;
+    GWBP_REQUIRE(num_ptrs && den_ptrs, "peer_reduce_finalize: NULL pointer table");
+    for (int r = 0; r < world; ++r) {
+        GWBP_REQUIRE(num_ptrs[r] && den_ptrs[r], "peer_reduce_finalize: NULL pointer for rank %d", r);
+        GWBP_REQUIRE(((uintptr_t)num_ptrs[r] & 15) == 0, "peer_reduce_finalize: num of rank %d is not 16-byte aligned", r);
+    }
+    GWBP_REQUIRE((((uintptr_t)out_feat | (uintptr_t)out_num) & 15) == 0, "peer_reduce_finalize: outputs must be 16-byte aligned");
+    return launch_peer_reduce_finalize((const float *const *)num_ptrs, (const float *const *)den_ptrs, world, lo, rows, d, eps,
+                                       out_feat, out_num, out_den, (cudaStream_t)stream);
 }
 
 int gwbp_mask3d(const float *x, int64_t rows, int32_t d, const float *text, int32_t p, int32_t npos, float threshold,

@@ -160,6 +160,12 @@ int launch_ratio_accumulate(const float4 *grec, int64_t n_vis, float *num_v, flo
 int launch_sh_colors(int64_t n, int degree, const float *means, const float *coeffs, int64_t sN, int64_t sK, int64_t sC,
                      const float *cam_pos_host, float *out, cudaStream_t st);
 int launch_finalize(const float *num, const float *den, float *out, int64_t n, int d, cudaStream_t st);
+// sparse reduce-scatter over peer memory fused with the finalise (finalize.cu): rows [lo, lo + rows) of the field
+constexpr int kMaxPeers = GWBP_MAX_PEERS;
+bool peer_reduce_supported(int world, int d);
+int launch_peer_reduce_finalize(const float *const *num_ptrs, const float *const *den_ptrs, int world, int64_t lo,
+                                int64_t rows, int d, float eps, float *out_feat, float *out_num, float *out_den,
+                                cudaStream_t st);
 int launch_mask(const float *x, int64_t rows, int d, const float *text, int p, int npos, float thr,
                 int use_thr, uint8_t *mask, float *score, cudaStream_t st);
 

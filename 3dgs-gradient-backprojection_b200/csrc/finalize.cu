@@ -111,6 +111,121 @@ int launch_finalize(const float *num, const float *den, float *out, int64_t n, i
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Closing step of a view-sharded job, fused: sparse reduce-scatter over NVLink PEER MEMORY + finalise in ONE kernel.
+//
+// Every rank holds full (num[N,D], den[N]) accumulators but its views only touched a fraction of the rows (config G,
+// 8 ranks x 20 views: 12 % per rank -- the rows a view reaches are the un-occluded surface, which is why the reference
+// needs prune_by_gradients at all).  A dense reduce-scatter moves all 11.9 GB regardless.  Here rank r owns rows
+// [lo, lo + rows); one warp per owned row reads the W den values (4 bytes per peer), and pulls a peer's 2 KB num row
+// through its NVLink mapping ONLY if that peer touched the row (den_peer > eps); the partial rows are added in rank
+// order (deterministic, unlike a ring), divided by the summed den, normalised (backproject.py:166-169) and written
+// once.  Rows nobody touched cost W den reads and one zero row.  Pointers come from cudaIpcOpenMemHandle
+// (gwbp_ipc_*), W <= 8 ranks of one node.
+// ---------------------------------------------------------------------------------------------------------------
+struct PeerPtrs {
+    const float *num[kMaxPeers];
+    const float *den[kMaxPeers];
+};
+
+__device__ __forceinline__ float4 ld_peer4(const float4 *p) {  // L2-only: peer rows are read once
+    return __ldcg(p);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) peer_reduce_finalize_kernel(PeerPtrs p, int world, int64_t lo, int64_t rows, int d,
+                                                                   float eps, float *__restrict__ out_feat,
+                                                                   float *__restrict__ out_num, float *__restrict__ out_den) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int64_t g = lo + row;
+    const float dr = lane < world ? __ldcg(p.den[lane] + g) : 0.0f;
+    const unsigned touched = __ballot_sync(0xffffffffu, lane < world && dr > eps);
+    // the reference's 1e-12 initialiser is counted once (dist.py): den_0 + sum_{r>0} (den_r - eps), rank order
+    float total = __shfl_sync(0xffffffffu, dr, 0);
+    for (int r = 1; r < world; ++r) total += __shfl_sync(0xffffffffu, dr, r) - eps;
+    if (lane == 0 && out_den) out_den[row] = total;
+    const int n4 = d >> 2;
+    float4 acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned m = touched;
+    while (m) {  // two peers' rows in flight per step, added in rank order
+        const int r0 = __ffs(m) - 1;
+        m &= m - 1;
+        const int r1 = m ? __ffs(m) - 1 : -1;
+        if (r1 >= 0) m &= m - 1;
+        const float4 *s0 = reinterpret_cast<const float4 *>(p.num[r0] + g * d);
+        const float4 *s1 = r1 >= 0 ? reinterpret_cast<const float4 *>(p.num[r1] + g * d) : nullptr;
+        float4 a[VEC], b[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const int k = lane + 32 * j;
+            a[j] = k < n4 ? ld_peer4(s0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const int k = lane + 32 * j;
+            b[j] = (s1 && k < n4) ? ld_peer4(s1 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            acc[j].x += a[j].x; acc[j].y += a[j].y; acc[j].z += a[j].z; acc[j].w += a[j].w;
+            acc[j].x += b[j].x; acc[j].y += b[j].y; acc[j].z += b[j].z; acc[j].w += b[j].w;
+        }
+    }
+    if (out_num) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const int k = lane + 32 * j;
+            if (k < n4) reinterpret_cast<float4 *>(out_num + row * d)[k] = acc[j];
+        }
+    }
+    if (!out_feat) return;
+    // finalise exactly as finalize_kernel<VEC> (one reciprocal per row; NaN -> 0)
+    const float rd = 1.0f / total;
+    float ss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        acc[j].x *= rd; acc[j].y *= rd; acc[j].z *= rd; acc[j].w *= rd;
+        ss += acc[j].x * acc[j].x + acc[j].y * acc[j].y + acc[j].z * acc[j].z + acc[j].w * acc[j].w;
+    }
+    ss = warp_sum(ss);
+    const float rn = 1.0f / sqrtf(ss);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const int k = lane + 32 * j;
+        if (k < n4) {
+            float4 v = make_float4(acc[j].x * rn, acc[j].y * rn, acc[j].z * rn, acc[j].w * rn);
+            v.x = isnan(v.x) ? 0.0f : v.x; v.y = isnan(v.y) ? 0.0f : v.y;
+            v.z = isnan(v.z) ? 0.0f : v.z; v.w = isnan(v.w) ? 0.0f : v.w;
+            reinterpret_cast<float4 *>(out_feat + row * d)[k] = v;
+        }
+    }
+}
+
+bool peer_reduce_supported(int world, int d) { return world >= 1 && world <= kMaxPeers && (d & 3) == 0 && d >= 4 && d <= 1024; }
+
+int launch_peer_reduce_finalize(const float *const *num_ptrs, const float *const *den_ptrs, int world, int64_t lo,
+                                int64_t rows, int d, float eps, float *out_feat, float *out_num, float *out_den,
+                                cudaStream_t st) {
+    if (rows == 0) return 0;
+    PeerPtrs p = {};
+    for (int r = 0; r < world; ++r) {
+        p.num[r] = num_ptrs[r];
+        p.den[r] = den_ptrs[r];
+    }
+    const unsigned blocks = (unsigned)((rows + 7) / 8);
+    if (d <= 512)
+        peer_reduce_finalize_kernel<4><<<blocks, 256, 0, st>>>(p, world, lo, rows, d, eps, out_feat, out_num, out_den);
+    else
+        peer_reduce_finalize_kernel<8><<<blocks, 256, 0, st>>>(p, world, lo, rows, d, eps, out_feat, out_num, out_den);
+    count_launches(1);
+    GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // Per-view-ratio accumulation over the Gaussians one view saw (packed records, depth order): one warp per
 // record.  Rows the view never touched hold zeros in (num_v, den_v) and contribute 0/(0+eps) = 0 in the
 // reference's dense expression, so skipping them is exact.

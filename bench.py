@@ -262,8 +262,20 @@ def run_ours(args, cfg):
 
     for i in range(args.warmup):
         step(i)
-    if world > 1:  # warm-up of the closing exchange too (NCCL channel setup / buffer registration is lazy)
-        if args.collective == "allreduce":
+    px, collective, peer_note = None, args.collective, None
+    if world > 1:  # warm-up of the closing exchange too (NCCL channel setup / buffer registration / IPC mappings are lazy)
+        if collective in ("auto", "peer"):
+            px = gwbp.dist.peer_exchange_for(bp)  # collective: every rank maps every rank's accumulators (CUDA IPC)
+            if px is None:
+                if collective == "peer":
+                    raise RuntimeError("--collective peer: peer memory could not be set up on this box")
+                peer_note = "peer memory unavailable on this box: NCCL reduce-scatter instead"
+                collective = "reduce_scatter"
+            else:
+                collective = "peer"
+        if collective == "peer":
+            px.reduce_finalize()
+        elif collective == "allreduce":
             gwbp.dist.allreduce_accumulators(bp.num, bp.den)
         else:
             gwbp.dist.reduce_scatter_accumulators(bp.num, bp.den)
@@ -284,7 +296,9 @@ def run_ours(args, cfg):
     e1.record()
     launches = int(gwbp._lib.lib().gwbp_launch_count()) - launches0  # kernels libgwbp.so launched in the timed loop
     if world > 1:
-        if args.collective == "allreduce":
+        if collective == "peer":  # sparse pull over NVLink peer memory + finalise, ONE kernel per rank (dist.PeerExchange)
+            px.reduce_finalize()
+        elif collective == "allreduce":
             gwbp.dist.allreduce_accumulators(bp.num, bp.den)
         else:  # every rank keeps (and would finalise / save) its own rows of the feature field
             gwbp.dist.reduce_scatter_accumulators(bp.num, bp.den)
@@ -466,9 +480,12 @@ def run_ours(args, cfg):
                            **cfg, "kernel": args.kernel, "features": args.features,
                            "l2": f"{pool_n} feature maps of {fmap_bytes / 1e9:.2f} GB cycled: every view's input "
                                  "is far larger than the 126 MB L2",
-                           "parallelism": f"views sharded over {world} GPU(s), one {args.collective} of (num, den) at the end"},
+                           "parallelism": f"views sharded over {world} GPU(s), one closing exchange of (num, den): " + {
+                               "peer": "sparse reduce-scatter over NVLink peer memory fused with the finalise (one kernel per rank)",
+                               "reduce_scatter": "NCCL reduce-scatter", "allreduce": "NCCL all-reduce",
+                               "auto": "none (1 GPU)"}[collective]},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "ms_views": ms_views, "exchange_ms": ms_total - ms_views, "exchange": args.collective if world > 1 else None,
+                "ms_views": ms_views, "exchange_ms": ms_total - ms_views, "exchange": collective if world > 1 else None, "exchange_note": peer_note,
                 "roofline": roofline, "cpu_baseline": cpu, "shim": shim}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
@@ -600,10 +617,11 @@ def main():
     ap.add_argument("--features", default="full", choices=["full", "lowres"],
                     help="full: [H,W,D] map resident in HBM (the BASELINE metric); lowres: encoder-resolution map, "
                          "bilinear upsample fused into the feature re-layout (not the headline)")
-    ap.add_argument("--collective", default="reduce_scatter", choices=["allreduce", "reduce_scatter"],
-                    help="closing exchange of (num, den) for N > 1: reduce_scatter (default; every rank ends with the "
-                         "global sums of ITS rows, finalises and saves them -- half the NVLink volume) or allreduce "
-                         "(every rank ends with the full field)")
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "allreduce", "reduce_scatter"],
+                    help="closing exchange of (num, den) for N > 1: peer = sparse reduce-scatter over NVLink peer memory "
+                         "fused with the finalise, one hand-written kernel per rank (auto: peer when CUDA IPC mappings "
+                         "can be set up, else reduce_scatter); reduce_scatter = NCCL, every rank ends with the global "
+                         "sums of ITS rows; allreduce = NCCL, every rank ends with the full field")
     ap.add_argument("--stage-views", type=int, default=6, help="views of the per-stage profiling loop (0 = skip)")
     ap.add_argument("--shim-views", type=int, default=2,
                     help="views of the zero-edit shim loop (3 x rasterization + 2 x backward per view; 0 = skip)")

@@ -31,6 +31,8 @@
  *                            (affordance_transfer/demo_affordance_transfer.py:768-796)
  *   gwbp_sh_colors ......... the SH -> RGB stage of `rasterization(sh_degree=3)` (backproject.py:88-100)
  *   gwbp_finalize .......... backproject.py:166-169
+ *   gwbp_peer_reduce_finalize  the multi-GPU closing step (all-reduce of the accumulators) + finalise,
+ *                            fused into one kernel over NVLink peer memory; gwbp_ipc_* carry the mappings
  *   gwbp_mask3d ............ segment.py:52-58
  *   gwbp_mask2d ............ segment.py:221-224
  */
@@ -237,6 +239,27 @@ int gwbp_sh_colors(int64_t n, int32_t degree, const float *means, const float *c
 
 /* out[g,:] = normalise(num[g,:]/den[g]); NaN -> 0   (backproject.py:166-169); out may alias num */
 int gwbp_finalize(const float *num, const float *den, float *out, int64_t n, int32_t d, void *stream);
+
+/* ---- closing step of a view-sharded job over NVLink peer memory (replaces the NCCL all-reduce of SURVEY.md 8e + the
+ * finalise of backproject.py:166-169 when every rank only needs ITS rows of the field) ----
+ * gwbp_ipc_export: CUDA IPC handle (64 bytes) of the allocation that holds `ptr` + the byte offset of `ptr` inside it;
+ * gwbp_ipc_open: map a peer process' allocation into this process (peer access enabled lazily), returns its base;
+ * gwbp_ipc_close: unmap.  The handles travel over the host side's own channel (torch.distributed all_gather_object). */
+#define GWBP_MAX_PEERS 8
+#define GWBP_IPC_HANDLE_BYTES 64
+int gwbp_ipc_export(const void *ptr, void *handle_out, int64_t *offset_out);
+int gwbp_ipc_open(const void *handle, void **base_out);
+int gwbp_ipc_close(void *base);
+/* 1 if gwbp_peer_reduce_finalize covers (world, d): world <= 8, d % 4 == 0, d <= 1024 */
+int gwbp_peer_reduce_supported(int32_t world, int32_t d);
+/* For the rows [lo, lo + rows) this rank owns: den = den_0 + sum_{r>0}(den_r - eps); num = sum over the ranks that
+ * touched the row (den_r > eps), rank order; out_feat = normalise(num/den), NaN -> 0.  num_ptrs / den_ptrs: HOST arrays
+ * of `world` DEVICE pointers to every rank's full num[N,d] / den[N] (own pointers for this rank, gwbp_ipc_open mappings
+ * for the peers).  out_feat [rows,d], out_num [rows,d], out_den [rows]: each optional (NULL).  The caller orders the call
+ * after every rank's last view (barrier) and keeps the accumulators untouched until every rank's call has finished. */
+int gwbp_peer_reduce_finalize(const void *const *num_ptrs, const void *const *den_ptrs, int32_t world, int64_t lo,
+                              int64_t rows, int32_t d, float eps, float *out_feat, float *out_num, float *out_den,
+                              void *stream);
 
 /* mask[i] = max_{j<npos} s_ij > max_{j>=npos} s_ij (and s_i0 > threshold if use_threshold),
  * s = normalise(x_i) . normalise(text_j).  x [rows,d] contiguous, text [p,d]; score [rows,p] optional */
