@@ -64,6 +64,8 @@ SIGNATURES = {
                                         C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gwbp_lowres_adjoint_supported": (C.c_int, [C.c_int32] * 6),
+    "gwbp_pack_lowres_adjoint": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                           C.c_void_p, C.c_void_p]),
     "gwbp_backproject_view_lowres": (C.c_int, [C.POINTER(Scene), C.POINTER(Camera), C.c_void_p, C.POINTER(ViewInfo),
                                                C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64,
                                                C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -92,6 +94,7 @@ SIGNATURES = {
 }
 
 IPC_HANDLE_BYTES, MAX_PEERS = 64, 8
+LOWRES_PACKED = 2
 
 PROFILE_STAGES = ("project", "count_scan_and_readback", "compact", "depth_sort", "tile_binning", "feature_relayout",
                   "backproject")

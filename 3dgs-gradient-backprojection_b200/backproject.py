@@ -178,23 +178,31 @@ class BackProjector:
             elif self.kernel == L.KERNEL_TC:
                 raise RuntimeError(f"tcgen05 kernel does not support D={self.d}")
         adjoint = fp is not None and lowres_mode is not None and self.lowres_impl == "adjoint"
-        overlap = fp is not None and self.overlap_pack and not adjoint
+        if adjoint and not L.lib().gwbp_lowres_adjoint_supported(cam.width, cam.height, feats.shape[0], feats.shape[1],
+                                                                  self.d, 1 if lowres_mode == "nearest" else 0):
+            adjoint = False  # window too large for the adjoint kernel: fused upsample + the full-resolution kernel
+        overlap = fp is not None and self.overlap_pack
         if overlap and self._side is None:
-            # The feature re-layout (a 69k-CTA, HBM-bound grid) depends only on F, the geometry pipeline
-            # (a dozen small kernels) only on the camera: run them concurrently.  The geometry stream gets
-            # the higher priority, otherwise its small grids queue behind the big one and nothing overlaps.
+            # The feature re-layout (a 69k-CTA, HBM-bound grid; for the adjoint path the 39 us bf16 copy of the low-res
+            # map) depends only on F, the geometry pipeline (a dozen small kernels) only on the camera: run them
+            # concurrently.  The geometry stream gets the higher priority, otherwise its small grids queue behind the
+            # big one and nothing overlaps.
             self._side = torch.cuda.Stream(self.device, priority=0)
             self._main = torch.cuda.Stream(self.device, priority=-1)
         main = self._main if overlap else cur
         if overlap:
             main.wait_stream(cur)
-        if fp is not None and not adjoint:  # re-layout first (own entry point, so the fused kernel can be timed on its own)
+        if fp is not None:  # re-layout first (own entry point, so the fused kernel can be timed on its own)
             side = self._side if overlap else main
             if overlap:
                 side.wait_stream(main)  # previous view's kernel has finished reading fpack; F is ready
             sH, sW, sD = feats.stride()
             with torch.cuda.device(self.device):
-                if lowres_mode is None:
+                if adjoint:
+                    L.check(L.lib().gwbp_pack_lowres_adjoint(feats.data_ptr(), feats.shape[0], feats.shape[1], sH, sW, sD,
+                                                             self.d, fp.data_ptr(), int(side.cuda_stream)),
+                            "gwbp_pack_lowres_adjoint")
+                elif lowres_mode is None:
                     L.check(L.lib().gwbp_pack_features(cam.width, cam.height, feats.data_ptr(), sH, sW, sD, self.d,
                                                        fp.data_ptr(), int(side.cuda_stream)), "gwbp_pack_features")
                 else:
@@ -204,7 +212,8 @@ class BackProjector:
                         "gwbp_pack_features_lowres")
             if overlap:
                 feats.record_stream(side)
-            kernel = (L.KERNEL_TC if kernel == L.KERNEL_AUTO else kernel) | L.KERNEL_FPACK_READY
+            if not adjoint:
+                kernel = (L.KERNEL_TC if kernel == L.KERNEL_AUTO else kernel) | L.KERNEL_FPACK_READY
         with torch.cuda.stream(main):
             view = View(self.scene, cam, self.cap, self._ws, self.tile_cull,
                         supertile=self.supertile and fp is not None and self.kernel != L.KERNEL_SIMT)
@@ -217,7 +226,7 @@ class BackProjector:
             ratio = self.accumulate == "per_view_ratio"
             num, den = (self.num_v, self.den_v) if ratio else (self.num, self.den)
             if adjoint:
-                view.backproject_lowres(feats, lowres_mode == "nearest", num, den, fp, self._stats)
+                view.backproject_lowres(feats, lowres_mode == "nearest", num, den, fp, self._stats, packed=True)
             elif kernel & L.KERNEL_FPACK_READY:
                 view.backproject_packed(self.d, num, den, kernel, fp, self._stats)
             else:

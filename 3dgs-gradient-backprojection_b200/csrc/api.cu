@@ -182,7 +182,11 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
     info->n_entries = cd.super ? (int64_t)totals[2] : info->n_isects;
     prof_mark(kEvCompact, st);
     int dsel = 0;
-    if (int rc = launch_depth_sort(info->n_vis, w, &dsel, st)) return rc;
+    // the per-Gaussian entry counts ride along with the last pass of the depth sort (the counting-bin path gathers its
+    // emission records as well and keeps its own gather kernel)
+    const bool counting = !cd.super && bin_fast_supported(cd.tw * cd.th) && (flags & GWBP_PREPARE_COUNTING_BIN);
+    const int *counts_src = counting ? nullptr : cd.super ? w.spg : w.tiles_per_gauss;
+    if (int rc = launch_depth_sort(info->n_vis, w, &dsel, st, counts_src)) return rc;
     prof_mark(kEvDepthSort, st);
     const unsigned *order = w.dvals[dsel];
     const int n_tiles = cd.tw * cd.th;
@@ -191,16 +195,16 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
         // supertile id while there are <= 256 of them, ranges per supertile in `offsets`
         info->list_kind = 1;
         info->super_w = cd.nsx; info->super_h = nsy;
-        if (int rc = launch_gather_counts(info->n_vis, order, w, false, st, true)) return rc;
         if (int rc = launch_scan_counts(info->n_vis, w, st)) return rc;
         const int kb = n_super <= 256 ? 1 : n_super <= 65536 ? 2 : 4;
         info->tile_key_bytes = kb;
         if (int rc = launch_emit_super(info->n_vis, cd, order, w, cap, kb, st)) return rc;
         int sorted = 0, sbits = 1;
         while ((1 << sbits) < n_super) ++sbits;
-        if (int rc = launch_super_sort(info->n_entries, sbits, w, kb, &sorted, st)) return rc;
+        // <= 256 supertiles: the single pass's bin offsets are the per-supertile ranges
+        if (int rc = launch_super_sort(info->n_entries, sbits, w, kb, &sorted, st, kb == 1 ? n_super : 0)) return rc;
         info->sorted_buf = sorted;
-        const int rc = launch_offsets(info->n_entries, n_super, w.tkeys[sorted], kb == 2, w.offsets, st, kb == 1);
+        const int rc = kb == 1 ? 0 : launch_offsets(info->n_entries, n_super, w.tkeys[sorted], kb == 2, w.offsets, st, false);
         prof_mark(kEvBin, st);
         return rc;
     }
@@ -216,7 +220,6 @@ int gwbp_view_prepare(const gwbp_scene *scene, const gwbp_camera *cam, void *ws,
         return rc;
     }
     // default: emit (tile, index) pairs in depth order, stable radix sort on the <= 13 tile bits, range finding
-    if (int rc = launch_gather_counts(info->n_vis, order, w, false, st)) return rc;
     if (int rc = launch_scan_counts(info->n_vis, w, st)) return rc;
     const bool key16 = n_tiles <= 65536;
     info->tile_key_bytes = key16 ? 2 : 4;
@@ -323,6 +326,16 @@ int gwbp_lowres_adjoint_supported(int32_t width, int32_t height, int32_t src_h, 
     return lr_supported(width, height, src_h, src_w, d, nearest) ? 1 : 0;
 }
 
+int gwbp_pack_lowres_adjoint(const float *S, int32_t src_h, int32_t src_w, int64_t sH, int64_t sW, int64_t sD, int32_t d,
+                             void *fpack, void *stream) {
+    GWBP_REQUIRE(S && fpack, "pack_lowres_adjoint: NULL pointer");
+    GWBP_REQUIRE(src_h >= 1 && src_w >= 1 && tc_supported(d), "pack_lowres_adjoint: bad shape (%d x %d x %d)", src_h, src_w, d);
+    prof_mark(kEvPack0, (cudaStream_t)stream);
+    const int rc = launch_lr_pack(S, src_h, src_w, sH, sW, sD, d, fpack, (cudaStream_t)stream);
+    prof_mark(kEvPack1, (cudaStream_t)stream);
+    return rc;
+}
+
 int gwbp_backproject_view_lowres(const gwbp_scene *scene, const gwbp_camera *cam, const void *ws,
                                  const gwbp_view_info *info, const float *S, int32_t src_h, int32_t src_w, int64_t sH,
                                  int64_t sW, int64_t sD, int32_t nearest, int32_t d, float *num, float *den, void *fpack,
@@ -337,15 +350,21 @@ int gwbp_backproject_view_lowres(const gwbp_scene *scene, const gwbp_camera *cam
     if (int rc = gwbp_workspace_layout(scene->n, cam->width, cam->height, info->cap_isects, &L)) return rc;
     const TileCtx t = tile_ctx(cam, ws, L, info);
     cudaStream_t st = (cudaStream_t)stream;
+    const bool packed = (nearest & GWBP_LOWRES_PACKED) != 0;
+    nearest &= 1;
     if (lr_supported(cam->width, cam->height, src_h, src_w, d, nearest)) {
         // adjoint path: weights down-sampled on the tensor cores, contracted with the low-res map itself
-        prof_mark(kEvPack0, st);
-        prof_mark(kEvPack1, st);
+        if (!packed) {
+            prof_mark(kEvPack0, st);
+            prof_mark(kEvPack1, st);
+        }
         prof_mark(kEvBp0, st);
-        const int rc = launch_backproject_lr(t, S, src_h, src_w, sH, sW, sD, nearest, d, num, den, fpack, (long long *)stats, st);
+        const int rc = launch_backproject_lr(t, S, src_h, src_w, sH, sW, sD, nearest, d, num, den, fpack, packed,
+                                             (long long *)stats, st);
         prof_mark(kEvBp1, st);
         return rc;
     }
+    GWBP_REQUIRE(!packed, "GWBP_LOWRES_PACKED: this geometry is not covered by the adjoint kernel (gwbp_lowres_adjoint_supported)");
     // windows too large for the adjoint kernel (down-sampling or mild up-sampling): fused upsample + re-layout, then the
     // full-resolution contraction
     prof_mark(kEvPack0, st);

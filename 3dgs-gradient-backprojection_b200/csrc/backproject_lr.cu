@@ -777,12 +777,11 @@ size_t lr_scratch_bytes(int sh, int sw, int d) {
     return 2 * ((part + 127) & ~(size_t)127);
 }
 
-int launch_backproject_lr(const TileCtx &t, const float *S, int sh, int sw, int64_t ssh, int64_t ssw, int64_t ssd,
-                          int nearest, int d, float *num, float *den, void *scratch, long long *stats, cudaStream_t st) {
-    const int ntiles = t.tw * t.th;
-    if (ntiles == 0) return 0;
+// bf16 hi/lo copy of the low-res map in the layout the TMA boxes expect (2 x 59 MB at 240 x 240 x 512, ~39 us): depends
+// only on the map, so the host side may run it on a second stream next to the geometry pipeline of the same view
+int launch_lr_pack(const float *S, int sh, int sw, int64_t ssh, int64_t ssw, int64_t ssd, int d, void *scratch,
+                   cudaStream_t st) {
     GWBP_REQUIRE(((uintptr_t)scratch & 127) == 0, "scratch must be 128-byte aligned");
-    GWBP_REQUIRE(((uintptr_t)num & 15) == 0, "num must be 16-byte aligned");
     const int dp = round_up(d, 16), ngp = dp / 8;
     const size_t part = (((size_t)sh * sw * dp * 2) + 127) & ~(size_t)127;
     uint4 *hi = (uint4 *)scratch, *lo = (uint4 *)((uint8_t *)scratch + part);
@@ -790,6 +789,21 @@ int launch_backproject_lr(const TileCtx &t, const float *S, int sh, int sw, int6
     flow_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S, sh, sw, ssh, ssw, ssd, d, ngp, hi, lo);
     count_launches(1);
     GWBP_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_backproject_lr(const TileCtx &t, const float *S, int sh, int sw, int64_t ssh, int64_t ssw, int64_t ssd,
+                          int nearest, int d, float *num, float *den, void *scratch, bool packed, long long *stats,
+                          cudaStream_t st) {
+    const int ntiles = t.tw * t.th;
+    if (ntiles == 0) return 0;
+    GWBP_REQUIRE(((uintptr_t)scratch & 127) == 0, "scratch must be 128-byte aligned");
+    GWBP_REQUIRE(((uintptr_t)num & 15) == 0, "num must be 16-byte aligned");
+    const int dp = round_up(d, 16), ngp = dp / 8;
+    const size_t part = (((size_t)sh * sw * dp * 2) + 127) & ~(size_t)127;
+    uint4 *hi = (uint4 *)scratch, *lo = (uint4 *)((uint8_t *)scratch + part);
+    if (!packed)
+        if (int rc = launch_lr_pack(S, sh, sw, ssh, ssw, ssd, d, scratch, st)) return rc;
 
     EncodeTiledFn enc = encode_tiled_fn();
     GWBP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");

@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const K *__res
 }
 
 // ---- per pass: exclusive scan of the 256 bins ----
-__global__ void __launch_bounds__(kRadixBins) radix_scan_kernel(const unsigned *__restrict__ ghist, unsigned *__restrict__ gofs) {
+// offsets_out (single-pass sorts): the bin offsets ARE the per-list ranges of the sorted array -- offsets_out[d] for
+// d < n_lists, offsets_out[n_lists] = n -- so no range-finding pass over the sorted keys is needed.
+__global__ void __launch_bounds__(kRadixBins) radix_scan_kernel(const unsigned *__restrict__ ghist, unsigned *__restrict__ gofs,
+                                                                int *__restrict__ offsets_out, int n_lists, unsigned n) {
     __shared__ unsigned s_w[kRadixBins / 32];
     const int d = threadIdx.x, lane = d & 31, w = d >> 5;
     const unsigned h = ghist[blockIdx.x * kRadixBins + d];
@@ -83,6 +86,10 @@ __global__ void __launch_bounds__(kRadixBins) radix_scan_kernel(const unsigned *
     unsigned off = incl - h;
     for (int k = 0; k < w; ++k) off += s_w[k];
     gofs[blockIdx.x * kRadixBins + d] = off;
+    if (offsets_out && blockIdx.x == 0) {
+        if (d < n_lists) offsets_out[d] = (int)off;
+        if (d == 0) offsets_out[n_lists] = (int)n;
+    }
 }
 
 // ---- one stable LSD pass ----
@@ -93,7 +100,9 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(const K
                                                                       const V *__restrict__ vin, V *__restrict__ vout,
                                                                       int64_t n, int shift, int nbits,
                                                                       const unsigned *__restrict__ gofs,
-                                                                      unsigned *__restrict__ status) {
+                                                                      unsigned *__restrict__ status,
+                                                                      const int *__restrict__ gather_src,
+                                                                      unsigned *__restrict__ gather_dst) {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     V *s_v = reinterpret_cast<V *>(s_dyn);
     K *s_k = reinterpret_cast<K *>(s_dyn + sizeof(V) * kSortTile);
@@ -212,10 +221,15 @@ __global__ void __launch_bounds__(kSortThreads, 3) radix_onesweep_kernel(const K
         if (p < nv) {
             const K kk = s_k[p];
             const unsigned dst = s_gbase[digit_of(kk, shift, mask)] + (unsigned)p;
+            const V vv = s_v[p];
             kout[dst] = kk;
-            vout[dst] = s_v[p];
+            vout[dst] = vv;
+            // last pass of the depth sort: the per-Gaussian entry counts follow their Gaussian into depth order (input
+            // of the scan that positions the emission) instead of a separate gather kernel
+            if (gather_src) gather_dst[dst] = (unsigned)gather_src[(size_t)vv];
         }
     }
+    if (gather_src && tile == 0 && tid == 0) gather_dst[n] = 0u;  // terminator: the scan runs over n + 1 counters
 }
 
 struct SortTmp {
@@ -229,9 +243,14 @@ size_t sort_tmp_need(int64_t n, int passes) {
 }
 
 template <typename K, typename V>
-int sort_pairs(K *k0, K *k1, V *v0, V *v1, int64_t n, int bits, WsDev ws, int *sorted_buf, cudaStream_t st) {
+int sort_pairs(K *k0, K *k1, V *v0, V *v1, int64_t n, int bits, WsDev ws, int *sorted_buf, cudaStream_t st,
+               const int *gather_src = nullptr, unsigned *gather_dst = nullptr, int *offsets_out = nullptr, int n_lists = 0) {
     *sorted_buf = 0;
-    if (n == 0 || bits <= 0) return 0;
+    if (n == 0 || bits <= 0) {
+        if (gather_src) GWBP_CUDA_OK(cudaMemsetAsync(gather_dst, 0, sizeof(unsigned), st));
+        if (offsets_out) GWBP_CUDA_OK(cudaMemsetAsync(offsets_out, 0, sizeof(int) * (size_t)(n_lists + 1), st));
+        return 0;
+    }
     GWBP_REQUIRE(n < (1ll << 30), "radix sort: %lld keys exceed the 2^30 limit of the 30-bit chain counters", (long long)n);
     GWBP_REQUIRE(bits <= (int)(8 * sizeof(K)) && bits <= kMaxPasses * kRadixBits, "radix sort: bad key width %d", bits);
     const int passes = (bits + kRadixBits - 1) / kRadixBits;
@@ -242,7 +261,8 @@ int sort_pairs(K *k0, K *k1, V *v0, V *v1, int64_t n, int bits, WsDev ws, int *s
     GWBP_CUDA_OK(cudaMemsetAsync(ws.sort_tmp, 0, need, st));  // histograms + every pass's status words
     const unsigned hist_blocks = (unsigned)min((long long)tiles, (long long)num_sms() * 4);
     radix_hist_kernel<K><<<hist_blocks, kSortThreads, 0, st>>>(k0, n, passes, bits, ghist);
-    radix_scan_kernel<<<passes, kRadixBins, 0, st>>>(ghist, gofs);
+    GWBP_REQUIRE(offsets_out == nullptr || (passes == 1 && n_lists <= kRadixBins), "list offsets need a single-pass sort");
+    radix_scan_kernel<<<passes, kRadixBins, 0, st>>>(ghist, gofs, offsets_out, n_lists, (unsigned)n);
     constexpr int smem = (int)(sizeof(K) + sizeof(V)) * kSortTile;
     int look = 16;  // predecessors per look-back step
 #ifdef GWBP_EXPERIMENTS
@@ -260,8 +280,10 @@ int sort_pairs(K *k0, K *k1, V *v0, V *v1, int64_t n, int bits, WsDev ws, int *s
         }
         for (int p = 0; p < passes; ++p) {
             const int nb = bits - p * kRadixBits < kRadixBits ? bits - p * kRadixBits : kRadixBits;
+            const bool lastp = p == passes - 1;
             kern<<<tiles, kSortThreads, smem, st>>>(kb[p & 1], kb[(p + 1) & 1], vb[p & 1], vb[(p + 1) & 1], n, p * kRadixBits, nb,
-                                                    gofs + p * kRadixBins, status + (size_t)p * tiles * kRadixBins);
+                                                    gofs + p * kRadixBins, status + (size_t)p * tiles * kRadixBins,
+                                                    lastp ? gather_src : nullptr, lastp ? gather_dst : nullptr);
         }
         return 0;
     };
@@ -345,8 +367,10 @@ size_t binning_tmp_bytes(int64_t n, int64_t cap) {
 }
 
 // stage 1: visible Gaussians by depth bits (stable: ties keep ascending packed index)
-int launch_depth_sort(int64_t n_vis, WsDev ws, int *sorted_buf, cudaStream_t st) {
-    return sort_pairs(ws.dkeys[0], ws.dkeys[1], ws.dvals[0], ws.dvals[1], n_vis, 32, ws, sorted_buf, st);
+// counts_src (optional): per-Gaussian entry counts in PACKED order; the last pass also writes them in depth order to
+// ws.cnt2 (+ terminator), which replaces gather_counts_kernel
+int launch_depth_sort(int64_t n_vis, WsDev ws, int *sorted_buf, cudaStream_t st, const int *counts_src) {
+    return sort_pairs(ws.dkeys[0], ws.dkeys[1], ws.dvals[0], ws.dvals[1], n_vis, 32, ws, sorted_buf, st, counts_src, ws.cnt2);
 }
 
 // exclusive offsets of the per-Gaussian tile counts in depth order (n_vis + 1 entries)
@@ -370,10 +394,11 @@ int launch_tile_sort(int64_t n_isects, int tile_bits, WsDev ws, bool key16, int 
 }
 
 // supertile lists: stable sort of the depth-ordered (supertile id, packed index | tile mask << 32) entries by supertile id
-int launch_super_sort(int64_t n_entries, int bits, WsDev ws, int key_bytes, int *sorted_buf, cudaStream_t st) {
+// n_lists > 0 (single-pass sorts only): ws.offsets is filled from the pass's bin offsets, no range-finding kernel needed
+int launch_super_sort(int64_t n_entries, int bits, WsDev ws, int key_bytes, int *sorted_buf, cudaStream_t st, int n_lists) {
     if (key_bytes == 1)
         return sort_pairs((unsigned char *)ws.tkeys[0], (unsigned char *)ws.tkeys[1], ws.svals[0], ws.svals[1], n_entries,
-                          bits, ws, sorted_buf, st);
+                          bits, ws, sorted_buf, st, nullptr, nullptr, n_lists > 0 ? ws.offsets : nullptr, n_lists);
     if (key_bytes == 2)
         return sort_pairs((unsigned short *)ws.tkeys[0], (unsigned short *)ws.tkeys[1], ws.svals[0], ws.svals[1], n_entries,
                           bits, ws, sorted_buf, st);

@@ -121,10 +121,10 @@ int launch_gather_counts(int64_t n_vis, const unsigned *order, WsDev ws, bool ga
 // supertile binning: (supertile id, packed index | tile mask << 32) entries in depth order, stable sort on the id, ranges
 int launch_emit_super(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, int key_bytes,
                       cudaStream_t st);
-int launch_super_sort(int64_t n_entries, int bits, WsDev ws, int key_bytes, int *sorted_buf, cudaStream_t st);
+int launch_super_sort(int64_t n_entries, int bits, WsDev ws, int key_bytes, int *sorted_buf, cudaStream_t st, int n_lists = 0);
 int launch_emit(int64_t n_vis, const CamDev &cam, const unsigned *order, WsDev ws, int64_t cap, bool key16, cudaStream_t st);
 size_t binning_tmp_bytes(int64_t n, int64_t cap);
-int launch_depth_sort(int64_t n_vis, WsDev ws, int *sorted_buf, cudaStream_t st);
+int launch_depth_sort(int64_t n_vis, WsDev ws, int *sorted_buf, cudaStream_t st, const int *counts_src = nullptr);
 int launch_scan_counts(int64_t n_vis, WsDev ws, cudaStream_t st);
 // key16: tile ids are stored as uint16 in the tkeys buffers (tiles <= 65536): 25 % less sort traffic
 int launch_tile_sort(int64_t n_isects, int tile_bits, WsDev ws, bool key16, int *sorted_buf, cudaStream_t st);
@@ -183,8 +183,11 @@ int launch_backproject_tc(const TileCtx &t, const float *F, int64_t sH, int64_t 
 // encoder-resolution maps: down-sampled weights x low-res map, two chained tcgen05 GEMMs (backproject_lr.cu)
 bool lr_supported(int W, int H, int sh, int sw, int d, int nearest);
 size_t lr_scratch_bytes(int sh, int sw, int d);
+int launch_lr_pack(const float *S, int sh, int sw, int64_t ssh, int64_t ssw, int64_t ssd, int d, void *scratch,
+                   cudaStream_t st);
 int launch_backproject_lr(const TileCtx &t, const float *S, int sh, int sw, int64_t ssh, int64_t ssw, int64_t ssd,
-                          int nearest, int d, float *num, float *den, void *scratch, long long *stats, cudaStream_t st);
+                          int nearest, int d, float *num, float *den, void *scratch, bool packed, long long *stats,
+                          cudaStream_t st);
 
 // tcgen05 forward render (render_tc.cu)
 bool render_tc_supported(const float *colors, int64_t cstride, int d);

@@ -221,9 +221,9 @@ class View:
                 "gwbp_backproject_view")
 
     def backproject_lowres(self, feats_low: torch.Tensor, nearest: bool, num: torch.Tensor, den: torch.Tensor,
-                           fpack: torch.Tensor, stats: Optional[torch.Tensor] = None) -> None:
+                           fpack: torch.Tensor, stats: Optional[torch.Tensor] = None, packed: bool = False) -> None:
         """backproject(interpolate(feats_low)) for an encoder-resolution map [h,w,D] (any strides), without the
-        full-resolution map: gwbp_backproject_view_lowres."""
+        full-resolution map: gwbp_backproject_view_lowres.  packed=True: gwbp_pack_lowres_adjoint already filled `fpack`."""
         _require_cuda(feats_low, "feats_low")
         assert feats_low.dtype == torch.float32 and feats_low.dim() == 3
         d = feats_low.shape[2]
@@ -233,7 +233,8 @@ class View:
         with torch.cuda.device(self.scene.device):
             L.check(L.lib().gwbp_backproject_view_lowres(
                 C.byref(self.scene.c), C.byref(self.cam), self.ws.data_ptr(), C.byref(self.info), feats_low.data_ptr(),
-                feats_low.shape[0], feats_low.shape[1], sH, sW, sD, 1 if nearest else 0, d, num.data_ptr(),
+                feats_low.shape[0], feats_low.shape[1], sH, sW, sD, (1 if nearest else 0) | (L.LOWRES_PACKED if packed else 0),
+                d, num.data_ptr(),
                 den.data_ptr(), fpack.data_ptr(), stats.data_ptr() if stats is not None else None,
                 _stream_ptr(self.scene.device)), "gwbp_backproject_view_lowres")
 

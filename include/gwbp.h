@@ -192,7 +192,13 @@ int gwbp_backproject_view(const gwbp_scene *scene, const gwbp_camera *cam_host, 
  * without building F or its packed copy: the weights are down-sampled on the tensor cores (the adjoint of the
  * up-sample) and contracted with the low-res map fetched by TMA (backproject_lr.cu).  `fpack` is scratch of at least
  * gwbp_fpack_bytes(width, height, d) bytes.  Geometries whose per-tile window of S exceeds 8 rows x 8 texels
- * (gwbp_lowres_adjoint_supported() == 0) silently take gwbp_pack_features_lowres + the full-resolution kernel. */
+ * (gwbp_lowres_adjoint_supported() == 0) silently take gwbp_pack_features_lowres + the full-resolution kernel.
+ * The bf16 copy of S the TMA boxes read (2 x 59 MB at 240 x 240 x 512) depends only on S: gwbp_pack_lowres_adjoint writes
+ * it into `fpack` on its own (e.g. on a second stream next to gwbp_view_prepare of the same view); pass
+ * `nearest | GWBP_LOWRES_PACKED` to gwbp_backproject_view_lowres then (adjoint-supported geometries only). */
+#define GWBP_LOWRES_PACKED 2
+int gwbp_pack_lowres_adjoint(const float *S, int32_t src_h, int32_t src_w, int64_t sH, int64_t sW, int64_t sD, int32_t d,
+                             void *fpack, void *stream);
 int gwbp_lowres_adjoint_supported(int32_t width, int32_t height, int32_t src_h, int32_t src_w, int32_t d, int32_t nearest);
 int gwbp_backproject_view_lowres(const gwbp_scene *scene, const gwbp_camera *cam_host, const void *ws,
                                  const gwbp_view_info *info_host, const float *S, int32_t src_h, int32_t src_w, int64_t sH,
