@@ -278,13 +278,24 @@ class BackProjector:
             return _finalize(self.num, torch.ones_like(self.den), out)
         return _finalize(self.num, self.den, out)
 
-    def save(self, path: str, prune: bool = True, with_index: bool = True) -> torch.Tensor:
+    def save(self, path: str, prune: bool = True, with_index: bool = True,
+             keep: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Write the feature field the way the reference does (backproject.py:330): ONE float32 tensor
         [N_pruned, D] whose rows follow `prune_by_gradients`' mask (utils.py:257-268), so segment.py can
         `torch.load` it unchanged.  with_index additionally writes `<path>.kept.pt` (the kept Gaussian
-        indices) so consumers need not re-derive the mask."""
+        indices) so consumers need not re-derive the mask.
+
+        The mask is `den > 0` over the views ADDED TO THIS OBJECT: it equals prune_by_gradients' mask only if every
+        COLMAP image that function renders was added (the reference prunes first and back-projects the pruned set; a
+        zero-weight Gaussian that terminates a pixel here is absent there, which moves later weights by a threshold
+        flip at most -- INTEGRATION.md).  Pass `keep` [N] bool (e.g. the mask prune_by_gradients returned for these
+        splats) to make the rows align with an externally pruned checkpoint regardless of the views added."""
         feats = self.finalize()
-        keep = self.prune_mask() if prune else torch.ones_like(self.den, dtype=torch.bool)
+        if keep is not None:
+            keep = torch.as_tensor(keep, device=self.device).to(torch.bool).reshape(-1)
+            assert keep.numel() == self.scene.n, f"keep must have {self.scene.n} entries, got {keep.numel()}"
+        else:
+            keep = self.prune_mask() if prune else torch.ones_like(self.den, dtype=torch.bool)
         out = feats[keep].contiguous()
         torch.save(out, path)
         if with_index:

@@ -13,8 +13,9 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --c
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/r02_final_launches_lowres.csv $B --features lowres > gpurun_out/b1.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:bp_tc_kernel -s 4 -c 1 -f -o gpurun_out/r02_bp_tc_full $B > gpurun_out/b2.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:bp_lr_kernel -s 4 -c 1 -f -o gpurun_out/r02_bp_lr_full $B --features lowres > gpurun_out/b2.log 2>&1
-timeout 400 ncu --set full --clock-control none -k regex:project_kernel -s 4 -c 1 -f -o gpurun_out/r02_project_full $B > gpurun_out/b2.log 2>&1
+timeout 400 ncu --set full --clock-control none -k regex:project_pack_kernel -s 4 -c 1 -f -o gpurun_out/r02_project_full $B > gpurun_out/b2.log 2>&1
 timeout 400 ncu --set full --clock-control none -k regex:fpack_planar -s 4 -c 1 -f -o gpurun_out/r02_fpack_full $B > gpurun_out/b2.log 2>&1
+timeout 400 ncu --set full --clock-control none -k regex:radix_onesweep_kernel -s 21 -c 1 -f -o gpurun_out/r02_radix_onesweep_full $B --features lowres > gpurun_out/b2.log 2>&1
 timeout 300 python tools/parity_report.py > gpurun_out/r02_parity.txt 2>&1
 for f in default C C16 M G_lowres M_lowres; do python - <<PY
 import json
