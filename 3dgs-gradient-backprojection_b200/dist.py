@@ -131,16 +131,18 @@ class PeerExchange:
                 if r == self.rank:
                     self._num_ptrs[r], self._den_ptrs[r] = num.data_ptr(), den.data_ptr()
                     continue
-                ptrs = []
+                ptrs, opened = [], {}  # num and den may live in ONE allocation of the peer: map it once
                 for hbytes, off in handles:
-                    base = C.c_void_p()
-                    rc = lib.gwbp_ipc_open(hbytes, C.byref(base))
-                    if rc != 0:
-                        failed = failed or f"gwbp_ipc_open(rank {r}): {L.last_error()}"
-                        ptrs.append(0)
-                        continue
-                    self._bases.append(base.value)
-                    ptrs.append(base.value + off)
+                    if hbytes not in opened:
+                        base = C.c_void_p()
+                        rc = lib.gwbp_ipc_open(hbytes, C.byref(base))
+                        if rc != 0:
+                            failed = failed or f"gwbp_ipc_open(rank {r}): {L.last_error()}"
+                            ptrs.append(0)
+                            continue
+                        self._bases.append(base.value)
+                        opened[hbytes] = base.value
+                    ptrs.append(opened[hbytes] + off)
                 self._num_ptrs[r], self._den_ptrs[r] = ptrs
         flags = [None] * self.world
         dist.all_gather_object(flags, failed, group=group)

@@ -749,6 +749,13 @@ def test_rasterization_backgrounds_depth_modes_and_sh(gwbp, coracle, noracle, ca
     assert loaded.shape == (int(bp.prune_mask().sum()), 8) and loaded.dtype == torch.float32
     assert torch.equal(loaded.cpu(), saved.cpu()) and kept.numel() == loaded.shape[0]
     assert torch.allclose(loaded.norm(dim=1), torch.ones(loaded.shape[0], device=loaded.device), atol=1e-4)
+    # rows for an externally pruned checkpoint (the mask prune_by_gradients returned, utils.py:257-268)
+    ext = torch.zeros(sc.n, dtype=torch.bool)
+    ext[::3] = True
+    saved_ext = bp.save(str(tmp_path / "features_ext.pt"), keep=ext)
+    assert saved_ext.shape == (int(ext.sum()), 8)
+    assert torch.equal(torch.load(str(tmp_path / "features_ext.pt.kept.pt")), torch.nonzero(ext).flatten())
+    assert torch.equal(saved_ext.cpu(), bp.finalize()[ext.cuda()].cpu())
 
 
 def test_probe_pixel_render_and_click_prompt(gwbp, coracle, noracle, case):
