@@ -13,7 +13,7 @@
 // L2-resident low-resolution map: ~1/5 of the tensor work of bp_tc_kernel, 1/4 of its shared-memory operand traffic,
 // and the weight block W is consumed by one short sweep, so the ALU warps never wait for a second column-chunk sweep.
 //
-// Persistent CTA, 1 per SM, 672 threads, warp-specialised:
+// Persistent CTA, 1 per SM, 736 threads, warp-specialised:
 //   warps 0-7   ALU       : exactly bp_tc_kernel's weight generation (thread = pixel, sequential T, bf16 hi/lo W^T)
 //   warps 8-11  epilogue  : exactly bp_tc_kernel's (tcgen05.ld -> smem transpose -> red.global.add.v4.f32 rows)
 //   warps 12-15 converter : tcgen05.ld W' (fp32, lane = Gaussian) -> bf16 hi/lo -> A operand of GEMM2 in smem

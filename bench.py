@@ -374,8 +374,9 @@ def run_ours(args, cfg):
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e["lowres_variant"] = {"value": world * k2 / float(tt.item()), "unit": UNIT,
                                      "h2d_bytes_per_step": d * enc * enc * 4 + 100, "d2h_bytes_per_step": d2h,
-                                     "note": f"host hands over the {enc}x{enc} encoder map; bilinear upsample fused "
-                                             "into the feature re-layout kernel (SURVEY 8f row 3)"}
+                                     "note": f"host hands over the {enc}x{enc} encoder map (what the reference has before "
+                                             "F.interpolate, backproject.py:108-112); back-projected against that map "
+                                             "directly by the adjoint kernel, no [H,W,D] tensor (SURVEY 8f row 3)"}
         except Exception as ex:  # never let the extra measurement break the contract line
             e2e["lowres_variant"] = {"error": str(ex)[:200]}
 
@@ -443,19 +444,19 @@ def run_ours(args, cfg):
         if stage_ms is not None:
             adjoint = args.features == "lowres" and bool(gwbp._lib.lib().gwbp_lowres_adjoint_supported(W, H, enc, enc, d, 0))
             low_bytes = (enc * enc * d * 4.0) if args.features == "lowres" else float(fmap_bytes)
-            sb = {"project": 44.0 * n_g + 40.0 * n_vis,                  # SURVEY 8d "Project"
-                  "count_scan_and_readback": 16.0 * n_g,                 # 8-byte counters read + prefix written
-                  "compact": 16.0 * n_g + 96.0 * n_vis,                  # counters + records in, packed records + sort input out
+            sb = {"project": 44.0 * n_g + 40.0 * n_vis,                  # SURVEY 8d "Project" (projection + tile test + ordered compaction: one kernel)
+                  "count_scan_and_readback": 0.0,                        # host read-back of the view's totals (the one sync per view)
+                  "compact": 0.0,                                        # fused into project_pack_kernel: nothing runs here any more
                   "depth_sort": 16.0 * n_vis,                            # one logical pass over (key, value) pairs
                   "tile_binning": 24.0 * n_is + 4.0 * tiles,             # SURVEY 8d "Bin+sort": 12 I written + 12 I read
-                  # map read + packed operand written (adjoint low-res path: the 2 x 118 MB pack is part of "backproject")
-                  "feature_relayout": 0.0 if adjoint else low_bytes + float(fpack_dev_bytes),
+                  # map read + packed operand written (adjoint low-res path: fp32 map read + 2 x bf16 copy written)
+                  "feature_relayout": 2.0 * low_bytes if adjoint else low_bytes + float(fpack_dev_bytes),
                   "backproject": algo_bytes}
             stages = []
             for name, ms in zip(gwbp._lib.PROFILE_STAGES, stage_ms):
-                ach = sb[name] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+                ach = sb[name] / (ms * 1e-3) / 1e9 if ms > 0 and sb[name] > 0 else None
                 stages.append({"stage": name, "ms": ms, "algorithmic_bytes": sb[name], "achieved_gbs": ach,
-                               "frac": ach / hbm})
+                               "frac": ach / hbm if ach is not None else None})
             stages.append({"stage": "sum", "ms": sum(stage_ms), "note": f"{args.stage_views} views, CUDA events at the stage "
                            "boundaries inside the library (one sync per view to read them)"})
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
@@ -475,7 +476,7 @@ def run_ours(args, cfg):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"config {args.config}" + (" --features lowres (encoder-resolution maps, fused upsample)"
+                "config": {"workload": f"config {args.config}" + (" --features lowres (encoder-resolution maps, adjoint kernel)"
                                                                   if args.features == "lowres" else ""),
                            **cfg, "kernel": args.kernel, "features": args.features,
                            "l2": f"{pool_n} feature maps of {fmap_bytes / 1e9:.2f} GB cycled: every view's input "
@@ -616,7 +617,7 @@ def main():
     ap.add_argument("--pool", type=int, default=8, help="distinct resident feature maps cycled through")
     ap.add_argument("--features", default="full", choices=["full", "lowres"],
                     help="full: [H,W,D] map resident in HBM (the BASELINE metric); lowres: encoder-resolution map, "
-                         "bilinear upsample fused into the feature re-layout (not the headline)")
+                         "back-projected directly by the adjoint kernel bp_lr_kernel (not the headline)")
     ap.add_argument("--collective", default="auto", choices=["auto", "peer", "allreduce", "reduce_scatter"],
                     help="closing exchange of (num, den) for N > 1: peer = sparse reduce-scatter over NVLink peer memory "
                          "fused with the finalise, one hand-written kernel per rank (auto: peer when CUDA IPC mappings "

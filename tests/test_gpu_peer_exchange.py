@@ -44,21 +44,33 @@ def _worker(rank, world, port, n, d, out):
     for v in range(n_views):
         ref.add_view(vm[v], K, W, H, feats[v])
     f_ref, keep_ref = ref.finalize(), ref.prune_mask()
-    ok = True
+    failed = []
+
+    def check(name, cond):
+        if not bool(cond):
+            failed.append(name)
+
+    def rows_close(a, b, scale, tol):
+        """max_j |a - b| <= tol * scale per row: the two jobs add the same fp32 terms in different orders (per-rank
+        partial sums, atomics), so the error bound is relative to the size of the TERMS (the row's den, features being
+        unit vectors), not to the possibly cancelled sum."""
+        return float(((a - b).abs().amax(dim=1) / scale.clamp_min(1e-30)).max()) <= tol
+
     f, keep, lo, hi = gwbp.dist.finalize_sharded(bp, exchange="peer")
-    ok = ok and (lo, hi) == gwbp.dist.shard_rows(n, rank, world) and f.shape == (hi - lo, d)
-    ok = ok and bool(torch.equal(keep, keep_ref[lo:hi]))
-    ok = ok and bool(torch.allclose(f, f_ref[lo:hi], atol=2e-6, rtol=1e-5))
-    ok = ok and float(f[~keep].abs().max() if (~keep).any() else 0.0) == 0.0  # rows nobody touched are exactly zero
-    # raw sums too, twice (the exchange is repeatable: the accumulators are left untouched)
+    check("row range", (lo, hi) == gwbp.dist.shard_rows(n, rank, world) and f.shape == (hi - lo, d))
+    check("prune mask", torch.equal(keep, keep_ref[lo:hi]))
+    seen = ref.den[lo:hi] > 1e-6
+    rel = (f[seen] - f_ref[lo:hi][seen]).norm(dim=1) / f_ref[lo:hi][seen].norm(dim=1).clamp_min(1e-12)
+    check(f"feature rows rel-err {float(rel.max()) if rel.numel() else 0:.2e}", rel.numel() == 0 or float(rel.max()) <= 1e-4)
+    check("untouched rows are zero", float(f[~keep].abs().max() if (~keep).any() else 0.0) == 0.0)
+    # raw sums too, twice (the exchange is repeatable and deterministic: rank-ordered sums, accumulators left untouched)
     px = gwbp.dist.peer_exchange_for(bp)
-    for _ in range(2):
+    for rep in range(2):
         f2, den2, lo2, hi2, num2 = px.reduce_finalize(want_num=True)
-        ok = ok and bool(torch.equal(f2, f))
-        ok = ok and bool(torch.allclose(num2, ref.num[lo:hi], atol=1e-6, rtol=1e-5))
-        ok = ok and bool(torch.allclose(den2, ref.den[lo:hi], atol=1e-9, rtol=1e-5))
-    # touched fraction is what makes the exchange sparse: report it
-    out[rank] = (bool(ok), float((bp.den > gwbp.DEN_EPS).float().mean()))
+        check(f"repeat {rep}: bit-identical features", torch.equal(f2, f))
+        check(f"repeat {rep}: num", rows_close(num2, ref.num[lo:hi], ref.den[lo:hi], 2e-6))
+        check(f"repeat {rep}: den", torch.allclose(den2, ref.den[lo:hi], atol=1e-12, rtol=2e-6))
+    out[rank] = (failed, float((bp.den > gwbp.DEN_EPS).float().mean()))
     px.close()
     dist.destroy_process_group()
 
@@ -74,5 +86,5 @@ def test_peer_exchange_two_processes_one_gpu(n, d):
         [p.join(300) for p in procs]
         assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
         res = dict(out)
-        assert res[0][0] and res[1][0], res
+        assert res[0][0] == [] and res[1][0] == [], res
         print(f"[peer exchange] rows touched per rank: {res[0][1]:.3f}, {res[1][1]:.3f}")

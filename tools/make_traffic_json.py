@@ -14,9 +14,12 @@ def grab(path):
         m = re.search(r"^\s*" + re.escape(key) + r"\s+([0-9.]+)\s+(\S+)", txt, re.M)
         v, unit = float(m.group(1)), m.group(2)
         return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(unit, 1.0)
+    def val_ms(key):
+        m = re.search(r"^\s*" + re.escape(key) + r"\s+([0-9.]+)\s+(\S+)", txt, re.M)
+        return float(m.group(1)) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(m.group(2), 1.0)
     return {"traffic": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
             "tensor_pipe_pct": float(re.search(r"sm__pipe_tensor_cycles_active\S*\s+([0-9.]+)", txt).group(1)),
-            "kernel_us_under_ncu": float(re.search(r"gpu__time_duration.sum\s+([0-9.]+)", txt).group(1)), "file": "profiles/" + path}
+            "kernel_ms_under_ncu": val_ms("gpu__time_duration.sum"), "file": "profiles/" + path}
 
 
 out = {"source_sha": bench._source_sha(), "G:full:tc": grab("r02_bp_tc_full_summary.txt"), "G:lowres:tc": grab("r02_bp_lr_full_summary.txt")}
