@@ -116,7 +116,8 @@ def make_feature_map_np(view: int, d: int, height: int, width: int, seed: int = 
     return np.transpose(planar, (1, 2, 0))  # strided view, NOT contiguous
 
 
-def make_feature_map_torch(view: int, d: int, height: int, width: int, device, seed: int = 0, enc_res: int = 240):
+def make_feature_map_torch(view: int, d: int, height: int, width: int, device, seed: int = 0, enc_res: int = 240,
+                           mode: str = "bilinear"):
     """Benchmark-scale feature map built on `device` with torch (2.2 GB at 1297x840x512 —
     too big to ship from the host every time).  LSeg-shaped: encoder-resolution randn,
     L2-normalised over channels, bilinear-upsampled, exposed as the permuted view."""
@@ -126,7 +127,7 @@ def make_feature_map_torch(view: int, d: int, height: int, width: int, device, s
     g.manual_seed(seed * 1000003 + view * 101 + d)
     low = torch.randn(1, d, enc_res, enc_res, generator=g, device=device, dtype=torch.float32)
     low = torch.nn.functional.normalize(low, dim=1)
-    up = torch.nn.functional.interpolate(low, size=(height, width), mode="bilinear")[0]
+    up = torch.nn.functional.interpolate(low, size=(height, width), mode=mode)[0]
     return up.permute(1, 2, 0)
 
 
@@ -144,4 +145,6 @@ CONFIGS = {
     "C": dict(n=5_800_000, views=185, width=1297, height=840, d=64),
     "C16": dict(n=5_800_000, views=185, width=1297, height=840, d=16),
     "M": dict(n=6_000_000, views=1000, width=1920, height=1080, d=768),
+    # the reference's second model family (backproject.py:214-289): DINOv2 1024-d tokens, 64 x 64, nearest up-sampling
+    "D": dict(n=5_800_000, views=185, width=1297, height=840, d=1024, enc=64, mode="nearest"),
 }

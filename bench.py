@@ -237,9 +237,11 @@ def run_ours(args, cfg):
                             collect_stats=True)
     if args.overlap_pack >= 0:
         bp.overlap_pack = bool(args.overlap_pack)
-    enc = 240 if min(W, H) >= 480 else 24
+    enc = cfg.get("enc", 240 if min(W, H) >= 480 else 24)  # encoder resolution (LSeg 240 x 240; config D: 64 x 64 DINOv2 tokens)
+    lmode = cfg.get("mode", "bilinear")                    # how the reference up-samples it (backproject.py:110-112 / :245-249)
+    nearest = 1 if lmode == "nearest" else 0
     pool_n = max(1, min(V, args.pool))
-    pool = [S.make_feature_map_torch(v, d, H, W, dev, 0, enc_res=enc) for v in range(pool_n)]
+    pool = [S.make_feature_map_torch(v, d, H, W, dev, 0, enc_res=enc, mode=lmode) for v in range(pool_n)]
     fmap_bytes = H * W * d * 4
     fpack_dev_bytes = gwbp.fpack_bytes(W, H, d)
     my_view = lambda i: (rank + i * world) % V  # noqa: E731
@@ -252,7 +254,7 @@ def run_ours(args, cfg):
     def step(i):
         v = my_view(i)
         if low_pool is not None:
-            return bp.add_view_lowres(vm[v], K, W, H, low_pool[v % pool_n], mode="bilinear")
+            return bp.add_view_lowres(vm[v], K, W, H, low_pool[v % pool_n], mode=lmode)
         return bp.add_view(vm[v], K, W, H, pool[v % pool_n])
 
     def barrier():
@@ -357,14 +359,14 @@ def run_ours(args, cfg):
         try:
             hlow = [torch.nn.functional.normalize(torch.randn(d, enc, enc), dim=0).pin_memory() for _ in range(2)]
             for i in range(2):
-                bp.add_view_host(vm[my_view(i)], K, W, H, hlow[i % 2], lowres_mode="bilinear")
+                bp.add_view_host(vm[my_view(i)], K, W, H, hlow[i % 2], lowres_mode=lmode)
             bp.flush()
             torch.cuda.synchronize(dev)
             bp.reset()
             barrier()
             t0 = time.perf_counter()
             for i in range(k2):
-                bp.add_view_host(vm[my_view(i)], K, W, H, hlow[i % 2], lowres_mode="bilinear")
+                bp.add_view_host(vm[my_view(i)], K, W, H, hlow[i % 2], lowres_mode=lmode)
                 res = bp._stats.cpu()
             bp.flush()
             res = bp._stats.cpu()
@@ -413,7 +415,7 @@ def run_ours(args, cfg):
         # algorithmic bytes of the fused kernel: walked entries x (4 B id + 32 B record)
         # + the feature map once + one (D+1)-float accumulator update per non-zero row
         lr_adjoint = args.features == "lowres" and args.kernel != "simt" and bool(
-            gwbp._lib.lib().gwbp_lowres_adjoint_supported(W, H, enc, enc, d, 0))
+            gwbp._lib.lib().gwbp_lowres_adjoint_supported(W, H, enc, enc, d, nearest))
         in_bytes = float(enc * enc * d * 4) if args.features == "lowres" else float(fmap_bytes)  # the map as supplied
         algo_bytes = walked * 36.0 + (in_bytes if lr_adjoint else fmap_bytes) + rows * (d + 1) * 4.0
         achieved = algo_bytes / (ms_kernel * 1e-3) / 1e9 if ms_kernel > 0 else 0.0
@@ -442,7 +444,7 @@ def run_ours(args, cfg):
         view["frac"] = view["achieved"] / hbm
         stages = None
         if stage_ms is not None:
-            adjoint = args.features == "lowres" and bool(gwbp._lib.lib().gwbp_lowres_adjoint_supported(W, H, enc, enc, d, 0))
+            adjoint = args.features == "lowres" and bool(gwbp._lib.lib().gwbp_lowres_adjoint_supported(W, H, enc, enc, d, nearest))
             low_bytes = (enc * enc * d * 4.0) if args.features == "lowres" else float(fmap_bytes)
             sb = {"project": 44.0 * n_g + 40.0 * n_vis,                  # SURVEY 8d "Project" (projection + tile test + ordered compaction: one kernel)
                   "count_scan_and_readback": 0.0,                        # host read-back of the view's totals (the one sync per view)
