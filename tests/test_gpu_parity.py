@@ -236,6 +236,21 @@ def test_encoder_resolution_maps_against_the_oracle(gwbp, coracle, noracle, mode
     for name, bp in jobs.items():
         _check_features(bp, num_o, den_o, noracle, margin, f" lowres {mode} D={d} {name}")
         assert bp.stats() == jobs["materialised"].stats(), name  # same weights, same rows
+    # the single C-ABI call without the separate pack (gwbp_backproject_view_lowres packs the map itself, or takes the
+    # fused-upsample fallback when the geometry is not covered): same accumulators as the two-call path above
+    from gwbp.engine import View, make_camera, fpack_bytes
+    bp1 = gwbp.BackProjector(*args, kernel="tc")
+    fp = torch.empty(fpack_bytes(W, H, d), dtype=torch.uint8, device="cuda")
+    for v in range(2):
+        planar_low = _dev(np.ascontiguousarray(np.transpose(lows[v], (2, 0, 1))))
+        view = View(bp1.scene, make_camera(vm[v], K, W, H), tile_cull=True, supertile=True)
+        view.backproject_lowres(planar_low.permute(1, 2, 0), mode == "nearest", bp1.num, bp1.den, fp)
+    ref = jobs["adjoint"] if adjoint else jobs["upsample"]
+    assert torch.equal(bp1.den > 1e-12, ref.den > 1e-12)
+    assert torch.allclose(bp1.den, ref.den, rtol=2e-6, atol=1e-12)
+    seen = ref.den > 1e-6
+    err = (bp1.num[seen] - ref.num[seen]).abs().amax(dim=1) / ref.den[seen]
+    assert float(err.max()) < 2e-6, float(err.max())
 
 
 def test_tile_culling_does_not_change_the_accumulators(gwbp, case):
@@ -255,7 +270,8 @@ def test_tile_culling_does_not_change_the_accumulators(gwbp, case):
 
 
 @pytest.mark.parametrize("cull", [False, True])
-@pytest.mark.parametrize("scale_mul,W,H", [(1.0, 256, 256), (1.0, 422, 274), (6.0, 330, 230), (25.0, 211, 137)])
+@pytest.mark.parametrize("scale_mul,W,H", [(1.0, 256, 256), (1.0, 422, 274), (6.0, 330, 230), (25.0, 211, 137),
+                                           (3.0, 2304, 1296)])  # 18 x 21 = 378 supertiles: 16-bit ids, two radix passes
 def test_supertile_lists_give_the_per_tile_results(gwbp, scale_mul, W, H, cull):
     """BackProjector bins views for the tcgen05 kernels into 8 x 4-tile supertiles (one entry per Gaussian and
     supertile + a 32-bit tile mask, filtered per tile by the kernels' lister warp).  Same Gaussians in the same order as
@@ -267,7 +283,11 @@ def test_supertile_lists_give_the_per_tile_results(gwbp, scale_mul, W, H, cull):
     scales = (sc.scales * scale_mul).astype(np.float32)
     vm, K = S.make_cameras(3, W, H, 3)
     d = 32
-    feats = [_feat_dev(S.make_feature_map_np(v, d, H, W, 3)) for v in range(3)]
+    if W * H > 500_000:  # large image: generate on the device (the numpy up-sampler would need GBs of host temporaries)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        feats = [torch.rand(d, H, W, generator=g, device="cuda").permute(1, 2, 0) for _ in range(3)]
+    else:
+        feats = [_feat_dev(S.make_feature_map_np(v, d, H, W, 3)) for v in range(3)]
     out = []
     for sup in (False, True):
         bp = gwbp.BackProjector(_dev(sc.means), _dev(sc.quats), _dev(scales), _dev(sc.opacities), d, kernel="tc",
