@@ -283,6 +283,16 @@ __global__ void __launch_bounds__(kThreads, 1) bp_tc_kernel(const TcArgs a) {
                 } else {
 #pragma unroll 2
                     for (int j = 0; j < MB / 16; ++j) {
+                        // every pixel of this warp finished INSIDE this batch (typically the tile's last one): the rest
+                        // of its slab is zero, written without evaluating a single pair
+                        if (j > 0 && __all_sync(0xffffffffu, done)) {
+                            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                            for (int jj = 2 * j; jj < MB / 8; ++jj) {
+                                *reinterpret_cast<uint4 *>(smem + Smem::w_hi + jj * A_SBO + wslab) = z;
+                                *reinterpret_cast<uint4 *>(smem + Smem::w_lo + jj * A_SBO + wslab) = z;
+                            }
+                            break;
+                        }
                         // 16 Gaussians per step: alpha evaluation is independent across Gaussians (ILP);
                         // only the T update is a serial chain
                         float w[16];
