@@ -344,9 +344,10 @@ __global__ void __launch_bounds__(kThreads, 1) bp_lr_kernel(const LrArgs a, cons
                 } else {
 #pragma unroll 2
                     for (int j = 0; j < MB / 16; ++j) {
-                        // every pixel of this warp finished INSIDE this batch (typically the tile's last one): the rest
-                        // of its slab is zero, written without evaluating a single pair
-                        if (j > 0 && __all_sync(0xffffffffu, done)) {
+                        // every pixel of this warp finished INSIDE this batch (typically the tile's last one), or the
+                        // batch holds no more than 16 j Gaussians (the tail of a list that ends before the tile
+                        // saturates): the rest of the slab is zero, written without evaluating a single pair
+                        if (j > 0 && (16 * j >= n_cur || __all_sync(0xffffffffu, done))) {
                             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
                             for (int jj = 2 * j; jj < MB / 8; ++jj) {
                                 *reinterpret_cast<uint4 *>(smem + Smem::w_hi + jj * A_SBO + wslab) = z;
